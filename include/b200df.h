@@ -1,0 +1,179 @@
+/*
+ * b200df.h -- C ABI of libb200df.so: the Blackwell (sm_100a) execution path for rust-dataframe's
+ * per-RecordBatch compute.  Plain pointers and sizes only; no C++/torch/arrow types cross this boundary.
+ *
+ * Reference = nevi-me/rust-dataframe @ a8310afd (paths relative to the reference root).  The reference
+ * has no FFI today; the seam is the set of Rust functions below, whose BODIES become one call each
+ * (INTEGRATION.md shows the Rust binding).  One call carries ALL chunks of the column(s)
+ * (Vec<&PrimitiveArray<T>>, one entry per RecordBatch -- src/table.rs:114-123), so batching, streams and
+ * device memory are owned by the library.
+ *
+ *   bdf_binary      replaces the bodies of ScalarFunctions::{add,subtract,multiply,par_multiply,divide}
+ *                   (src/functions/scalar.rs:16-103 -> arrow::compute::{add,subtract,multiply,divide}) and
+ *                   atan2/hypot/log (scalar.rs:148,274,291 -> math_op scalar.rs:499-523)
+ *   bdf_unary       replaces ScalarFunctions::{abs,sin,cos,tan,acos,...} (scalar.rs:106-457 -> scalar_op
+ *                   scalar.rs:525-540)
+ *   bdf_cast        replaces the arrow::compute::cast call of Function::Cast (src/evaluation.rs:296-315)
+ *   bdf_aggregate   replaces AggregateFunctions::{sum,min,max,count} (src/functions/aggregate.rs:12-93)
+ *   bdf_avg         replaces AggregateFunctions::avg (aggregate.rs:32-65)
+ *   bdf_*_dev       the same operators on device-resident columns, so a chain of Calculations
+ *                   (src/evaluation.rs:66-96 evaluates one after another) uploads once and downloads once.
+ *
+ * Error convention: every entry returns a bdf_status; BDF_OK == 0.  bdf_last_error() gives a
+ * thread-local message.  No exception or abort crosses the ABI.  Mapping to the reference's errors:
+ *   BDF_LENGTH_MISMATCH -> ArrowError::ComputeError("Cannot perform math operation on arrays of different length")
+ *                          (text as src/functions/scalar.rs:508-511)
+ *   BDF_DIVIDE_BY_ZERO  -> ArrowError::DivideByZero
+ *   BDF_UNSUPPORTED     -> a trait bound the reference enforces at compile time (e.g. sin on integers,
+ *                          max on floats: T::Native: Float / Ord)
+ *   BDF_WOULD_PANIC     -> the reference panics here (max/min .unwrap() on an all-null or empty chunk,
+ *                          aggregate.rs:19,29); the binding turns it back into a panic
+ *   BDF_CUDA / BDF_OOM / BDF_INVALID -> ArrowError::ComputeError(bdf_last_error())
+ * There is NO CPU fallback: without a usable CUDA device bdf_init fails with BDF_CUDA.
+ *
+ * Ownership: host buffers (inputs and outputs) belong to the caller; the library never frees them and,
+ * except for BDF_ASYNC uploads, never touches them after the call returns.  Device memory, streams and
+ * events belong to bdf_ctx / bdf_col handles.  A bdf_ctx serialises concurrent callers with a mutex.
+ */
+#ifndef B200DF_H
+#define B200DF_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
+#endif
+
+#define BDF_ABI_VERSION 1
+
+/* Arrow primitive types, in arrow::datatypes::DataType order. */
+typedef enum {
+    BDF_I8 = 0, BDF_I16, BDF_I32, BDF_I64, BDF_U8, BDF_U16, BDF_U32, BDF_U64, BDF_F32, BDF_F64, BDF_NTYPES
+} bdf_dtype;
+
+typedef enum { BDF_ADD = 0, BDF_SUB, BDF_MUL, BDF_DIV, BDF_ATAN2, BDF_HYPOT, BDF_LOG, BDF_NBINARY } bdf_binop;
+
+typedef enum {
+    BDF_ABS = 0, BDF_SIN, BDF_COS, BDF_TAN,
+    BDF_ACOS, BDF_ASIN, BDF_ATAN, BDF_CBRT, BDF_CEIL, BDF_COSH, BDF_DEGREES, BDF_EXP, BDF_EXPM1,
+    BDF_FLOOR, BDF_LOG10, BDF_LOG2, BDF_RADIANS, BDF_ROUND, BDF_SINH, BDF_SQRT, BDF_TANH, BDF_NUNARY
+} bdf_unop;
+
+typedef enum { BDF_SUM = 0, BDF_MIN, BDF_MAX, BDF_COUNT, BDF_NAGG } bdf_aggop;
+
+typedef enum {
+    BDF_OK = 0, BDF_LENGTH_MISMATCH = 1, BDF_DIVIDE_BY_ZERO = 2, BDF_UNSUPPORTED = 3, BDF_CUDA = 4,
+    BDF_NCCL = 5 /* reserved */, BDF_OOM = 6, BDF_WOULD_PANIC = 7, BDF_INVALID = 8
+} bdf_status;
+
+/* One chunk = one PrimitiveArray<T> in Arrow memory layout (ArrayData: buffers[0], null bitmap, len, offset). */
+typedef struct {
+    const void*    values;     /* base of the values buffer, NOT offset-adjusted                         */
+    const uint8_t* validity;   /* LSB-first bitmap, 1 = valid; NULL when the array has no null buffer     */
+    int64_t        len;        /* logical length in elements                                              */
+    int64_t        offset;     /* element offset, applies to values and to validity bits (sliced arrays)  */
+    int64_t        null_count; /* cached ArrayData::null_count, or -1 if unknown                          */
+} bdf_view;
+
+/* Output chunk.  values >= len*width bytes, validity >= ceil(len/8) bytes, both caller-allocated
+ * (arrow MutableBuffer).  validity is written at bit offset 0 with zero padding bits.  validity may be
+ * NULL only if the result carries no bitmap (has_validity == 0 on return), else BDF_INVALID. */
+typedef struct {
+    void*    values;
+    uint8_t* validity;
+    int64_t  len;          /* IN: capacity in elements (must equal the result length); OUT: length */
+    int64_t  null_count;   /* OUT */
+    int32_t  has_validity; /* OUT: 0 => every slot valid and no bitmap was written */
+} bdf_out;
+
+/* All four aggregates from one pass.  Each value slot holds T::Native in its low bytes (little endian). */
+typedef struct {
+    uint64_t sum, min, max;  /* bit patterns of T::Native, zero-padded to 8 bytes                      */
+    int64_t  count;          /* non-null slots                                                         */
+    int64_t  rows;           /* total slots                                                            */
+    int32_t  any_valid;      /* 0 => min/max are None                                                  */
+    int32_t  would_panic;    /* 1 => some chunk is empty/all-null: reference max/min .unwrap() panics  */
+} bdf_agg4;
+
+typedef struct bdf_ctx bdf_ctx;
+typedef struct bdf_col bdf_col;
+
+/* ---- lifecycle ------------------------------------------------------------------------------ */
+int          bdf_abi_version(void);
+const char*  bdf_last_error(void);
+int          bdf_init(int device, bdf_ctx** out);   /* one context per GPU (one process per GPU) */
+void         bdf_destroy(bdf_ctx* ctx);
+int          bdf_synchronize(bdf_ctx* ctx);
+int          bdf_device_info(bdf_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);
+
+/* Pinned host memory ("Arrow buffers are pinned and copied to device once per batch"). */
+int          bdf_host_alloc(bdf_ctx* ctx, size_t bytes, void** out);
+int          bdf_host_free(bdf_ctx* ctx, void* p);
+int          bdf_host_register(bdf_ctx* ctx, void* p, size_t bytes);
+int          bdf_host_unregister(bdf_ctx* ctx, void* p);
+
+/* ---- host in / host out: drop-in bodies for the reference functions --------------------------- */
+/* zip() semantics: n = min(n_left, n_right) chunks are processed (scalar.rs:28-31). */
+int bdf_binary(bdf_ctx* ctx, int op, int dtype, int64_t n_left, const bdf_view* left, int64_t n_right,
+               const bdf_view* right, bdf_out* out);
+int bdf_unary(bdf_ctx* ctx, int op, int dtype, int64_t n_chunks, const bdf_view* in, bdf_out* out);
+int bdf_cast(bdf_ctx* ctx, int from, int to, int64_t n_chunks, const bdf_view* in, bdf_out* out);
+/* out_scalar: T::Native for SUM/MIN/MAX, int64_t for COUNT.  *is_some == 0 <=> Rust None. */
+int bdf_aggregate(bdf_ctx* ctx, int op, int dtype, int64_t n_chunks, const bdf_view* in, void* out_scalar,
+                  int32_t* is_some);
+int bdf_aggregate_all(bdf_ctx* ctx, int dtype, int64_t n_chunks, const bdf_view* in, bdf_agg4* out);
+int bdf_avg(bdf_ctx* ctx, int dtype, int64_t n_chunks, const bdf_view* in, double* out, int32_t* is_some);
+
+/* ---- device-resident columns -------------------------------------------------------------------- */
+#define BDF_ASYNC 1 /* bdf_upload returns before the copies finish: host buffers must stay valid and
+                       unmodified until bdf_col_wait / bdf_synchronize / a download of a dependent column */
+int  bdf_upload(bdf_ctx* ctx, int dtype, int64_t n_chunks, const bdf_view* in, int flags, bdf_col** out);
+int  bdf_col_wait(bdf_ctx* ctx, const bdf_col* col);
+int  bdf_col_describe(const bdf_col* col, int32_t* dtype, int64_t* n_chunks, int64_t* total_len);
+int  bdf_col_chunk_info(bdf_ctx* ctx, const bdf_col* col, int64_t chunk, int64_t* len, int64_t* null_count,
+                        int32_t* has_validity);
+int  bdf_binary_dev(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, bdf_col** out);
+int  bdf_unary_dev(bdf_ctx* ctx, int op, const bdf_col* in, bdf_col** out);
+int  bdf_cast_dev(bdf_ctx* ctx, int to, const bdf_col* in, bdf_col** out);
+int  bdf_aggregate_dev(bdf_ctx* ctx, int op, const bdf_col* in, void* out_scalar, int32_t* is_some);
+int  bdf_aggregate_all_dev(bdf_ctx* ctx, const bdf_col* in, bdf_agg4* out);
+int  bdf_avg_dev(bdf_ctx* ctx, const bdf_col* in, double* out, int32_t* is_some);
+int  bdf_download(bdf_ctx* ctx, const bdf_col* col, bdf_out* out /* n_chunks entries */);
+void bdf_col_free(bdf_ctx* ctx, bdf_col* col);
+
+/* ---- measurement support ------------------------------------------------------------------------ */
+/* Per-launch CUDA-event timing on the library's compute stream (the stream the kernels run on). */
+typedef struct {
+    int32_t kernel;   /* bdf_kernel_id */
+    int32_t dtype;    /* output dtype   */
+    int64_t rows;     /* elements processed by the launch */
+    int64_t bytes;    /* algorithmic bytes of the launch (SURVEY 8(d) per-row figure x rows) */
+    float   ms;       /* device time between the bracketing events */
+} bdf_launch_record;
+typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG } bdf_kernel_id;
+int     bdf_profile_enable(bdf_ctx* ctx, int on);
+int     bdf_profile_read(bdf_ctx* ctx, bdf_launch_record* buf, int64_t cap, int64_t* n); /* syncs; drains */
+int64_t bdf_launch_count(bdf_ctx* ctx);           /* kernels launched since bdf_init */
+/* Stream-ordered stopwatch on the compute stream: start/stop record events; stop syncs and reports ms. */
+int     bdf_timer_start(bdf_ctx* ctx);
+int     bdf_timer_stop(bdf_ctx* ctx, float* ms);
+/* Writes `bytes` of device memory (an L2 flush when bytes > L2 size). */
+int     bdf_flush_l2(bdf_ctx* ctx, size_t bytes);
+
+/* Counter-based synthetic columns generated on the device (bench / large-config tests).
+ * Reproduces oracle/oracle.c:orc_generate bit-for-bit.  kind 0: real uniform [lo,hi), 1: real +-[1,2),
+ * 2: integer full range, 3: integer uniform [-2^40,2^40).  null_mod 0: no bitmap. */
+int bdf_generate(bdf_ctx* ctx, int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col_id,
+                 int64_t n_chunks, const int64_t* chunk_lens, int64_t row0, uint32_t null_mod, bdf_col** out);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200DF_H */

@@ -1,0 +1,181 @@
+"""ctypes front-end for the CPU oracle (oracle/liboracle.so).
+
+TEST INFRASTRUCTURE ONLY -- imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
+legs; never by the product package.  Chunks are duck-typed: any object with
+``dtype, values (np.ndarray), validity (np.ndarray[uint8] | None), offset, length, null_count``.
+Results come back as plain ``OracleArray`` tuples of numpy buffers.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "liboracle.so")
+
+I8, I16, I32, I64, U8, U16, U32, U64, F32, F64 = range(10)
+NP_DTYPES = [np.int8, np.int16, np.int32, np.int64, np.uint8, np.uint16, np.uint32, np.uint64, np.float32, np.float64]
+ADD, SUB, MUL, DIV, ATAN2, HYPOT, LOG = range(7)
+(ABS, SIN, COS, TAN, ACOS, ASIN, ATAN, CBRT, CEIL, COSH, DEGREES, EXP, EXPM1, FLOOR, LOG10, LOG2, RADIANS, ROUND, SINH,
+ SQRT, TANH) = range(21)
+SUM, MIN, MAX, COUNT, MIN_AS_WRITTEN = range(5)
+OK, LENGTH_MISMATCH, DIVIDE_BY_ZERO, UNSUPPORTED, PANIC = 0, 1, 2, 3, 7
+
+
+class View(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("len", C.c_int64), ("offset", C.c_int64),
+                ("null_count", C.c_int64)]
+
+
+class Out(C.Structure):
+    _fields_ = [("values", C.c_void_p), ("validity", C.c_void_p), ("len", C.c_int64), ("null_count", C.c_int64),
+                ("has_validity", C.c_int32)]
+
+
+@dataclass
+class OracleArray:
+    dtype: int
+    values: np.ndarray            # length == len, offset 0
+    validity: Optional[np.ndarray]  # uint8 bitmap (offset 0) or None when arrow-rs attaches none
+    null_count: int
+
+    @property
+    def length(self) -> int:
+        return int(self.values.shape[0])
+
+    offset = 0
+
+    def valid_mask(self) -> np.ndarray:
+        if self.validity is None:
+            return np.ones(self.length, dtype=bool)
+        return np.unpackbits(self.validity, bitorder="little")[: self.length].astype(bool)
+
+
+def build(force: bool = False) -> str:
+    """Compile liboracle.so from oracle.c (gcc; see Makefile)."""
+    src = os.path.join(_HERE, "oracle.c")
+    if force or not os.path.exists(_LIB_PATH) or os.path.getmtime(_LIB_PATH) < max(
+            os.path.getmtime(src), os.path.getmtime(os.path.join(_HERE, "oracle.h"))):
+        subprocess.check_call(["make", "-C", _HERE, "-B", "liboracle.so"], stdout=subprocess.DEVNULL)
+    return _LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_LIB_PATH):
+            build()
+        L = C.CDLL(_LIB_PATH)
+        PV, PO = C.POINTER(View), C.POINTER(Out)
+        L.orc_binary.argtypes = [C.c_int, C.c_int, PV, PV, PO]
+        L.orc_unary.argtypes = [C.c_int, C.c_int, PV, PO]
+        L.orc_cast.argtypes = [C.c_int, C.c_int, PV, PO]
+        L.orc_col_binary.argtypes = [C.c_int, C.c_int, C.c_int64, PV, C.c_int64, PV, PO, C.c_int]
+        L.orc_col_unary.argtypes = [C.c_int, C.c_int, C.c_int64, PV, PO, C.c_int]
+        L.orc_col_cast.argtypes = [C.c_int, C.c_int, C.c_int64, PV, PO, C.c_int]
+        L.orc_aggregate.argtypes = [C.c_int, C.c_int, C.c_int64, PV, C.c_void_p, C.POINTER(C.c_int32)]
+        L.orc_avg.argtypes = [C.c_int, C.c_int64, PV, C.POINTER(C.c_double), C.POINTER(C.c_int32)]
+        L.orc_sum_exact.argtypes = [C.c_int, C.c_int64, PV, C.POINTER(C.c_longdouble), C.POINTER(C.c_longdouble)]
+        L.orc_splitmix64.argtypes = [C.c_uint64]
+        L.orc_splitmix64.restype = C.c_uint64
+        L.orc_generate.argtypes = [C.c_int, C.c_int, C.c_double, C.c_double, C.c_uint64, C.c_uint64, C.c_int64,
+                                   C.c_int64, C.c_uint32, C.c_void_p, C.c_void_p, C.POINTER(C.c_int64)]
+        L.orc_generate.restype = None
+        L.orc_null_count.argtypes = [PV]
+        L.orc_null_count.restype = C.c_int64
+        _lib = L
+    return _lib
+
+
+def _views(chunks: Sequence) -> "C.Array[View]":
+    arr = (View * max(len(chunks), 1))()
+    for i, c in enumerate(chunks):
+        arr[i].values = c.values.ctypes.data if c.values.size else 0
+        arr[i].validity = c.validity.ctypes.data if c.validity is not None else None
+        arr[i].len = c.length
+        arr[i].offset = c.offset
+        arr[i].null_count = getattr(c, "null_count", -1)
+    return arr
+
+
+def _alloc_outs(dtype: int, lens: Sequence[int]):
+    outs = (Out * max(len(lens), 1))()
+    bufs = []
+    for i, n in enumerate(lens):
+        v = np.zeros(n, dtype=NP_DTYPES[dtype])
+        b = np.zeros((n + 7) // 8, dtype=np.uint8)
+        outs[i].values = v.ctypes.data if n else 0
+        outs[i].validity = b.ctypes.data if b.size else 0
+        bufs.append((v, b))
+    return outs, bufs
+
+
+def _collect(dtype, outs, bufs):
+    res = []
+    for i, (v, b) in enumerate(bufs):
+        res.append(OracleArray(dtype, v, b if outs[i].has_validity else None, int(outs[i].null_count)))
+    return res
+
+
+def col_binary(op: int, dtype: int, left: Sequence, right: Sequence, threads: int = 1):
+    """ScalarFunctions::{add,subtract,multiply,divide}.  Returns (status, [OracleArray])."""
+    n = min(len(left), len(right))
+    outs, bufs = _alloc_outs(dtype, [left[i].length for i in range(n)])
+    st = lib().orc_col_binary(op, dtype, len(left), _views(left), len(right), _views(right), outs, threads)
+    return st, (_collect(dtype, outs, bufs) if st == OK else None)
+
+
+def col_unary(op: int, dtype: int, chunks: Sequence, threads: int = 1):
+    outs, bufs = _alloc_outs(dtype, [c.length for c in chunks])
+    st = lib().orc_col_unary(op, dtype, len(chunks), _views(chunks), outs, threads)
+    return st, (_collect(dtype, outs, bufs) if st == OK else None)
+
+
+def col_cast(from_t: int, to_t: int, chunks: Sequence, threads: int = 1):
+    outs, bufs = _alloc_outs(to_t, [c.length for c in chunks])
+    st = lib().orc_col_cast(from_t, to_t, len(chunks), _views(chunks), outs, threads)
+    return st, (_collect(to_t, outs, bufs) if st == OK else None)
+
+
+def aggregate(op: int, dtype: int, chunks: Sequence):
+    """AggregateFunctions::{sum,min,max,count}.  Returns (status, value | None)."""
+    out_dtype = np.int64 if op == COUNT else NP_DTYPES[dtype]
+    out = np.zeros(1, dtype=out_dtype)
+    some = C.c_int32(0)
+    st = lib().orc_aggregate(op, dtype, len(chunks), _views(chunks), out.ctypes.data, C.byref(some))
+    if st != OK:
+        return st, None
+    return st, (out[0] if some.value else None)
+
+
+def avg(dtype: int, chunks: Sequence):
+    out = C.c_double(0)
+    some = C.c_int32(0)
+    st = lib().orc_avg(dtype, len(chunks), _views(chunks), C.byref(out), C.byref(some))
+    return st, (out.value if (st == OK and some.value) else None)
+
+
+def sum_exact(dtype: int, chunks: Sequence):
+    """(compensated long-double sum, sum of |x|) over valid slots, as Python floats (np.longdouble)."""
+    s, sa = C.c_longdouble(0), C.c_longdouble(0)
+    st = lib().orc_sum_exact(dtype, len(chunks), _views(chunks), C.byref(s), C.byref(sa))
+    assert st == OK
+    return np.longdouble(s.value), np.longdouble(sa.value)
+
+
+def generate(dtype: int, kind: int, lo: float, hi: float, seed: int, col: int, row0: int, length: int,
+             null_mod: int = 0) -> OracleArray:
+    v = np.zeros(length, dtype=NP_DTYPES[dtype])
+    b = np.zeros((length + 7) // 8, dtype=np.uint8) if null_mod else None
+    nc = C.c_int64(0)
+    lib().orc_generate(dtype, kind, lo, hi, seed, col, row0, length, null_mod, v.ctypes.data if length else 0,
+                       b.ctypes.data if (b is not None and b.size) else None, C.byref(nc))
+    return OracleArray(dtype, v, b, int(nc.value))

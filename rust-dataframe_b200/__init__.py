@@ -1,0 +1,20 @@
+"""rust-dataframe_b200: the Blackwell (sm_100a) execution path for rust-dataframe's per-RecordBatch compute
+(elementwise add/sub/mul/div, trig, numeric cast, sum/min/max/count with null-bitmap propagation).
+
+The product is ``libb200df.so`` -- hand-written CUDA kernels behind the C ABI in ``include/b200df.h``.
+This package is the thin host-side mirror of the reference's operator interface over that ABI
+(``ScalarFunctions``, ``AggregateFunctions``, ``cast``) plus the device-resident ``Column`` handle.
+Import as ``rust_dataframe_b200`` (alias module at the repository root).
+"""
+from . import _native as native
+from ._native import (ArrowError, ComputeError, Context, DivideByZero, ReferencePanic, UnsupportedType,
+                      default_context)
+from .arrays import (DTYPE_NAMES, F32, F64, I8, I16, I32, I64, NP_DTYPES, U8, U16, U32, U64, PrimitiveArray, dtype_of,
+                     width_of)
+from .functions import AggregateFunctions, Column, ScalarFunctions, cast
+
+__all__ = [
+    "native", "ArrowError", "ComputeError", "Context", "DivideByZero", "ReferencePanic", "UnsupportedType",
+    "default_context", "PrimitiveArray", "ScalarFunctions", "AggregateFunctions", "Column", "cast",
+    "I8", "I16", "I32", "I64", "U8", "U16", "U32", "U64", "F32", "F64", "NP_DTYPES", "DTYPE_NAMES", "dtype_of", "width_of",
+]

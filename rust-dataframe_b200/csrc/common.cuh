@@ -1,0 +1,217 @@
+// common.cuh -- device helpers shared by the sm_100a kernels of libb200df.
+//
+// Data layout in HBM (DESIGN.md "Layout"): every chunk of a device column is an Arrow PrimitiveArray
+// whose values start 256-byte aligned (element offset already applied at upload) and whose validity
+// bitmap (LSB-first, 1 = valid) is a 4-byte-aligned array of 32-bit words with a residual BIT offset
+// `off` (0..7 for uploaded slices, 0 for kernel-made columns).  Bitmaps are padded so that one word past
+// the last used one may be read.
+//
+// Work decomposition: a *tile* is THREADS x U vectors of 16 bytes per array (coalesced: lane l of a warp
+// touches vector j*THREADS + l).  A thread therefore owns E = 16/sizeof(T) consecutive elements per step
+// and E consecutive validity bits; 32/E neighbouring lanes share one bitmap word, which they assemble
+// with a log2(32/E)-step shuffle-OR so the warp writes whole 32-bit words.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace bdf {
+
+enum : int { T_I8 = 0, T_I16, T_I32, T_I64, T_U8, T_U16, T_U32, T_U64, T_F32, T_F64, T_NTYPES };
+
+__host__ __device__ inline int dtype_width(int t) {
+    switch (t) {
+        case T_I8: case T_U8: return 1;
+        case T_I16: case T_U16: return 2;
+        case T_I32: case T_U32: case T_F32: return 4;
+        default: return 8;
+    }
+}
+__host__ __device__ inline bool dtype_is_float(int t) { return t == T_F32 || t == T_F64; }
+__host__ __device__ inline bool dtype_is_signed_int(int t) { return t >= T_I8 && t <= T_I64; }
+
+constexpr int kThreads = 256;  // CTA size of every streaming kernel
+constexpr int kUnroll = 4;     // 16-byte vectors in flight per thread per array
+constexpr int kTileBytes = kThreads * kUnroll * 16;  // bytes of the widest array per tile (16 KiB)
+
+// ---- 128-bit streaming loads/stores -----------------------------------------------------------
+// Inputs are read exactly once and outputs written exactly once: bypass L1 allocation so the small
+// validity words (which ARE re-read by neighbouring lanes) keep the L1.
+__device__ __forceinline__ uint4 ld_stream16(const void* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ld_stream8(const void* p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t ld_stream4(const void* p) {
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint16_t ld_stream2(const void* p) {
+    uint16_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st_stream16(void* p, uint4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.u32 [%0], {%1,%2,%3,%4};"
+                 :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_stream8(void* p, uint2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.u32 [%0], {%1,%2};" :: "l"(p), "r"(v.x), "r"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_stream4(void* p, uint32_t v) {
+    asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void st_stream2(void* p, uint16_t v) {
+    asm volatile("st.global.L1::no_allocate.u16 [%0], %1;" :: "l"(p), "h"(v) : "memory");
+}
+
+// A register-resident vector of N elements of T moved with one access of N*sizeof(T) bytes (2..16).
+template <typename T, int N>
+struct Vec {
+    static constexpr int kBytes = N * (int)sizeof(T);
+    static_assert(kBytes == 16 || kBytes == 8 || kBytes == 4 || kBytes == 2, "unsupported vector size");
+    union {
+        T e[N];
+        uint4 q;
+        uint2 d;
+        uint32_t w;
+        uint16_t h;
+    };
+    __device__ __forceinline__ void load(const void* p) {
+        if constexpr (kBytes == 16) q = ld_stream16(p);
+        else if constexpr (kBytes == 8) d = ld_stream8(p);
+        else if constexpr (kBytes == 4) w = ld_stream4(p);
+        else h = ld_stream2(p);
+    }
+    __device__ __forceinline__ void store(void* p) const {
+        if constexpr (kBytes == 16) st_stream16(p, q);
+        else if constexpr (kBytes == 8) st_stream8(p, d);
+        else if constexpr (kBytes == 4) st_stream4(p, w);
+        else st_stream2(p, h);
+    }
+};
+
+// ---- validity bitmap access ----------------------------------------------------------------------
+// E consecutive bits starting at absolute bit index `bit` of word array v.
+template <int E>
+__device__ __forceinline__ uint32_t load_bits(const uint32_t* __restrict__ v, int64_t bit) {
+    const int64_t w = bit >> 5;
+    const int sh = (int)(bit & 31);
+    const uint32_t lo = __ldg(v + w);
+    const uint32_t hi = (sh + E > 32) ? __ldg(v + w + 1) : 0u;
+    const uint32_t r = __funnelshift_r(lo, hi, sh);
+    if constexpr (E == 32) return r;
+    else return r & ((1u << E) - 1u);
+}
+
+// Each lane contributes E bits for elements [e0, e0+E) (e0 a multiple of E, bit offset 0 on output); the
+// 32/E lanes that share a word OR their pieces together and the first of them stores the word.
+// Must be executed by all 32 lanes of the warp.  `active` = this lane's e0 lies inside the chunk.
+template <int E>
+__device__ __forceinline__ void store_bits(uint32_t* __restrict__ vout, int64_t e0, uint32_t bits, bool active) {
+    constexpr int G = 32 / E;
+    const int lane = threadIdx.x & 31;
+    uint32_t c = bits << (E * (lane % G));
+#pragma unroll
+    for (int o = 1; o < G; o <<= 1) c |= __shfl_xor_sync(0xffffffffu, c, o);
+    if ((lane % G) == 0 && active) vout[e0 >> 5] = c;
+}
+
+// Mask of the elements of [e0, e0+E) that lie below len.
+template <int E>
+__device__ __forceinline__ uint32_t tail_mask(int64_t e0, int64_t len) {
+    const int64_t rem = len - e0;
+    if (rem >= E) return (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
+    if (rem <= 0) return 0u;
+    return (1u << (int)rem) - 1u;
+}
+
+// Chunk lookup: descriptors are sorted by tile0 (first tile of the chunk); returns the chunk owning `tile`.
+template <typename Desc>
+__device__ __forceinline__ int find_chunk(const Desc* __restrict__ descs, int n_chunks, int64_t tile) {
+    int lo = 0, hi = n_chunks - 1;
+    while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&descs[mid].tile0) <= tile) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+
+// ---- warp / block reductions -------------------------------------------------------------------
+template <typename T, typename F>
+__device__ __forceinline__ T warp_reduce(T v, F f) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = f(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of a per-thread count (all threads call; result valid in thread 0).
+__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* smem /* >= 32 */) {
+    v = warp_reduce(v, [](unsigned long long a, unsigned long long b) { return a + b; });
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) smem[warp] = v;
+    __syncthreads();
+    unsigned long long r = 0;
+    if (warp == 0) {
+        r = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0ull;
+        r = warp_reduce(r, [](unsigned long long a, unsigned long long b) { return a + b; });
+    }
+    return r;
+}
+
+// ---- descriptors (one per chunk, device-resident array sorted by tile0) ------------------------
+struct BinDesc {
+    const void* a; const void* b; void* out;
+    const uint32_t* va; const uint32_t* vb; uint32_t* vout;
+    int64_t len; int64_t tile0;
+    int32_t offa, offb;
+};
+struct UnDesc {
+    const void* in; void* out;
+    const uint32_t* vin; uint32_t* vout;
+    int64_t len; int64_t tile0;
+    int32_t off; int32_t pad;
+};
+struct RedDesc {
+    const void* in; const uint32_t* vin;
+    int64_t len; int64_t tile0;
+    int32_t off; int32_t pad;
+};
+struct GenDesc {
+    void* out; uint32_t* vout;
+    int64_t len; int64_t tile0; int64_t row0;
+};
+
+// Result of the reduce kernel, in device memory.
+struct AggDev {
+    unsigned long long sum_bits;  // ints: 64-bit wrapping sum (two's complement); floats: double bit pattern
+    unsigned long long min_bits;  // ints only: T widened to 64 bit (sign- or zero-extended)
+    unsigned long long max_bits;
+    unsigned long long count;     // valid slots
+};
+
+// ---- launchers (defined in k_*.cu) ---------------------------------------------------------------
+int elems_per_tile(int dtype);                 // tile size in elements for arrays of dtype
+int elems_per_tile_cast(int from, int to);
+cudaError_t launch_binary(int op, int dtype, const BinDesc* d_descs, int n_chunks, int64_t total_tiles,
+                          unsigned long long* d_valid_counts, int* d_flags, cudaStream_t s);
+cudaError_t launch_unary(int op, int dtype, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
+                         unsigned long long* d_valid_counts, cudaStream_t s);
+cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
+                        unsigned long long* d_valid_counts, cudaStream_t s);
+int reduce_grid(int sm_count);
+cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, int grid,
+                          AggDev* d_partials, unsigned int* d_ticket, AggDev* d_result, cudaStream_t s);
+cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
+                            const GenDesc* d_descs, int n_chunks, int64_t total_tiles,
+                            unsigned long long* d_valid_counts, cudaStream_t s);
+cudaError_t launch_fill(void* p, size_t bytes, cudaStream_t s);
+
+}  // namespace bdf

@@ -1,0 +1,1115 @@
+// runtime.cu -- host runtime and C ABI of libb200df.so (see include/b200df.h for the contract).
+//
+// One bdf_ctx per GPU (one process per GPU).  Three non-blocking streams: h2d (uploads), compute (all
+// kernels, all stream-ordered allocations), d2h (downloads).  Columns are device-resident lists of Arrow
+// chunks carved out of two arenas (values, validity).  Chunks become ready in *groups*; every group has
+// an event, so the kernels of group g run while group g+1 is still crossing PCIe and group g-1 is
+// already on its way back.  When all inputs are already resident an operator is ONE batched launch over
+// every chunk of the column.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/b200df.h"
+#include "common.cuh"
+
+using namespace bdf;
+
+// ---------------------------------------------------------------------------------------------------
+// errors
+
+static thread_local std::string g_err;
+
+static int fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return status;
+}
+
+static int cuda_status(cudaError_t e) { return e == cudaErrorMemoryAllocation ? BDF_OOM : BDF_CUDA; }
+
+#define CK(call)                                                                                       \
+    do {                                                                                               \
+        cudaError_t _e = (call);                                                                       \
+        if (_e != cudaSuccess)                                                                         \
+            return fail(cuda_status(_e), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+#define TRY(expr)                  \
+    do {                           \
+        int _st = (expr);          \
+        if (_st != BDF_OK) return _st; \
+    } while (0)
+
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------------------------------
+// objects
+
+struct Group {
+    int64_t begin, end;  // chunks [begin, end)
+    cudaEvent_t ev;      // chunks are complete in HBM once ev has fired
+};
+
+struct DevChunk {
+    char* values;
+    uint32_t* validity;  // nullptr = no bitmap
+    int64_t len;
+    int32_t bit_off;
+};
+
+struct bdf_col {
+    int dtype = 0;
+    int64_t total_len = 0;
+    std::vector<DevChunk> chunks;
+    char* arena_values = nullptr;
+    char* arena_validity = nullptr;
+    unsigned long long* d_valid_counts = nullptr;  // per chunk, written by the producing kernel
+    bool counts_on_device = false;                 // d_valid_counts not yet mirrored into null_counts
+    std::vector<int64_t> null_counts;              // -1 = unknown
+    std::vector<Group> groups;
+};
+
+struct ProfEntry {
+    bdf_launch_record rec;
+    cudaEvent_t e0, e1;
+};
+
+struct bdf_ctx {
+    int device = 0;
+    int sm_count = 0, cc_major = 0, cc_minor = 0;
+    size_t hbm_bytes = 0;
+    cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    std::mutex mu;
+    // pinned staging: descriptor ring + small result area
+    char* ring = nullptr;
+    size_t ring_cap = 0, ring_head = 0;
+    AggDev* h_agg = nullptr;        // pinned, kAggSlots entries
+    int* h_flag = nullptr;          // pinned
+    // device scratch
+    AggDev* d_partials = nullptr;
+    AggDev* d_agg = nullptr;        // kAggSlots entries
+    unsigned int* d_ticket = nullptr;
+    int* d_flag = nullptr;
+    int red_grid_cap = 0;
+    cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    size_t pipeline_bytes = (size_t)32 << 20;
+    bool profiling = false;
+    std::vector<ProfEntry> prof;
+    int64_t launches = 0;
+};
+
+static constexpr int kAggSlots = 4096;
+
+// ---------------------------------------------------------------------------------------------------
+// small helpers
+
+static int check_dtype(int t) {
+    if (t < 0 || t >= BDF_NTYPES) return fail(BDF_INVALID, "invalid dtype %d", t);
+    return BDF_OK;
+}
+
+static int ring_alloc(bdf_ctx* c, size_t bytes, void** out) {
+    bytes = align_up(bytes, 64);
+    if (bytes > c->ring_cap) return fail(BDF_OOM, "descriptor ring too small for %zu bytes", bytes);
+    if (c->ring_head + bytes > c->ring_cap) {
+        CK(cudaStreamSynchronize(c->s_compute));  // everything that read the ring has finished
+        c->ring_head = 0;
+    }
+    *out = c->ring + c->ring_head;
+    c->ring_head += bytes;
+    return BDF_OK;
+}
+
+struct LaunchTimer {  // brackets one launch with events when profiling is on
+    bdf_ctx* c;
+    ProfEntry e{};
+    bool on;
+    LaunchTimer(bdf_ctx* ctx, int kernel, int dtype, int64_t rows, int64_t bytes) : c(ctx), on(ctx->profiling) {
+        c->launches++;
+        if (!on) return;
+        e.rec.kernel = kernel; e.rec.dtype = dtype; e.rec.rows = rows; e.rec.bytes = bytes; e.rec.ms = 0.f;
+        cudaEventCreate(&e.e0); cudaEventCreate(&e.e1);
+        cudaEventRecord(e.e0, c->s_compute);
+    }
+    ~LaunchTimer() {
+        if (!on) return;
+        cudaEventRecord(e.e1, c->s_compute);
+        c->prof.push_back(e);
+    }
+};
+
+static void col_destroy_host(bdf_col* col) {
+    for (auto& g : col->groups) if (g.ev) cudaEventDestroy(g.ev);
+    delete col;
+}
+
+// Free device memory of a column in stream order on the compute stream.
+static void col_release(bdf_ctx* c, bdf_col* col) {
+    if (!col) return;
+    for (auto& g : col->groups) if (g.ev) cudaStreamWaitEvent(c->s_compute, g.ev, 0);
+    if (col->arena_values) cudaFreeAsync(col->arena_values, c->s_compute);
+    if (col->arena_validity) cudaFreeAsync(col->arena_validity, c->s_compute);
+    if (col->d_valid_counts) cudaFreeAsync(col->d_valid_counts, c->s_compute);
+    col_destroy_host(col);
+}
+
+struct ChunkPlan {
+    int64_t len;
+    bool has_validity;
+};
+
+// Allocate arenas for a column with the given chunk plan (validity at bit offset `bit_off[i]`).
+static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, const std::vector<int32_t>* bit_offs,
+                     bdf_col** out) {
+    bdf_col* col = new (std::nothrow) bdf_col();
+    if (!col) return fail(BDF_OOM, "host allocation failed");
+    col->dtype = dtype;
+    const int w = dtype_width(dtype);
+    const size_t n = plan.size();
+    std::vector<size_t> voff(n), boff(n);
+    size_t vbytes = 0, bbytes = 0;
+    for (size_t i = 0; i < n; i++) {
+        voff[i] = vbytes;
+        vbytes += align_up((size_t)plan[i].len * w, 256);
+        boff[i] = bbytes;
+        if (plan[i].has_validity) {
+            const int bo = bit_offs ? (*bit_offs)[i] : 0;
+            bbytes += align_up(((size_t)plan[i].len + bo + 7) / 8 + 8, 256);
+        }
+        col->total_len += plan[i].len;
+    }
+    cudaError_t e = cudaSuccess;
+    if (vbytes) e = cudaMallocAsync((void**)&col->arena_values, vbytes, c->s_compute);
+    if (e == cudaSuccess && bbytes) e = cudaMallocAsync((void**)&col->arena_validity, bbytes, c->s_compute);
+    if (e == cudaSuccess && n) e = cudaMallocAsync((void**)&col->d_valid_counts, n * sizeof(unsigned long long), c->s_compute);
+    if (e == cudaSuccess && bbytes) e = cudaMemsetAsync(col->arena_validity, 0, bbytes, c->s_compute);
+    if (e == cudaSuccess && n) e = cudaMemsetAsync(col->d_valid_counts, 0, n * sizeof(unsigned long long), c->s_compute);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, col);
+        return fail(cuda_status(e), "device allocation of %zu bytes failed: %s", vbytes + bbytes, cudaGetErrorString(e));
+    }
+    col->chunks.resize(n);
+    col->null_counts.assign(n, 0);
+    for (size_t i = 0; i < n; i++) {
+        DevChunk& ch = col->chunks[i];
+        ch.values = col->arena_values ? col->arena_values + voff[i] : nullptr;
+        ch.validity = plan[i].has_validity ? (uint32_t*)(col->arena_validity + boff[i]) : nullptr;
+        ch.len = plan[i].len;
+        ch.bit_off = bit_offs ? (*bit_offs)[i] : 0;
+    }
+    *out = col;
+    return BDF_OK;
+}
+
+static int new_event(cudaEvent_t* ev) {
+    CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
+    return BDF_OK;
+}
+
+// True when every group event of the column has already fired.
+static bool col_complete(const bdf_col* col) {
+    for (auto& g : col->groups)
+        if (cudaEventQuery(g.ev) != cudaSuccess) { cudaGetLastError(); return false; }
+    return true;
+}
+
+static void wait_groups(cudaStream_t s, const bdf_col* col, int64_t begin, int64_t end) {
+    for (auto& g : col->groups)
+        if (g.begin < end && g.end > begin) cudaStreamWaitEvent(s, g.ev, 0);
+}
+
+// Group boundaries for an operator over `n` chunks: a single group when the inputs are resident, else
+// the union of the inputs' group ends (so work starts as soon as its own inputs have landed).
+static std::vector<int64_t> plan_groups(int64_t n, std::initializer_list<const bdf_col*> inputs) {
+    bool all_done = true;
+    for (auto* col : inputs) all_done = all_done && col_complete(col);
+    std::vector<int64_t> ends;
+    if (!all_done)
+        for (auto* col : inputs)
+            for (auto& g : col->groups)
+                if (g.end < n) ends.push_back(g.end);
+    ends.push_back(n);
+    std::sort(ends.begin(), ends.end());
+    ends.erase(std::unique(ends.begin(), ends.end()), ends.end());
+    return ends;
+}
+
+static int64_t bitmap_bytes(int64_t len) { return (len + 7) / 8; }
+
+// Mirror kernel-written valid counts into host null_counts (one small D2H + sync on the compute stream).
+static int fetch_counts(bdf_ctx* c, bdf_col* col) {
+    if (!col->counts_on_device) return BDF_OK;
+    const size_t n = col->chunks.size();
+    if (n) {
+        std::vector<unsigned long long> tmp(n);
+        wait_groups(c->s_compute, col, 0, (int64_t)n);
+        CK(cudaMemcpyAsync(tmp.data(), col->d_valid_counts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        for (size_t i = 0; i < n; i++)
+            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)tmp[i] : 0;
+    }
+    col->counts_on_device = false;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// reduce plumbing
+
+static int64_t reduce_bytes(const bdf_col* col, int64_t begin, int64_t end) {
+    int64_t b = 0;
+    const int w = dtype_width(col->dtype);
+    for (int64_t i = begin; i < end; i++)
+        b += col->chunks[i].len * w + (col->chunks[i].validity ? bitmap_bytes(col->chunks[i].len) : 0);
+    return b;
+}
+
+// Launch one reduce over chunks [begin,end) of col into d_agg[slot].  Caller has made the stream wait.
+static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t end, int slot) {
+    const int64_t n = end - begin;
+    const int tile = elems_per_tile(col->dtype);
+    void* hp = nullptr;
+    TRY(ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(RedDesc), &hp));
+    RedDesc* hd = (RedDesc*)hp;
+    int64_t tiles = 0, rows = 0;
+    for (int64_t i = 0; i < n; i++) {
+        const DevChunk& ch = col->chunks[begin + i];
+        hd[i].in = ch.values; hd[i].vin = ch.validity; hd[i].len = ch.len; hd[i].tile0 = tiles; hd[i].off = ch.bit_off; hd[i].pad = 0;
+        tiles += (ch.len + tile - 1) / tile;
+        rows += ch.len;
+    }
+    RedDesc* dd = nullptr;
+    CK(cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(RedDesc), c->s_compute));
+    if (n) CK(cudaMemcpyAsync(dd, hd, (size_t)n * sizeof(RedDesc), cudaMemcpyHostToDevice, c->s_compute));
+    {
+        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));
+        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->red_grid_cap, c->d_partials, c->d_ticket, c->d_agg + slot, c->s_compute));
+    }
+    CK(cudaFreeAsync(dd, c->s_compute));
+    return BDF_OK;
+}
+
+// Make sure every chunk's null count is known on the host (metadata for count / would_panic).
+static int ensure_null_counts(bdf_ctx* c, bdf_col* col) {
+    TRY(fetch_counts(c, col));
+    std::vector<int64_t> unknown;
+    for (size_t i = 0; i < col->chunks.size(); i++)
+        if (col->null_counts[i] < 0) unknown.push_back((int64_t)i);
+    if (unknown.empty()) return BDF_OK;
+    wait_groups(c->s_compute, col, 0, (int64_t)col->chunks.size());
+    for (size_t k = 0; k < unknown.size(); k += kAggSlots) {
+        const size_t m = std::min<size_t>(kAggSlots, unknown.size() - k);
+        for (size_t j = 0; j < m; j++) TRY(reduce_range(c, col, unknown[k + j], unknown[k + j] + 1, (int)j));
+        CK(cudaMemcpyAsync(c->h_agg, c->d_agg, m * sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        for (size_t j = 0; j < m; j++) {
+            const int64_t i = unknown[k + j];
+            col->null_counts[i] = col->chunks[i].len - (int64_t)c->h_agg[j].count;
+        }
+    }
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// upload / download
+
+struct UploadSpec {
+    int dtype;
+    int64_t n;
+    const bdf_view* views;
+};
+
+// Upload K columns with their chunks interleaved (a0,b0,a1,b1,...) so that a binary operator can start on
+// chunk i as soon as BOTH of its inputs have landed.
+static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool async, std::vector<bdf_col*>& cols) {
+    cols.assign(specs.size(), nullptr);
+    int64_t max_n = 0;
+    auto cleanup = [&]() { for (auto*& col : cols) { col_release(c, col); col = nullptr; } };
+    for (size_t k = 0; k < specs.size(); k++) {
+        const UploadSpec& s = specs[k];
+        std::vector<ChunkPlan> plan((size_t)s.n);
+        std::vector<int32_t> offs((size_t)s.n);
+        for (int64_t i = 0; i < s.n; i++) {
+            const bdf_view& v = s.views[i];
+            if (v.len < 0 || v.offset < 0 || (v.len > 0 && !v.values)) { cleanup(); return fail(BDF_INVALID, "bad view %lld", (long long)i); }
+            plan[i] = {v.len, v.validity != nullptr};
+            offs[i] = (int32_t)(v.offset & 7);
+        }
+        int st = col_alloc(c, s.dtype, plan, &offs, &cols[k]);
+        if (st != BDF_OK) { cleanup(); return st; }
+        for (int64_t i = 0; i < s.n; i++)
+            cols[k]->null_counts[i] = s.views[i].validity ? (s.views[i].null_count >= 0 ? s.views[i].null_count : -1) : 0;
+        max_n = std::max(max_n, s.n);
+    }
+    // allocations are stream-ordered on the compute stream: let the copy stream see them
+    cudaError_t e = cudaEventRecord(c->ev_tmp, c->s_compute);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_h2d, c->ev_tmp, 0);
+    size_t pending = 0;
+    int64_t group_begin = 0;
+    for (int64_t i = 0; i < max_n && e == cudaSuccess; i++) {
+        for (size_t k = 0; k < specs.size() && e == cudaSuccess; k++) {
+            if (i >= specs[k].n) continue;
+            const bdf_view& v = specs[k].views[i];
+            const DevChunk& ch = cols[k]->chunks[i];
+            const int w = dtype_width(specs[k].dtype);
+            if (v.len) {
+                e = cudaMemcpyAsync(ch.values, (const char*)v.values + v.offset * w, (size_t)v.len * w, cudaMemcpyHostToDevice, c->s_h2d);
+                pending += (size_t)v.len * w;
+                if (e == cudaSuccess && v.validity)
+                    e = cudaMemcpyAsync(ch.validity, v.validity + (v.offset >> 3), (size_t)((v.len + (v.offset & 7) + 7) / 8),
+                                        cudaMemcpyHostToDevice, c->s_h2d);
+            }
+        }
+        if (e == cudaSuccess && (pending >= c->pipeline_bytes || i == max_n - 1)) {
+            for (size_t k = 0; k < specs.size() && e == cudaSuccess; k++) {
+                const int64_t b = std::min(group_begin, specs[k].n), en = std::min(i + 1, specs[k].n);
+                if (en <= b) continue;
+                Group g{b, en, nullptr};
+                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_h2d);
+                cols[k]->groups.push_back(g);
+            }
+            pending = 0;
+            group_begin = i + 1;
+        }
+    }
+    if (e == cudaSuccess && !async) e = cudaStreamSynchronize(c->s_h2d);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        cudaStreamSynchronize(c->s_h2d);
+        cleanup();
+        return fail(cuda_status(e), "upload failed: %s", cudaGetErrorString(e));
+    }
+    return BDF_OK;
+}
+
+static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out);  // identity cast: bit offset -> 0
+
+static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
+    bool misaligned = false;
+    for (auto& ch : col->chunks) misaligned = misaligned || (ch.validity && ch.bit_off != 0);
+    if (misaligned) {  // an uploaded slice downloaded as-is: shift its bitmap to offset 0 first
+        bdf_col* tmp = nullptr;
+        TRY(realign(c, col, &tmp));
+        int st = download(c, tmp, out);
+        col_release(c, tmp);
+        return st;
+    }
+    const int w = dtype_width(col->dtype);
+    const int64_t n = (int64_t)col->chunks.size();
+    for (int64_t i = 0; i < n; i++) {
+        const DevChunk& ch = col->chunks[i];
+        if (out[i].len != ch.len) return fail(BDF_INVALID, "output chunk %lld has capacity %lld, result has %lld rows", (long long)i, (long long)out[i].len, (long long)ch.len);
+        if (ch.len && !out[i].values) return fail(BDF_INVALID, "output chunk %lld has no values buffer", (long long)i);
+        if (ch.validity && !out[i].validity) return fail(BDF_INVALID, "output chunk %lld needs a validity buffer", (long long)i);
+    }
+    std::vector<unsigned long long> counts((size_t)n);
+    for (auto& g : col->groups) {
+        CK(cudaStreamWaitEvent(c->s_d2h, g.ev, 0));
+        for (int64_t i = g.begin; i < g.end; i++) {
+            const DevChunk& ch = col->chunks[i];
+            if (!ch.len) continue;
+            CK(cudaMemcpyAsync(out[i].values, ch.values, (size_t)ch.len * w, cudaMemcpyDeviceToHost, c->s_d2h));
+            if (ch.validity) CK(cudaMemcpyAsync(out[i].validity, ch.validity, (size_t)bitmap_bytes(ch.len), cudaMemcpyDeviceToHost, c->s_d2h));
+        }
+    }
+    if (col->counts_on_device && n)
+        CK(cudaMemcpyAsync(counts.data(), col->d_valid_counts, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_d2h));
+    CK(cudaStreamSynchronize(c->s_d2h));
+    if (col->counts_on_device) {
+        for (int64_t i = 0; i < n; i++)
+            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)counts[i] : 0;
+        col->counts_on_device = false;
+    }
+    TRY(ensure_null_counts(c, col));
+    for (int64_t i = 0; i < n; i++) {
+        out[i].len = col->chunks[i].len;
+        out[i].has_validity = col->chunks[i].validity != nullptr;
+        out[i].null_count = col->null_counts[i];
+    }
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// operators on device columns
+
+static bool cast_is_fallible(int from, int to) {
+    if (from == to || dtype_is_float(to)) return false;
+    if (dtype_is_float(from)) return true;
+    const bool fs = dtype_is_signed_int(from), ts = dtype_is_signed_int(to);
+    const int fw = dtype_width(from), tw = dtype_width(to);
+    if (fs == ts) return tw < fw;
+    if (fs) return true;        // signed -> unsigned: negatives fail
+    return tw <= fw;            // unsigned -> signed: needs a strictly wider target
+}
+
+static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out) {
+    if (op < 0 || op >= BDF_NBINARY) return fail(BDF_INVALID, "invalid binary op %d", op);
+    if (l->dtype != r->dtype) return fail(BDF_INVALID, "binary op on columns of different types (%d, %d)", l->dtype, r->dtype);
+    const int dtype = l->dtype;
+    if (op > BDF_DIV && !dtype_is_float(dtype)) return fail(BDF_UNSUPPORTED, "atan2/hypot/log need a float column (T::Native: Float)");
+    const int64_t n = std::min<int64_t>((int64_t)l->chunks.size(), (int64_t)r->chunks.size());  // zip()
+    for (int64_t i = 0; i < n; i++)
+        if (l->chunks[i].len != r->chunks[i].len)
+            return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length");
+    std::vector<ChunkPlan> plan((size_t)n);
+    for (int64_t i = 0; i < n; i++)
+        plan[i] = {l->chunks[i].len, op > BDF_DIV || l->chunks[i].validity || r->chunks[i].validity};
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, dtype, plan, nullptr, &o));
+    o->counts_on_device = true;
+
+    const int tile = elems_per_tile(dtype);
+    const int w = dtype_width(dtype);
+    void* hp = nullptr;
+    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(BinDesc), &hp);
+    BinDesc* dd = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) {
+        BinDesc* hd = (BinDesc*)hp;
+        const std::vector<int64_t> ends = plan_groups(n, {l, r});
+        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(BinDesc), c->s_compute);
+        if (e == cudaSuccess && op == BDF_DIV) e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
+        int64_t begin = 0;
+        for (size_t gi = 0; gi < ends.size() && e == cudaSuccess; gi++) {
+            const int64_t end = ends[gi];
+            int64_t tiles = 0, rows = 0, bytes = 0;
+            for (int64_t i = begin; i < end; i++) {
+                const DevChunk &a = l->chunks[i], &b = r->chunks[i], &oc = o->chunks[i];
+                hd[i] = BinDesc{a.values, b.values, oc.values, a.validity, b.validity, oc.validity, a.len, tiles, a.bit_off, b.bit_off};
+                tiles += (a.len + tile - 1) / tile;
+                rows += a.len;
+                bytes += 3 * a.len * w + ((a.validity ? 1 : 0) + (b.validity ? 1 : 0) + (oc.validity ? 1 : 0)) * bitmap_bytes(a.len);
+            }
+            wait_groups(c->s_compute, l, begin, end);
+            wait_groups(c->s_compute, r, begin, end);
+            if (end > begin) {
+                e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(BinDesc), cudaMemcpyHostToDevice, c->s_compute);
+                if (e == cudaSuccess) {
+                    LaunchTimer t(c, BDF_K_BINARY, dtype, rows, bytes);
+                    e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->d_flag, c->s_compute);
+                }
+            }
+            if (e == cudaSuccess) {
+                Group g{begin, end, nullptr};
+                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
+                o->groups.push_back(g);
+            }
+            begin = end;
+        }
+        if (dd) cudaFreeAsync(dd, c->s_compute);
+        if (e == cudaSuccess && op == BDF_DIV) {
+            // DivideByZero must be returned INSTEAD of data: wait for the flag.
+            e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+            if (e == cudaSuccess && *c->h_flag) {
+                col_release(c, o);
+                return fail(BDF_DIVIDE_BY_ZERO, "Divide by zero error");
+            }
+        }
+    }
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "binary op failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+// Shared body of unary ops and casts (one input column, one output column).
+static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bdf_col** out) {
+    const int from = in->dtype;
+    int to = from;
+    if (is_cast) {
+        to = op_or_to;
+        TRY(check_dtype(to));
+    } else {
+        const int op = op_or_to;
+        if (op < 0 || op >= BDF_NUNARY) return fail(BDF_INVALID, "invalid unary op %d", op);
+        if (op == BDF_ABS) {
+            if (!dtype_is_float(from) && !dtype_is_signed_int(from)) return fail(BDF_UNSUPPORTED, "abs needs a signed type (T::Native: Signed)");
+        } else if (!dtype_is_float(from)) {
+            return fail(BDF_UNSUPPORTED, "float function on a non-float column (T::Native: Float)");
+        }
+    }
+    const int64_t n = (int64_t)in->chunks.size();
+    const bool fallible = is_cast && cast_is_fallible(from, to);
+    std::vector<ChunkPlan> plan((size_t)n);
+    for (int64_t i = 0; i < n; i++) plan[i] = {in->chunks[i].len, in->chunks[i].validity != nullptr || fallible};
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, to, plan, nullptr, &o));
+    o->counts_on_device = true;
+
+    const int tile = is_cast ? elems_per_tile_cast(from, to) : elems_per_tile(from);
+    const int wf = dtype_width(from), wt = dtype_width(to);
+    void* hp = nullptr;
+    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(UnDesc), &hp);
+    UnDesc* dd = nullptr;
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) {
+        UnDesc* hd = (UnDesc*)hp;
+        const std::vector<int64_t> ends = plan_groups(n, {in});
+        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(UnDesc), c->s_compute);
+        int64_t begin = 0;
+        for (size_t gi = 0; gi < ends.size() && e == cudaSuccess; gi++) {
+            const int64_t end = ends[gi];
+            int64_t tiles = 0, rows = 0, bytes = 0;
+            for (int64_t i = begin; i < end; i++) {
+                const DevChunk &a = in->chunks[i], &oc = o->chunks[i];
+                hd[i] = UnDesc{a.values, oc.values, a.validity, oc.validity, a.len, tiles, a.bit_off, 0};
+                tiles += (a.len + tile - 1) / tile;
+                rows += a.len;
+                bytes += a.len * (wf + wt) + ((a.validity ? 1 : 0) + (oc.validity ? 1 : 0)) * bitmap_bytes(a.len);
+            }
+            wait_groups(c->s_compute, in, begin, end);
+            if (end > begin) {
+                e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(UnDesc), cudaMemcpyHostToDevice, c->s_compute);
+                if (e == cudaSuccess) {
+                    LaunchTimer t(c, is_cast ? BDF_K_CAST : BDF_K_UNARY, to, rows, bytes);
+                    e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->s_compute)
+                                : launch_unary(op_or_to, from, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->s_compute);
+                }
+            }
+            if (e == cudaSuccess) {
+                Group g{begin, end, nullptr};
+                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
+                o->groups.push_back(g);
+            }
+            begin = end;
+        }
+        if (dd) cudaFreeAsync(dd, c->s_compute);
+    }
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "%s failed: %s", is_cast ? "cast" : "unary op", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out) { return map_dev(c, true, in->dtype, in, out); }
+
+static int aggregate_all_dev(bdf_ctx* c, bdf_col* col, bool need_counts, bdf_agg4* out) {
+    const int64_t n = (int64_t)col->chunks.size();
+    memset(out, 0, sizeof *out);
+    wait_groups(c->s_compute, col, 0, n);
+    TRY(reduce_range(c, col, 0, n, 0));
+    CK(cudaMemcpyAsync(c->h_agg, c->d_agg, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
+    CK(cudaStreamSynchronize(c->s_compute));
+    const AggDev a = c->h_agg[0];
+    const int dtype = col->dtype;
+    const int w = dtype_width(dtype);
+    const uint64_t mask = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1ull);
+    if (dtype == BDF_F64) {
+        out->sum = a.sum_bits;
+    } else if (dtype == BDF_F32) {
+        double d; memcpy(&d, &a.sum_bits, 8);
+        const float f = (float)d;
+        uint32_t fb; memcpy(&fb, &f, 4);
+        out->sum = fb;
+    } else {
+        out->sum = a.sum_bits & mask;
+        out->min = a.min_bits & mask;
+        out->max = a.max_bits & mask;
+    }
+    out->count = (int64_t)a.count;
+    out->rows = col->total_len;
+    out->any_valid = a.count > 0;
+    if (need_counts) {
+        TRY(ensure_null_counts(c, col));
+        for (int64_t i = 0; i < n; i++)
+            if (col->chunks[i].len - col->null_counts[i] == 0) out->would_panic = 1;
+    }
+    return BDF_OK;
+}
+
+static int aggregate_dev(bdf_ctx* c, int op, bdf_col* col, void* out_scalar, int32_t* is_some) {
+    if (op < 0 || op >= BDF_NAGG) return fail(BDF_INVALID, "invalid aggregate op %d", op);
+    const int dtype = col->dtype;
+    const int w = dtype_width(dtype);
+    if (op == BDF_COUNT) {  // metadata only, as in the reference (aggregate.rs:70-80)
+        TRY(ensure_null_counts(c, col));
+        int64_t total = 0;
+        for (size_t i = 0; i < col->chunks.size(); i++) total += col->chunks[i].len - col->null_counts[i];
+        *(int64_t*)out_scalar = total;
+        *is_some = 1;
+        return BDF_OK;
+    }
+    if ((op == BDF_MIN || op == BDF_MAX) && dtype_is_float(dtype))
+        return fail(BDF_UNSUPPORTED, "min/max need T::Native: Ord (integers only)");
+    bdf_agg4 a;
+    TRY(aggregate_all_dev(c, col, op != BDF_SUM, &a));
+    if (op == BDF_SUM) {
+        memcpy(out_scalar, &a.sum, (size_t)w);
+        *is_some = 1;
+        return BDF_OK;
+    }
+    if (a.would_panic) return fail(BDF_WOULD_PANIC, "max/min on an empty or all-null chunk: the reference unwraps None");
+    *is_some = col->chunks.empty() ? 0 : 1;
+    if (*is_some) memcpy(out_scalar, op == BDF_MIN ? &a.min : &a.max, (size_t)w);
+    return BDF_OK;
+}
+
+// avg (aggregate.rs:32-65): per-chunk mean from an exact/double sum and the valid count, then the
+// reference's weighted merge in chunk order.
+static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
+    const int dtype = col->dtype;
+    if (dtype == BDF_I64 || dtype == BDF_U64) return fail(BDF_UNSUPPORTED, "avg needs f64: From<T::Native>");
+    const int64_t n = (int64_t)col->chunks.size();
+    wait_groups(c->s_compute, col, 0, n);
+    double mean = 0.0;
+    int64_t count = 0;
+    for (int64_t k = 0; k < n; k += kAggSlots) {
+        const int64_t m = std::min<int64_t>(kAggSlots, n - k);
+        for (int64_t j = 0; j < m; j++) TRY(reduce_range(c, col, k + j, k + j + 1, (int)j));
+        CK(cudaMemcpyAsync(c->h_agg, c->d_agg, (size_t)m * sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaStreamSynchronize(c->s_compute));
+        for (int64_t j = 0; j < m; j++) {
+            const AggDev& a = c->h_agg[j];
+            const int64_t len = (int64_t)a.count;
+            double s;
+            if (dtype_is_float(dtype)) memcpy(&s, &a.sum_bits, 8);
+            else if (dtype_is_signed_int(dtype)) s = (double)(int64_t)a.sum_bits;
+            else s = (double)a.sum_bits;
+            const double mch = len ? s / (double)len : 0.0;
+            count += len;
+            mean = mean + ((mch - mean) * (double)len) / (double)count;
+        }
+    }
+    *is_some = count != 0;
+    *out = mean;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C ABI
+
+#define ENTER(ctx)                                                   \
+    if (!(ctx)) return fail(BDF_INVALID, "null context");           \
+    std::lock_guard<std::mutex> _lock((ctx)->mu);                    \
+    CK(cudaSetDevice((ctx)->device));
+
+extern "C" {
+
+int bdf_abi_version(void) { return BDF_ABI_VERSION; }
+
+const char* bdf_last_error(void) { return g_err.c_str(); }
+
+void bdf_destroy(bdf_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    if (c->s_compute) cudaStreamSynchronize(c->s_compute);
+    if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
+    if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    if (c->ring) cudaFreeHost(c->ring);
+    if (c->h_agg) cudaFreeHost(c->h_agg);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_agg) cudaFree(c->d_agg);
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_flag) cudaFree(c->d_flag);
+    if (c->flush_buf) cudaFree(c->flush_buf);
+    if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
+    if (c->ev_t0) cudaEventDestroy(c->ev_t0);
+    if (c->ev_t1) cudaEventDestroy(c->ev_t1);
+    if (c->s_compute) cudaStreamDestroy(c->s_compute);
+    if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
+    if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    delete c;
+}
+
+static int init_impl(bdf_ctx* c, int device) {
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0) {
+        cudaGetLastError();
+        return fail(BDF_CUDA, "no usable CUDA device (%s); this library has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n_dev) return fail(BDF_INVALID, "device %d out of range (0..%d)", device, n_dev - 1);
+    c->device = device;
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    c->sm_count = prop.multiProcessorCount; c->cc_major = prop.major; c->cc_minor = prop.minor; c->hbm_bytes = prop.totalGlobalMem;
+    if (prop.major != 10) return fail(BDF_CUDA, "device %d is sm_%d%d; libb200df is built for sm_100a only", device, prop.major, prop.minor);
+    CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CK(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t keep = ~0ull;  // keep freed arenas cached: operators allocate their outputs per call
+    CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    c->ring_cap = (size_t)8 << 20;
+    CK(cudaHostAlloc((void**)&c->ring, c->ring_cap, cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&c->h_agg, kAggSlots * sizeof(AggDev), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&c->h_flag, sizeof(int), cudaHostAllocDefault));
+    c->red_grid_cap = reduce_grid(c->sm_count);
+    CK(cudaMalloc((void**)&c->d_partials, (size_t)c->red_grid_cap * sizeof(AggDev)));
+    CK(cudaMalloc((void**)&c->d_agg, kAggSlots * sizeof(AggDev)));
+    CK(cudaMalloc((void**)&c->d_ticket, sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
+    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMemset(c->d_flag, 0, sizeof(int)));
+    CK(cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming));
+    CK(cudaEventCreate(&c->ev_t0));
+    CK(cudaEventCreate(&c->ev_t1));
+    const char* pb = getenv("BDF_PIPELINE_BYTES");
+    if (pb && atoll(pb) > 0) c->pipeline_bytes = (size_t)atoll(pb);
+    return BDF_OK;
+}
+
+int bdf_init(int device, bdf_ctx** out) {
+    if (!out) return fail(BDF_INVALID, "null out pointer");
+    *out = nullptr;
+    bdf_ctx* c = new (std::nothrow) bdf_ctx();
+    if (!c) return fail(BDF_OOM, "host allocation failed");
+    int st = init_impl(c, device);
+    if (st != BDF_OK) { std::string keep = g_err; bdf_destroy(c); g_err = keep; return st; }
+    *out = c;
+    return BDF_OK;
+}
+
+int bdf_synchronize(bdf_ctx* c) {
+    ENTER(c);
+    CK(cudaStreamSynchronize(c->s_h2d));
+    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(c->s_d2h));
+    return BDF_OK;
+}
+
+int bdf_device_info(bdf_ctx* c, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes) {
+    if (!c) return fail(BDF_INVALID, "null context");
+    if (sm_count) *sm_count = c->sm_count;
+    if (cc_major) *cc_major = c->cc_major;
+    if (cc_minor) *cc_minor = c->cc_minor;
+    if (hbm_bytes) *hbm_bytes = (int64_t)c->hbm_bytes;
+    return BDF_OK;
+}
+
+int bdf_host_alloc(bdf_ctx* c, size_t bytes, void** out) {
+    ENTER(c);
+    if (!out) return fail(BDF_INVALID, "null out pointer");
+    CK(cudaHostAlloc(out, bytes ? bytes : 1, cudaHostAllocDefault));
+    return BDF_OK;
+}
+int bdf_host_free(bdf_ctx* c, void* p) {
+    ENTER(c);
+    if (p) CK(cudaFreeHost(p));
+    return BDF_OK;
+}
+int bdf_host_register(bdf_ctx* c, void* p, size_t bytes) {
+    ENTER(c);
+    CK(cudaHostRegister(p, bytes, cudaHostRegisterDefault));
+    return BDF_OK;
+}
+int bdf_host_unregister(bdf_ctx* c, void* p) {
+    ENTER(c);
+    CK(cudaHostUnregister(p));
+    return BDF_OK;
+}
+
+// ---- device-resident API -----------------------------------------------------------------------
+
+int bdf_upload(bdf_ctx* c, int dtype, int64_t n_chunks, const bdf_view* in, int flags, bdf_col** out) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (!out || n_chunks < 0 || (n_chunks && !in)) return fail(BDF_INVALID, "bad arguments");
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n_chunks, in}}, (flags & BDF_ASYNC) != 0, cols));
+    *out = cols[0];
+    return BDF_OK;
+}
+
+int bdf_col_wait(bdf_ctx* c, const bdf_col* col) {
+    ENTER(c);
+    if (!col) return fail(BDF_INVALID, "null column");
+    for (auto& g : col->groups) CK(cudaEventSynchronize(g.ev));
+    return BDF_OK;
+}
+
+int bdf_col_describe(const bdf_col* col, int32_t* dtype, int64_t* n_chunks, int64_t* total_len) {
+    if (!col) return fail(BDF_INVALID, "null column");
+    if (dtype) *dtype = col->dtype;
+    if (n_chunks) *n_chunks = (int64_t)col->chunks.size();
+    if (total_len) *total_len = col->total_len;
+    return BDF_OK;
+}
+
+int bdf_col_chunk_info(bdf_ctx* c, const bdf_col* col, int64_t chunk, int64_t* len, int64_t* null_count, int32_t* has_validity) {
+    ENTER(c);
+    if (!col || chunk < 0 || chunk >= (int64_t)col->chunks.size()) return fail(BDF_INVALID, "bad chunk index");
+    if (len) *len = col->chunks[chunk].len;
+    if (has_validity) *has_validity = col->chunks[chunk].validity != nullptr;
+    if (null_count) {
+        TRY(ensure_null_counts(c, const_cast<bdf_col*>(col)));
+        *null_count = col->null_counts[chunk];
+    }
+    return BDF_OK;
+}
+
+int bdf_binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out) {
+    ENTER(c);
+    if (!l || !r || !out) return fail(BDF_INVALID, "null argument");
+    return binary_dev(c, op, l, r, out);
+}
+
+int bdf_unary_dev(bdf_ctx* c, int op, const bdf_col* in, bdf_col** out) {
+    ENTER(c);
+    if (!in || !out) return fail(BDF_INVALID, "null argument");
+    return map_dev(c, false, op, in, out);
+}
+
+int bdf_cast_dev(bdf_ctx* c, int to, const bdf_col* in, bdf_col** out) {
+    ENTER(c);
+    if (!in || !out) return fail(BDF_INVALID, "null argument");
+    return map_dev(c, true, to, in, out);
+}
+
+int bdf_aggregate_dev(bdf_ctx* c, int op, const bdf_col* in, void* out_scalar, int32_t* is_some) {
+    ENTER(c);
+    if (!in || !out_scalar || !is_some) return fail(BDF_INVALID, "null argument");
+    return aggregate_dev(c, op, const_cast<bdf_col*>(in), out_scalar, is_some);
+}
+
+int bdf_aggregate_all_dev(bdf_ctx* c, const bdf_col* in, bdf_agg4* out) {
+    ENTER(c);
+    if (!in || !out) return fail(BDF_INVALID, "null argument");
+    return aggregate_all_dev(c, const_cast<bdf_col*>(in), true, out);
+}
+
+int bdf_avg_dev(bdf_ctx* c, const bdf_col* in, double* out, int32_t* is_some) {
+    ENTER(c);
+    if (!in || !out || !is_some) return fail(BDF_INVALID, "null argument");
+    return avg_dev(c, const_cast<bdf_col*>(in), out, is_some);
+}
+
+int bdf_download(bdf_ctx* c, const bdf_col* col, bdf_out* out) {
+    ENTER(c);
+    if (!col || (!out && !col->chunks.empty())) return fail(BDF_INVALID, "null argument");
+    return download(c, const_cast<bdf_col*>(col), out);
+}
+
+void bdf_col_free(bdf_ctx* c, bdf_col* col) {
+    if (!c || !col) return;
+    std::lock_guard<std::mutex> lock(c->mu);
+    cudaSetDevice(c->device);
+    col_release(c, col);
+}
+
+// ---- host in / host out ------------------------------------------------------------------------
+
+int bdf_binary(bdf_ctx* c, int op, int dtype, int64_t n_left, const bdf_view* left, int64_t n_right, const bdf_view* right, bdf_out* out) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (n_left < 0 || n_right < 0 || (n_left && !left) || (n_right && !right)) return fail(BDF_INVALID, "bad arguments");
+    const int64_t n = std::min(n_left, n_right);
+    for (int64_t i = 0; i < n; i++)  // reject before moving a byte
+        if (left[i].len != right[i].len) return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length");
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n, left}, UploadSpec{dtype, n, right}}, true, cols));
+    bdf_col* o = nullptr;
+    int st = binary_dev(c, op, cols[0], cols[1], &o);
+    if (st == BDF_OK) st = download(c, o, out);
+    std::string keep = g_err;
+    cudaStreamSynchronize(c->s_h2d);  // host inputs must not be touched after return
+    col_release(c, o); col_release(c, cols[0]); col_release(c, cols[1]);
+    g_err = keep;
+    return st;
+}
+
+static int map_host(bdf_ctx* c, bool is_cast, int op_or_to, int dtype, int64_t n, const bdf_view* in, bdf_out* out) {
+    TRY(check_dtype(dtype));
+    if (n < 0 || (n && !in)) return fail(BDF_INVALID, "bad arguments");
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n, in}}, true, cols));
+    bdf_col* o = nullptr;
+    int st = map_dev(c, is_cast, op_or_to, cols[0], &o);
+    if (st == BDF_OK) st = download(c, o, out);
+    std::string keep = g_err;
+    cudaStreamSynchronize(c->s_h2d);
+    col_release(c, o); col_release(c, cols[0]);
+    g_err = keep;
+    return st;
+}
+
+int bdf_unary(bdf_ctx* c, int op, int dtype, int64_t n, const bdf_view* in, bdf_out* out) {
+    ENTER(c);
+    return map_host(c, false, op, dtype, n, in, out);
+}
+
+int bdf_cast(bdf_ctx* c, int from, int to, int64_t n, const bdf_view* in, bdf_out* out) {
+    ENTER(c);
+    return map_host(c, true, to, from, n, in, out);
+}
+
+int bdf_aggregate(bdf_ctx* c, int op, int dtype, int64_t n, const bdf_view* in, void* out_scalar, int32_t* is_some) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (n < 0 || (n && !in) || !out_scalar || !is_some) return fail(BDF_INVALID, "bad arguments");
+    if (op == BDF_COUNT) {  // metadata only when every null_count is known: no bytes move
+        bool known = true;
+        int64_t total = 0;
+        for (int64_t i = 0; i < n; i++) {
+            if (in[i].validity && in[i].null_count < 0) known = false;
+            total += in[i].len - (in[i].validity ? in[i].null_count : 0);
+        }
+        if (known) { *(int64_t*)out_scalar = total; *is_some = 1; return BDF_OK; }
+    }
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n, in}}, true, cols));
+    int st = aggregate_dev(c, op, cols[0], out_scalar, is_some);
+    std::string keep = g_err;
+    cudaStreamSynchronize(c->s_h2d);
+    col_release(c, cols[0]);
+    g_err = keep;
+    return st;
+}
+
+int bdf_aggregate_all(bdf_ctx* c, int dtype, int64_t n, const bdf_view* in, bdf_agg4* out) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (n < 0 || (n && !in) || !out) return fail(BDF_INVALID, "bad arguments");
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n, in}}, true, cols));
+    int st = aggregate_all_dev(c, cols[0], true, out);
+    std::string keep = g_err;
+    cudaStreamSynchronize(c->s_h2d);
+    col_release(c, cols[0]);
+    g_err = keep;
+    return st;
+}
+
+int bdf_avg(bdf_ctx* c, int dtype, int64_t n, const bdf_view* in, double* out, int32_t* is_some) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (n < 0 || (n && !in) || !out || !is_some) return fail(BDF_INVALID, "bad arguments");
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, {UploadSpec{dtype, n, in}}, true, cols));
+    int st = avg_dev(c, cols[0], out, is_some);
+    std::string keep = g_err;
+    cudaStreamSynchronize(c->s_h2d);
+    col_release(c, cols[0]);
+    g_err = keep;
+    return st;
+}
+
+// ---- measurement support -------------------------------------------------------------------------
+
+int bdf_profile_enable(bdf_ctx* c, int on) {
+    ENTER(c);
+    c->profiling = on != 0;
+    return BDF_OK;
+}
+
+int bdf_profile_read(bdf_ctx* c, bdf_launch_record* buf, int64_t cap, int64_t* n) {
+    ENTER(c);
+    CK(cudaStreamSynchronize(c->s_compute));
+    int64_t k = 0;
+    for (auto& p : c->prof) {
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, p.e0, p.e1);
+        p.rec.ms = ms;
+        if (buf && k < cap) buf[k++] = p.rec;
+        cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+    }
+    c->prof.clear();
+    if (n) *n = k;
+    return BDF_OK;
+}
+
+int64_t bdf_launch_count(bdf_ctx* c) { return c ? c->launches : 0; }
+
+int bdf_timer_start(bdf_ctx* c) {
+    ENTER(c);
+    CK(cudaEventRecord(c->ev_t0, c->s_compute));
+    return BDF_OK;
+}
+
+int bdf_timer_stop(bdf_ctx* c, float* ms) {
+    ENTER(c);
+    CK(cudaEventRecord(c->ev_t1, c->s_compute));
+    CK(cudaEventSynchronize(c->ev_t1));
+    if (ms) CK(cudaEventElapsedTime(ms, c->ev_t0, c->ev_t1));
+    return BDF_OK;
+}
+
+int bdf_flush_l2(bdf_ctx* c, size_t bytes) {
+    ENTER(c);
+    if (bytes > c->flush_bytes) {
+        if (c->flush_buf) CK(cudaFree(c->flush_buf));
+        c->flush_buf = nullptr; c->flush_bytes = 0;
+        CK(cudaMalloc(&c->flush_buf, bytes));
+        c->flush_bytes = bytes;
+    }
+    CK(launch_fill(c->flush_buf, bytes, c->s_compute));
+    return BDF_OK;
+}
+
+int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col_id, int64_t n_chunks,
+                 const int64_t* chunk_lens, int64_t row0, uint32_t null_mod, bdf_col** out) {
+    ENTER(c);
+    TRY(check_dtype(dtype));
+    if (!out || n_chunks < 0 || (n_chunks && !chunk_lens) || kind < 0 || kind > 3) return fail(BDF_INVALID, "bad arguments");
+    std::vector<ChunkPlan> plan((size_t)n_chunks);
+    for (int64_t i = 0; i < n_chunks; i++) {
+        if (chunk_lens[i] < 0) return fail(BDF_INVALID, "negative chunk length");
+        plan[i] = {chunk_lens[i], null_mod != 0};
+    }
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, dtype, plan, nullptr, &o));
+    o->counts_on_device = true;
+    const int tile = elems_per_tile(dtype);
+    void* hp = nullptr;
+    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n_chunks) * sizeof(GenDesc), &hp);
+    cudaError_t e = cudaSuccess;
+    GenDesc* dd = nullptr;
+    if (st == BDF_OK) {
+        GenDesc* hd = (GenDesc*)hp;
+        int64_t tiles = 0, rows = 0;
+        for (int64_t i = 0; i < n_chunks; i++) {
+            hd[i] = GenDesc{o->chunks[i].values, o->chunks[i].validity, chunk_lens[i], tiles, row0 + rows};
+            tiles += (chunk_lens[i] + tile - 1) / tile;
+            rows += chunk_lens[i];
+        }
+        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n_chunks) * sizeof(GenDesc), c->s_compute);
+        if (e == cudaSuccess && n_chunks) e = cudaMemcpyAsync(dd, hd, (size_t)n_chunks * sizeof(GenDesc), cudaMemcpyHostToDevice, c->s_compute);
+        if (e == cudaSuccess) {
+            LaunchTimer t(c, BDF_K_GENERATE, dtype, rows, rows * dtype_width(dtype));
+            e = launch_generate(dtype, kind, lo, hi, seed, col_id, null_mod, dd, (int)n_chunks, tiles, o->d_valid_counts, c->s_compute);
+        }
+        if (dd) cudaFreeAsync(dd, c->s_compute);
+        if (e == cudaSuccess) {
+            Group g{0, n_chunks, nullptr};
+            e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
+            o->groups.push_back(g);
+        }
+    }
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "generate failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+}  // extern "C"
