@@ -33,6 +33,9 @@ template <typename T> __device__ __forceinline__ constexpr uint64_t uint_max_of(
 }
 
 // num::cast::cast::<F,T>(v): returns false for None.
+template <typename F, typename T> struct SameType { static constexpr bool value = false; };
+template <typename T> struct SameType<T, T> { static constexpr bool value = true; };
+
 template <typename F, typename T>
 __device__ __forceinline__ bool cast_one(F v, T& out) {
     if constexpr (NumInfo<T>::is_float) {
@@ -105,7 +108,7 @@ k_cast(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __res
             for (int e = 0; e < E; e++) {
                 T y;
                 const bool good = cast_one<F, T>(x[j].e[e], y) && ((m[j] >> e) & 1u);
-                r.e[e] = good ? y : (T)0;
+                r.e[e] = (good || SameType<F, T>::value) ? y : (T)0;  // same type = clone: payloads survive
                 ok |= (good ? 1u : 0u) << e;
             }
             r.store(po + e0);
@@ -127,7 +130,7 @@ k_cast(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __res
                 if ((in_range >> e) & 1u) {
                     T y;
                     const bool good = cast_one<F, T>(pi[e0 + e], y) && ((m >> e) & 1u);
-                    po[e0 + e] = good ? y : (T)0;
+                    po[e0 + e] = (good || SameType<F, T>::value) ? y : (T)0;
                     ok |= (good ? 1u : 0u) << e;
                 }
             }

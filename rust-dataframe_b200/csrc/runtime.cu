@@ -414,7 +414,7 @@ static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         const DevChunk& ch = col->chunks[i];
         if (out[i].len != ch.len) return fail(BDF_INVALID, "output chunk %lld has capacity %lld, result has %lld rows", (long long)i, (long long)out[i].len, (long long)ch.len);
         if (ch.len && !out[i].values) return fail(BDF_INVALID, "output chunk %lld has no values buffer", (long long)i);
-        if (ch.validity && !out[i].validity) return fail(BDF_INVALID, "output chunk %lld needs a validity buffer", (long long)i);
+        if (ch.validity && ch.len && !out[i].validity) return fail(BDF_INVALID, "output chunk %lld needs a validity buffer", (long long)i);
     }
     std::vector<unsigned long long> counts((size_t)n);
     for (auto& g : col->groups) {
