@@ -101,6 +101,7 @@ typedef struct {
 
 typedef struct bdf_ctx bdf_ctx;
 typedef struct bdf_col bdf_col;
+typedef struct bdf_future bdf_future; /* an aggregate whose kernels are enqueued but not yet waited for */
 
 /* ---- lifecycle ------------------------------------------------------------------------------ */
 int          bdf_abi_version(void);
@@ -132,6 +133,10 @@ int bdf_avg(bdf_ctx* ctx, int dtype, int64_t n_chunks, const bdf_view* in, doubl
 #define BDF_ASYNC 1 /* bdf_upload returns before the copies finish: host buffers must stay valid and
                        unmodified until bdf_col_wait / bdf_synchronize / a download of a dependent column */
 int  bdf_upload(bdf_ctx* ctx, int dtype, int64_t n_chunks, const bdf_view* in, int flags, bdf_col** out);
+/* Several columns in one call, copies issued chunk-major (a0,b0,a1,b1,...) so that an operator over them
+ * can start on chunk i as soon as ITS inputs have landed while later chunks are still crossing PCIe. */
+int  bdf_upload_many(bdf_ctx* ctx, int64_t n_cols, const int32_t* dtypes, const int64_t* n_chunks,
+                     const bdf_view* const* in, int flags, bdf_col** out /* n_cols entries */);
 int  bdf_col_wait(bdf_ctx* ctx, const bdf_col* col);
 int  bdf_col_describe(const bdf_col* col, int32_t* dtype, int64_t* n_chunks, int64_t* total_len);
 int  bdf_col_chunk_info(bdf_ctx* ctx, const bdf_col* col, int64_t chunk, int64_t* len, int64_t* null_count,
@@ -143,6 +148,20 @@ int  bdf_aggregate_dev(bdf_ctx* ctx, int op, const bdf_col* in, void* out_scalar
 int  bdf_aggregate_all_dev(bdf_ctx* ctx, const bdf_col* in, bdf_agg4* out);
 int  bdf_avg_dev(bdf_ctx* ctx, const bdf_col* in, double* out, int32_t* is_some);
 int  bdf_download(bdf_ctx* ctx, const bdf_col* col, bdf_out* out /* n_chunks entries */);
+/* Split download: _begin enqueues the device->host copies (they start as soon as each chunk group is
+ * ready), _end waits for them and fills len / null_count / has_validity.  Same `out` array for both. */
+int  bdf_download_begin(bdf_ctx* ctx, const bdf_col* col, bdf_out* out);
+int  bdf_download_end(bdf_ctx* ctx, const bdf_col* col, bdf_out* out);
+/* Fused operator + aggregate: out = left (op) right AND sum/min/max/count of `out`,
+ * computed while `out` is being written -- one pass, 3 x width bytes/row instead of 4 x.  op in
+ * {ADD,SUB,MUL,DIV}.  The column is materialised exactly as bdf_binary_dev would.  agg->would_panic is
+ * not evaluated here (always 0); use bdf_aggregate_dev for the reference's unwrap() behaviour. */
+int  bdf_binary_agg_dev(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, bdf_col** out, bdf_agg4* agg);
+/* Asynchronous aggregates: the call enqueues the kernels and returns a future; bdf_future_wait blocks until
+ * the result has reached the host, converts it and CONSUMES the future (out may be NULL to discard). */
+int  bdf_binary_agg_dev_async(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, bdf_col** out, bdf_future** fut);
+int  bdf_aggregate_all_dev_async(bdf_ctx* ctx, const bdf_col* in, bdf_future** fut);
+int  bdf_future_wait(bdf_ctx* ctx, bdf_future* fut, bdf_agg4* out);
 void bdf_col_free(bdf_ctx* ctx, bdf_col* col);
 
 /* ---- measurement support ------------------------------------------------------------------------ */

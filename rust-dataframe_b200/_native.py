@@ -97,6 +97,7 @@ def lib() -> C.CDLL:
         "bdf_aggregate_all": ([vp, C.c_int, i64, P(View), P(Agg4)], C.c_int),
         "bdf_avg": ([vp, C.c_int, i64, P(View), P(C.c_double), P(i32)], C.c_int),
         "bdf_upload": ([vp, C.c_int, i64, P(View), C.c_int, P(vp)], C.c_int),
+        "bdf_upload_many": ([vp, i64, P(i32), P(i64), P(P(View)), C.c_int, P(vp)], C.c_int),
         "bdf_col_wait": ([vp, vp], C.c_int),
         "bdf_col_describe": ([vp, P(i32), P(i64), P(i64)], C.c_int),
         "bdf_col_chunk_info": ([vp, vp, i64, P(i64), P(i64), P(i32)], C.c_int),
@@ -107,6 +108,12 @@ def lib() -> C.CDLL:
         "bdf_aggregate_all_dev": ([vp, vp, P(Agg4)], C.c_int),
         "bdf_avg_dev": ([vp, vp, P(C.c_double), P(i32)], C.c_int),
         "bdf_download": ([vp, vp, P(Out)], C.c_int),
+        "bdf_download_begin": ([vp, vp, P(Out)], C.c_int),
+        "bdf_download_end": ([vp, vp, P(Out)], C.c_int),
+        "bdf_binary_agg_dev": ([vp, C.c_int, vp, vp, P(vp), P(Agg4)], C.c_int),
+        "bdf_binary_agg_dev_async": ([vp, C.c_int, vp, vp, P(vp), P(vp)], C.c_int),
+        "bdf_aggregate_all_dev_async": ([vp, vp, P(vp)], C.c_int),
+        "bdf_future_wait": ([vp, vp, P(Agg4)], C.c_int),
         "bdf_col_free": ([vp, vp], None),
         "bdf_profile_enable": ([vp, C.c_int], C.c_int),
         "bdf_profile_read": ([vp, P(LaunchRecord), i64, P(i64)], C.c_int),
@@ -130,9 +137,10 @@ def lib() -> C.CDLL:
 EXPORTED_SYMBOLS = [
     "bdf_abi_version", "bdf_last_error", "bdf_init", "bdf_destroy", "bdf_synchronize", "bdf_device_info",
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
-    "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_col_wait", "bdf_col_describe",
+    "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_upload_many", "bdf_col_wait", "bdf_col_describe",
     "bdf_col_chunk_info", "bdf_binary_dev", "bdf_unary_dev", "bdf_cast_dev", "bdf_aggregate_dev",
-    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_download", "bdf_col_free", "bdf_profile_enable", "bdf_profile_read",
+    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
+    "bdf_binary_agg_dev", "bdf_binary_agg_dev_async", "bdf_aggregate_all_dev_async", "bdf_future_wait", "bdf_col_free", "bdf_profile_enable", "bdf_profile_read",
     "bdf_launch_count", "bdf_timer_start", "bdf_timer_stop", "bdf_flush_l2", "bdf_generate",
 ]
 

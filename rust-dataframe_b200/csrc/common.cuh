@@ -200,8 +200,12 @@ struct AggDev {
 // ---- launchers (defined in k_*.cu) ---------------------------------------------------------------
 int elems_per_tile(int dtype);                 // tile size in elements for arrays of dtype
 int elems_per_tile_cast(int from, int to);
+// tile_partials != nullptr (add/sub/mul/div only): also write one AggDev per tile with the aggregate of the
+// OUTPUT (K5); fold them with launch_finish.  Integer min/max partials are unsigned keys (value ^ sign flip).
 cudaError_t launch_binary(int op, int dtype, const BinDesc* d_descs, int n_chunks, int64_t total_tiles,
-                          unsigned long long* d_valid_counts, int* d_flags, cudaStream_t s);
+                          unsigned long long* d_valid_counts, int* d_flags, cudaStream_t s, AggDev* tile_partials = nullptr);
+cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, int sm_count, AggDev* stage, unsigned int* ticket,
+                          AggDev* result, cudaStream_t s);
 cudaError_t launch_unary(int op, int dtype, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
                          unsigned long long* d_valid_counts, cudaStream_t s);
 cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,

@@ -75,10 +75,42 @@ __device__ __forceinline__ T bin_apply(T a, T b, bool valid, bool& divzero) {
     }
 }
 
-template <typename T, int OP>
+// ---- K5: aggregate of the OUTPUT fused into the same pass (sum/min/max/count of c while c is written) ----
+// Integers: wrapping 64-bit sum of the zero-extended values (only the low sizeof(T) bytes are meaningful),
+// min/max over order-preserving unsigned keys (value ^ sign flip).  Floats: sum in double.  One partial per
+// CTA (= per tile) in tile order; k_finish folds them in a fixed order => deterministic.
+template <typename T, bool F = IsFloat<T>::value> struct FusedAgg;
+template <typename T> struct FusedAgg<T, false> {
+    unsigned long long sum, kmin, kmax;
+    __device__ __forceinline__ void init() { sum = 0; kmin = ~0ull; kmax = 0; }
+    __device__ __forceinline__ void add(T x, bool valid, unsigned long long flip) {
+        using U = typename UnsignedOf<T>::type;
+        const unsigned long long z = (unsigned long long)(U)x;
+        if (valid) { sum += z; const unsigned long long k = z ^ flip; kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
+    }
+    __device__ __forceinline__ void merge_shfl(int o) {
+        const unsigned long long s2 = __shfl_xor_sync(0xffffffffu, sum, o), a2 = __shfl_xor_sync(0xffffffffu, kmin, o),
+                                 b2 = __shfl_xor_sync(0xffffffffu, kmax, o);
+        sum += s2; kmin = a2 < kmin ? a2 : kmin; kmax = b2 > kmax ? b2 : kmax;
+    }
+    __device__ __forceinline__ void merge(const FusedAgg& o) { sum += o.sum; kmin = o.kmin < kmin ? o.kmin : kmin; kmax = o.kmax > kmax ? o.kmax : kmax; }
+    __device__ __forceinline__ void store(AggDev* d, unsigned long long cnt) const { d->sum_bits = sum; d->min_bits = kmin; d->max_bits = kmax; d->count = cnt; }
+};
+template <typename T> struct FusedAgg<T, true> {
+    double sum;
+    __device__ __forceinline__ void init() { sum = 0.0; }
+    __device__ __forceinline__ void add(T x, bool valid, unsigned long long) { sum = __dadd_rn(sum, valid ? (double)x : 0.0); }
+    __device__ __forceinline__ void merge_shfl(int o) { sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o)); }
+    __device__ __forceinline__ void merge(const FusedAgg& o) { sum = __dadd_rn(sum, o.sum); }
+    __device__ __forceinline__ void store(AggDev* d, unsigned long long cnt) const {
+        d->sum_bits = (unsigned long long)__double_as_longlong(sum); d->min_bits = ~0ull; d->max_bits = 0; d->count = cnt;
+    }
+};
+
+template <typename T, int OP, bool AGG>
 __global__ void __launch_bounds__(kThreads)
 k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __restrict__ valid_counts,
-         int* __restrict__ flags) {
+         int* __restrict__ flags, AggDev* __restrict__ tile_partials, unsigned long long flip) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr uint32_t FULLMASK = (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
@@ -98,6 +130,8 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
 
     unsigned int nvalid = 0;
     bool divzero = false;
+    FusedAgg<T> agg;
+    if constexpr (AGG) agg.init();
 
     if (base + TILE <= len) {
         // ---- full tile: 2 x kUnroll 16-byte loads in flight per thread before first use ----
@@ -121,12 +155,13 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             Vec<T, E> r;
 #pragma unroll
-            for (int e = 0; e < E; e++) r.e[e] = bin_apply<T, OP>(a[j].e[e], b[j].e[e], (m[j] >> e) & 1u, divzero);
-            r.store(po + e0);
-            if (vo) {
-                store_bits<E>(vo, e0, m[j], true);
-                nvalid += __popc(m[j]);
+            for (int e = 0; e < E; e++) {
+                r.e[e] = bin_apply<T, OP>(a[j].e[e], b[j].e[e], (m[j] >> e) & 1u, divzero);
+                if constexpr (AGG) agg.add(r.e[e], (m[j] >> e) & 1u, flip);
             }
+            r.store(po + e0);
+            if (vo) store_bits<E>(vo, e0, m[j], true);
+            if (vo || AGG) nvalid += __popc(m[j]);
         }
     } else {
         // ---- tail tile of the chunk: element-wise guards ----
@@ -143,82 +178,175 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
             for (int e = 0; e < E; e++) {
                 if ((in_range >> e) & 1u) {
                     const T x = pa[e0 + e], y = pb[e0 + e];
-                    po[e0 + e] = bin_apply<T, OP>(x, y, (m >> e) & 1u, divzero);
+                    const T z = bin_apply<T, OP>(x, y, (m >> e) & 1u, divzero);
+                    po[e0 + e] = z;
+                    if constexpr (AGG) agg.add(z, (m >> e) & 1u, flip);
                 }
             }
-            if (vo) {
-                store_bits<E>(vo, e0, m, in_range != 0);
-                nvalid += __popc(m);
-            }
+            if (vo) store_bits<E>(vo, e0, m, in_range != 0);
+            if (vo || AGG) nvalid += __popc(m);
         }
     }
 
-    if (vo) {
+    if (vo || AGG) {
         const unsigned long long total = block_sum_u64(nvalid, s_red);
-        if (threadIdx.x == 0) atomicAdd(&valid_counts[c], total);
+        if (threadIdx.x == 0 && vo) atomicAdd(&valid_counts[c], total);
+        if constexpr (AGG) {
+            // fixed xor-shuffle tree inside each warp, then warp 0 folds the 8 warp results in warp order
+            __shared__ FusedAgg<T> s_agg[kThreads / 32];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) agg.merge_shfl(o);
+            if ((threadIdx.x & 31) == 0) s_agg[threadIdx.x >> 5] = agg;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                FusedAgg<T> t = s_agg[0];
+#pragma unroll
+                for (int w = 1; w < kThreads / 32; w++) t.merge(s_agg[w]);
+                t.store(&tile_partials[blockIdx.x], total);
+            }
+        }
     }
     if constexpr (OP == OP_DIV) {
         if (divzero) atomicOr(flags, 1);
     }
 }
 
+// Folds per-tile partials into one result.  Grid and per-thread assignment are fixed => deterministic.
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(kThreads)
+k_finish(const AggDev* __restrict__ parts, long long n_parts, AggDev* __restrict__ stage, unsigned int* __restrict__ ticket,
+         AggDev* __restrict__ result) {
+    __shared__ AggDev s_part[kThreads / 32];
+    __shared__ bool s_last;
+    auto ident = [] { AggDev a; a.sum_bits = 0; a.min_bits = ~0ull; a.max_bits = 0; a.count = 0; return a; };
+    auto merge = [](AggDev& a, const AggDev& b) {
+        if constexpr (IS_FLOAT)
+            a.sum_bits = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a.sum_bits), __longlong_as_double((long long)b.sum_bits)));
+        else a.sum_bits += b.sum_bits;
+        a.min_bits = b.min_bits < a.min_bits ? b.min_bits : a.min_bits;
+        a.max_bits = b.max_bits > a.max_bits ? b.max_bits : a.max_bits;
+        a.count += b.count;
+    };
+    auto shfl = [](const AggDev& a, int o) {
+        AggDev r;
+        r.sum_bits = __shfl_xor_sync(0xffffffffu, a.sum_bits, o); r.min_bits = __shfl_xor_sync(0xffffffffu, a.min_bits, o);
+        r.max_bits = __shfl_xor_sync(0xffffffffu, a.max_bits, o); r.count = __shfl_xor_sync(0xffffffffu, a.count, o);
+        return r;
+    };
+    auto block_fold = [&](AggDev v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { AggDev t = shfl(v, o); merge(v, t); }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+        __syncthreads();
+        AggDev r = s_part[0];
+        for (int w = 1; w < kThreads / 32; w++) merge(r, s_part[w]);
+        return r;  // identical in every thread
+    };
+    AggDev acc = ident();
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_parts; i += (long long)gridDim.x * kThreads) {
+        AggDev p;
+        p.sum_bits = __ldcg(&parts[i].sum_bits); p.min_bits = __ldcg(&parts[i].min_bits);
+        p.max_bits = __ldcg(&parts[i].max_bits); p.count = __ldcg(&parts[i].count);
+        merge(acc, p);
+    }
+    acc = block_fold(acc);
+    if (threadIdx.x == 0) {
+        stage[blockIdx.x] = acc;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    AggDev fin = ident();
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
+        AggDev p;
+        p.sum_bits = __ldcg(&stage[i].sum_bits); p.min_bits = __ldcg(&stage[i].min_bits);
+        p.max_bits = __ldcg(&stage[i].max_bits); p.count = __ldcg(&stage[i].count);
+        merge(fin, p);
+    }
+    fin = block_fold(fin);
+    if (threadIdx.x == 0) { *result = fin; *ticket = 0; }
+}
+
+cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, int sm_count, AggDev* stage, unsigned int* ticket,
+                          AggDev* result, cudaStream_t s) {
+    int64_t grid = (n_parts + 4 * kThreads - 1) / (4 * kThreads);
+    if (grid > sm_count) grid = sm_count;
+    if (grid < 1) grid = 1;
+    if (is_float) k_finish<true><<<(unsigned)grid, kThreads, 0, s>>>(parts, n_parts, stage, ticket, result);
+    else k_finish<false><<<(unsigned)grid, kThreads, 0, s>>>(parts, n_parts, stage, ticket, result);
+    return cudaGetLastError();
+}
+
 int elems_per_tile(int dtype) { return kTileBytes / dtype_width(dtype); }
 
+struct AggArgs { AggDev* partials; unsigned long long flip; };
+
 template <typename T, int OP>
-static cudaError_t launch_one(const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags, cudaStream_t s) {
-    k_binary<T, OP><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags);
+static cudaError_t launch_one(const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags, cudaStream_t s, AggArgs ag) {
+    if constexpr (OP <= OP_DIV) {
+        if (ag.partials) {
+            k_binary<T, OP, true><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, ag.partials, ag.flip);
+            return cudaGetLastError();
+        }
+    }
+    k_binary<T, OP, false><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, nullptr, 0ull);
     return cudaGetLastError();
 }
 
 template <typename T>
 static cudaError_t launch_wrapping(int op, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
-                                   cudaStream_t s) {
+                                   cudaStream_t s, AggArgs ag) {
     switch (op) {
-        case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s);
-        case OP_SUB: return launch_one<T, OP_SUB>(d, n, tiles, vc, flags, s);
-        default: return launch_one<T, OP_MUL>(d, n, tiles, vc, flags, s);
+        case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s, ag);
+        case OP_SUB: return launch_one<T, OP_SUB>(d, n, tiles, vc, flags, s, ag);
+        default: return launch_one<T, OP_MUL>(d, n, tiles, vc, flags, s, ag);
     }
 }
 
 template <typename T>
 static cudaError_t launch_float(int op, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
-                                cudaStream_t s) {
+                                cudaStream_t s, AggArgs ag) {
     switch (op) {
-        case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s);
-        case OP_SUB: return launch_one<T, OP_SUB>(d, n, tiles, vc, flags, s);
-        case OP_MUL: return launch_one<T, OP_MUL>(d, n, tiles, vc, flags, s);
-        case OP_DIV: return launch_one<T, OP_DIV>(d, n, tiles, vc, flags, s);
-        case OP_ATAN2: return launch_one<T, OP_ATAN2>(d, n, tiles, vc, flags, s);
-        case OP_HYPOT: return launch_one<T, OP_HYPOT>(d, n, tiles, vc, flags, s);
-        default: return launch_one<T, OP_LOG>(d, n, tiles, vc, flags, s);
+        case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s, ag);
+        case OP_SUB: return launch_one<T, OP_SUB>(d, n, tiles, vc, flags, s, ag);
+        case OP_MUL: return launch_one<T, OP_MUL>(d, n, tiles, vc, flags, s, ag);
+        case OP_DIV: return launch_one<T, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+        case OP_ATAN2: return launch_one<T, OP_ATAN2>(d, n, tiles, vc, flags, s, ag);
+        case OP_HYPOT: return launch_one<T, OP_HYPOT>(d, n, tiles, vc, flags, s, ag);
+        default: return launch_one<T, OP_LOG>(d, n, tiles, vc, flags, s, ag);
     }
 }
 
 cudaError_t launch_binary(int op, int dtype, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
-                          cudaStream_t s) {
+                          cudaStream_t s, AggDev* tile_partials) {
+    const int bits = 8 * dtype_width(dtype);
+    AggArgs ag{tile_partials, dtype_is_signed_int(dtype) ? (1ull << (bits - 1)) : 0ull};
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    if (dtype == T_F64) return launch_float<double>(op, d, n, tiles, vc, flags, s);
-    if (dtype == T_F32) return launch_float<float>(op, d, n, tiles, vc, flags, s);
+    if (dtype == T_F64) return launch_float<double>(op, d, n, tiles, vc, flags, s, ag);
+    if (dtype == T_F32) return launch_float<float>(op, d, n, tiles, vc, flags, s, ag);
     if (op > OP_DIV) return cudaErrorInvalidValue;
     if (op == OP_DIV) {
         switch (dtype) {
-            case T_I8: return launch_one<int8_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_I16: return launch_one<int16_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_I32: return launch_one<int32_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_I64: return launch_one<int64_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_U8: return launch_one<uint8_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_U16: return launch_one<uint16_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            case T_U32: return launch_one<uint32_t, OP_DIV>(d, n, tiles, vc, flags, s);
-            default: return launch_one<uint64_t, OP_DIV>(d, n, tiles, vc, flags, s);
+            case T_I8: return launch_one<int8_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_I16: return launch_one<int16_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_I32: return launch_one<int32_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_I64: return launch_one<int64_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_U8: return launch_one<uint8_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_U16: return launch_one<uint16_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            case T_U32: return launch_one<uint32_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
+            default: return launch_one<uint64_t, OP_DIV>(d, n, tiles, vc, flags, s, ag);
         }
     }
     // add/sub/mul wrap: identical bits for signed and unsigned -> one instantiation per width
     switch (dtype_width(dtype)) {
-        case 1: return launch_wrapping<uint8_t>(op, d, n, tiles, vc, flags, s);
-        case 2: return launch_wrapping<uint16_t>(op, d, n, tiles, vc, flags, s);
-        case 4: return launch_wrapping<uint32_t>(op, d, n, tiles, vc, flags, s);
-        default: return launch_wrapping<uint64_t>(op, d, n, tiles, vc, flags, s);
+        case 1: return launch_wrapping<uint8_t>(op, d, n, tiles, vc, flags, s, ag);
+        case 2: return launch_wrapping<uint16_t>(op, d, n, tiles, vc, flags, s, ag);
+        case 4: return launch_wrapping<uint32_t>(op, d, n, tiles, vc, flags, s, ag);
+        default: return launch_wrapping<uint64_t>(op, d, n, tiles, vc, flags, s, ag);
     }
 }
 

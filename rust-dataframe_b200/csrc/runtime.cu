@@ -78,6 +78,17 @@ struct bdf_col {
     bool counts_on_device = false;                 // d_valid_counts not yet mirrored into null_counts
     std::vector<int64_t> null_counts;              // -1 = unknown
     std::vector<Group> groups;
+    std::vector<unsigned long long> dl_counts;     // staging of d_valid_counts during a split download
+    bdf_col* dl_tmp = nullptr;                     // re-aligned copy used by a split download of a sliced column
+};
+
+// Result of an aggregate that is still in flight (or done): a pinned slot + the event that guards it.
+struct bdf_future {
+    int dtype;
+    int fused;       // 1: partials use order-preserving unsigned keys for min/max (k_binary AGG), 0: k_reduce format
+    int slot;        // index into h_agg / d_agg
+    int64_t rows;
+    cudaEvent_t ev;
 };
 
 struct ProfEntry {
@@ -92,15 +103,19 @@ struct bdf_ctx {
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
     std::mutex mu;
     // pinned staging: descriptor ring + small result area
-    char* ring = nullptr;
+    char* ring = nullptr;           // pinned host side of the descriptor ring
+    char* dring = nullptr;          // device side, same offsets
     size_t ring_cap = 0, ring_head = 0;
+    std::vector<cudaEvent_t> ev_pool;  // recycled cudaEventDisableTiming events
     AggDev* h_agg = nullptr;        // pinned, kAggSlots entries
     int* h_flag = nullptr;          // pinned
     // device scratch
     AggDev* d_partials = nullptr;
     AggDev* d_agg = nullptr;        // kAggSlots entries
-    unsigned int* d_ticket = nullptr;
+    unsigned int* d_ticket = nullptr;   // [0]: k_reduce, [1]: k_finish
+    AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
+    int fut_next = 0;                   // ring cursor over the future half of h_agg / d_agg
     int red_grid_cap = 0;
     cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void* flush_buf = nullptr;
@@ -121,17 +136,26 @@ static int check_dtype(int t) {
     return BDF_OK;
 }
 
-static int ring_alloc(bdf_ctx* c, size_t bytes, void** out) {
-    bytes = align_up(bytes, 64);
+// Descriptor ring: host writes descriptors into pinned memory, one async copy moves them to the same offset
+// of the device ring, kernels read them there.  No per-call allocation.
+static int ring_alloc(bdf_ctx* c, size_t bytes, void** host, void** dev) {
+    bytes = align_up(std::max<size_t>(bytes, 1), 256);
     if (bytes > c->ring_cap) return fail(BDF_OOM, "descriptor ring too small for %zu bytes", bytes);
     if (c->ring_head + bytes > c->ring_cap) {
         CK(cudaStreamSynchronize(c->s_compute));  // everything that read the ring has finished
         c->ring_head = 0;
     }
-    *out = c->ring + c->ring_head;
+    *host = c->ring + c->ring_head;
+    *dev = c->dring + c->ring_head;
     c->ring_head += bytes;
     return BDF_OK;
 }
+
+static cudaError_t ev_get(bdf_ctx* c, cudaEvent_t* ev) {
+    if (!c->ev_pool.empty()) { *ev = c->ev_pool.back(); c->ev_pool.pop_back(); return cudaSuccess; }
+    return cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+}
+static void ev_put(bdf_ctx* c, cudaEvent_t ev) { if (ev) c->ev_pool.push_back(ev); }
 
 struct LaunchTimer {  // brackets one launch with events when profiling is on
     bdf_ctx* c;
@@ -151,19 +175,21 @@ struct LaunchTimer {  // brackets one launch with events when profiling is on
     }
 };
 
-static void col_destroy_host(bdf_col* col) {
-    for (auto& g : col->groups) if (g.ev) cudaEventDestroy(g.ev);
+static void col_destroy_host(bdf_ctx* c, bdf_col* col) {
+    for (auto& g : col->groups) ev_put(c, g.ev);
     delete col;
 }
 
 // Free device memory of a column in stream order on the compute stream.
 static void col_release(bdf_ctx* c, bdf_col* col) {
     if (!col) return;
+    if (col->dl_tmp) { cudaStreamSynchronize(c->s_d2h); col_release(c, col->dl_tmp); col->dl_tmp = nullptr; }
+    if (!col->dl_counts.empty()) cudaStreamSynchronize(c->s_d2h);  // a split download is still writing into it
     for (auto& g : col->groups) if (g.ev) cudaStreamWaitEvent(c->s_compute, g.ev, 0);
     if (col->arena_values) cudaFreeAsync(col->arena_values, c->s_compute);
     if (col->arena_validity) cudaFreeAsync(col->arena_validity, c->s_compute);
     if (col->d_valid_counts) cudaFreeAsync(col->d_valid_counts, c->s_compute);
-    col_destroy_host(col);
+    col_destroy_host(c, col);
 }
 
 struct ChunkPlan {
@@ -194,9 +220,9 @@ static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, 
     cudaError_t e = cudaSuccess;
     if (vbytes) e = cudaMallocAsync((void**)&col->arena_values, vbytes, c->s_compute);
     if (e == cudaSuccess && bbytes) e = cudaMallocAsync((void**)&col->arena_validity, bbytes, c->s_compute);
-    if (e == cudaSuccess && n) e = cudaMallocAsync((void**)&col->d_valid_counts, n * sizeof(unsigned long long), c->s_compute);
+    if (e == cudaSuccess && bbytes) e = cudaMallocAsync((void**)&col->d_valid_counts, n * sizeof(unsigned long long), c->s_compute);
     if (e == cudaSuccess && bbytes) e = cudaMemsetAsync(col->arena_validity, 0, bbytes, c->s_compute);
-    if (e == cudaSuccess && n) e = cudaMemsetAsync(col->d_valid_counts, 0, n * sizeof(unsigned long long), c->s_compute);
+    if (e == cudaSuccess && bbytes) e = cudaMemsetAsync(col->d_valid_counts, 0, n * sizeof(unsigned long long), c->s_compute);
     if (e != cudaSuccess) {
         cudaGetLastError();
         col_release(c, col);
@@ -212,11 +238,6 @@ static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, 
         ch.bit_off = bit_offs ? (*bit_offs)[i] : 0;
     }
     *out = col;
-    return BDF_OK;
-}
-
-static int new_event(cudaEvent_t* ev) {
-    CK(cudaEventCreateWithFlags(ev, cudaEventDisableTiming));
     return BDF_OK;
 }
 
@@ -281,8 +302,8 @@ static int64_t reduce_bytes(const bdf_col* col, int64_t begin, int64_t end) {
 static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t end, int slot) {
     const int64_t n = end - begin;
     const int tile = elems_per_tile(col->dtype);
-    void* hp = nullptr;
-    TRY(ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(RedDesc), &hp));
+    void *hp = nullptr, *dp = nullptr;
+    TRY(ring_alloc(c, (size_t)n * sizeof(RedDesc), &hp, &dp));
     RedDesc* hd = (RedDesc*)hp;
     int64_t tiles = 0, rows = 0;
     for (int64_t i = 0; i < n; i++) {
@@ -291,14 +312,12 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
         tiles += (ch.len + tile - 1) / tile;
         rows += ch.len;
     }
-    RedDesc* dd = nullptr;
-    CK(cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(RedDesc), c->s_compute));
+    RedDesc* dd = (RedDesc*)dp;
     if (n) CK(cudaMemcpyAsync(dd, hd, (size_t)n * sizeof(RedDesc), cudaMemcpyHostToDevice, c->s_compute));
     {
         LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));
         CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->red_grid_cap, c->d_partials, c->d_ticket, c->d_agg + slot, c->s_compute));
     }
-    CK(cudaFreeAsync(dd, c->s_compute));
     return BDF_OK;
 }
 
@@ -378,7 +397,7 @@ static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool as
                 const int64_t b = std::min(group_begin, specs[k].n), en = std::min(i + 1, specs[k].n);
                 if (en <= b) continue;
                 Group g{b, en, nullptr};
-                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                e = ev_get(c, &g.ev);
                 if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_h2d);
                 cols[k]->groups.push_back(g);
             }
@@ -398,15 +417,18 @@ static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool as
 
 static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out);  // identity cast: bit offset -> 0
 
-static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
+// Downloads are split in two so that callers can overlap them with later work: enqueue puts the D2H copies
+// on the d2h stream behind the group events; finish waits for them and fills in the metadata.
+static int download_enqueue(bdf_ctx* c, bdf_col* col, bdf_out* out) {
     bool misaligned = false;
     for (auto& ch : col->chunks) misaligned = misaligned || (ch.validity && ch.bit_off != 0);
     if (misaligned) {  // an uploaded slice downloaded as-is: shift its bitmap to offset 0 first
         bdf_col* tmp = nullptr;
         TRY(realign(c, col, &tmp));
-        int st = download(c, tmp, out);
-        col_release(c, tmp);
-        return st;
+        int st = download_enqueue(c, tmp, out);
+        if (st != BDF_OK) { col_release(c, tmp); return st; }
+        col->dl_tmp = tmp;
+        return BDF_OK;
     }
     const int w = dtype_width(col->dtype);
     const int64_t n = (int64_t)col->chunks.size();
@@ -416,7 +438,6 @@ static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         if (ch.len && !out[i].values) return fail(BDF_INVALID, "output chunk %lld has no values buffer", (long long)i);
         if (ch.validity && ch.len && !out[i].validity) return fail(BDF_INVALID, "output chunk %lld needs a validity buffer", (long long)i);
     }
-    std::vector<unsigned long long> counts((size_t)n);
     for (auto& g : col->groups) {
         CK(cudaStreamWaitEvent(c->s_d2h, g.ev, 0));
         for (int64_t i = g.begin; i < g.end; i++) {
@@ -426,13 +447,28 @@ static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
             if (ch.validity) CK(cudaMemcpyAsync(out[i].validity, ch.validity, (size_t)bitmap_bytes(ch.len), cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
-    if (col->counts_on_device && n)
-        CK(cudaMemcpyAsync(counts.data(), col->d_valid_counts, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_d2h));
+    if (col->counts_on_device && n) {
+        col->dl_counts.resize((size_t)n);
+        CK(cudaMemcpyAsync(col->dl_counts.data(), col->d_valid_counts, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_d2h));
+    }
+    return BDF_OK;
+}
+
+static int download_finish(bdf_ctx* c, bdf_col* col, bdf_out* out) {
+    if (col->dl_tmp) {
+        bdf_col* tmp = col->dl_tmp;
+        col->dl_tmp = nullptr;
+        int st = download_finish(c, tmp, out);
+        col_release(c, tmp);
+        return st;
+    }
+    const int64_t n = (int64_t)col->chunks.size();
     CK(cudaStreamSynchronize(c->s_d2h));
-    if (col->counts_on_device) {
+    if (col->counts_on_device && (int64_t)col->dl_counts.size() == n) {
         for (int64_t i = 0; i < n; i++)
-            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)counts[i] : 0;
+            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)col->dl_counts[i] : 0;
         col->counts_on_device = false;
+        col->dl_counts.clear();
     }
     TRY(ensure_null_counts(c, col));
     for (int64_t i = 0; i < n; i++) {
@@ -441,6 +477,11 @@ static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         out[i].null_count = col->null_counts[i];
     }
     return BDF_OK;
+}
+
+static int download(bdf_ctx* c, bdf_col* col, bdf_out* out) {
+    TRY(download_enqueue(c, col, out));
+    return download_finish(c, col, out);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -456,7 +497,9 @@ static bool cast_is_fallible(int from, int to) {
     return tw <= fw;            // unsigned -> signed: needs a strictly wider target
 }
 
-static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out) {
+static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out);
+
+static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out, bdf_future** fut = nullptr) {
     if (op < 0 || op >= BDF_NBINARY) return fail(BDF_INVALID, "invalid binary op %d", op);
     if (l->dtype != r->dtype) return fail(BDF_INVALID, "binary op on columns of different types (%d, %d)", l->dtype, r->dtype);
     const int dtype = l->dtype;
@@ -470,19 +513,28 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
         plan[i] = {l->chunks[i].len, op > BDF_DIV || l->chunks[i].validity || r->chunks[i].validity};
     bdf_col* o = nullptr;
     TRY(col_alloc(c, dtype, plan, nullptr, &o));
-    o->counts_on_device = true;
+    o->counts_on_device = o->d_valid_counts != nullptr;
 
     const int tile = elems_per_tile(dtype);
     const int w = dtype_width(dtype);
-    void* hp = nullptr;
-    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(BinDesc), &hp);
-    BinDesc* dd = nullptr;
+    void *hp = nullptr, *dp = nullptr;
+    int st = ring_alloc(c, (size_t)n * sizeof(BinDesc), &hp, &dp);
+    BinDesc* dd = (BinDesc*)dp;
     cudaError_t e = cudaSuccess;
-    if (st == BDF_OK) {
+    // K5: aggregate of the output fused into the same pass -> one partial per tile, folded by k_finish
+    AggDev* partials = nullptr;
+    int64_t total_tiles = 0, tile_base = 0;
+    bdf_future* f = nullptr;
+    if (fut && st == BDF_OK) {
+        if (op > BDF_DIV) { col_release(c, o); return fail(BDF_UNSUPPORTED, "fused aggregate is available for add/subtract/multiply/divide"); }
+        for (int64_t i = 0; i < n; i++) total_tiles += (l->chunks[i].len + tile - 1) / tile;
+        st = future_new(c, dtype, 1, o->total_len, &f);
+        if (st == BDF_OK) e = cudaMallocAsync((void**)&partials, std::max<size_t>(1, (size_t)total_tiles) * sizeof(AggDev), c->s_compute);
+    }
+    if (st == BDF_OK && e == cudaSuccess) {
         BinDesc* hd = (BinDesc*)hp;
         const std::vector<int64_t> ends = plan_groups(n, {l, r});
-        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(BinDesc), c->s_compute);
-        if (e == cudaSuccess && op == BDF_DIV) e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
+        if (op == BDF_DIV) e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
         int64_t begin = 0;
         for (size_t gi = 0; gi < ends.size() && e == cudaSuccess; gi++) {
             const int64_t end = ends[gi];
@@ -500,24 +552,32 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
                 e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(BinDesc), cudaMemcpyHostToDevice, c->s_compute);
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, BDF_K_BINARY, dtype, rows, bytes);
-                    e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->d_flag, c->s_compute);
+                    e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->d_flag, c->s_compute, partials ? partials + tile_base : nullptr);
                 }
             }
             if (e == cudaSuccess) {
                 Group g{begin, end, nullptr};
-                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                e = ev_get(c, &g.ev);
                 if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
                 o->groups.push_back(g);
             }
             begin = end;
+            tile_base += tiles;
         }
-        if (dd) cudaFreeAsync(dd, c->s_compute);
+        if (e == cudaSuccess && f) {
+            c->launches++;
+            e = launch_finish(dtype_is_float(dtype), partials, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->d_agg + f->slot, c->s_compute);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_agg + f->slot, c->d_agg + f->slot, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute);
+            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
+        }
+        if (partials) cudaFreeAsync(partials, c->s_compute);
         if (e == cudaSuccess && op == BDF_DIV) {
             // DivideByZero must be returned INSTEAD of data: wait for the flag.
             e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
             if (e == cudaSuccess && *c->h_flag) {
                 col_release(c, o);
+                if (f) { ev_put(c, f->ev); delete f; }
                 return fail(BDF_DIVIDE_BY_ZERO, "Divide by zero error");
             }
         }
@@ -525,9 +585,11 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
     if (st != BDF_OK || e != cudaSuccess) {
         cudaGetLastError();
         col_release(c, o);
+        if (f) { ev_put(c, f->ev); delete f; }
         return st != BDF_OK ? st : fail(cuda_status(e), "binary op failed: %s", cudaGetErrorString(e));
     }
     *out = o;
+    if (fut) *fut = f;
     return BDF_OK;
 }
 
@@ -553,18 +615,17 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
     for (int64_t i = 0; i < n; i++) plan[i] = {in->chunks[i].len, in->chunks[i].validity != nullptr || fallible};
     bdf_col* o = nullptr;
     TRY(col_alloc(c, to, plan, nullptr, &o));
-    o->counts_on_device = true;
+    o->counts_on_device = o->d_valid_counts != nullptr;
 
     const int tile = is_cast ? elems_per_tile_cast(from, to) : elems_per_tile(from);
     const int wf = dtype_width(from), wt = dtype_width(to);
-    void* hp = nullptr;
-    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n) * sizeof(UnDesc), &hp);
-    UnDesc* dd = nullptr;
+    void *hp = nullptr, *dp = nullptr;
+    int st = ring_alloc(c, (size_t)n * sizeof(UnDesc), &hp, &dp);
+    UnDesc* dd = (UnDesc*)dp;
     cudaError_t e = cudaSuccess;
     if (st == BDF_OK) {
         UnDesc* hd = (UnDesc*)hp;
         const std::vector<int64_t> ends = plan_groups(n, {in});
-        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n) * sizeof(UnDesc), c->s_compute);
         int64_t begin = 0;
         for (size_t gi = 0; gi < ends.size() && e == cudaSuccess; gi++) {
             const int64_t end = ends[gi];
@@ -581,19 +642,18 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
                 e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(UnDesc), cudaMemcpyHostToDevice, c->s_compute);
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, is_cast ? BDF_K_CAST : BDF_K_UNARY, to, rows, bytes);
-                    e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->s_compute)
-                                : launch_unary(op_or_to, from, dd + begin, (int)(end - begin), tiles, o->d_valid_counts + begin, c->s_compute);
+                    e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->s_compute)
+                                : launch_unary(op_or_to, from, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->s_compute);
                 }
             }
             if (e == cudaSuccess) {
                 Group g{begin, end, nullptr};
-                e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+                e = ev_get(c, &g.ev);
                 if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
                 o->groups.push_back(g);
             }
             begin = end;
         }
-        if (dd) cudaFreeAsync(dd, c->s_compute);
     }
     if (st != BDF_OK || e != cudaSuccess) {
         cudaGetLastError();
@@ -606,15 +666,20 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
 
 static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out) { return map_dev(c, true, in->dtype, in, out); }
 
-static int aggregate_all_dev(bdf_ctx* c, bdf_col* col, bool need_counts, bdf_agg4* out) {
-    const int64_t n = (int64_t)col->chunks.size();
+static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out) {
+    bdf_future* f = new (std::nothrow) bdf_future();
+    if (!f) return fail(BDF_OOM, "host allocation failed");
+    f->dtype = dtype; f->fused = fused; f->rows = rows; f->ev = nullptr;
+    f->slot = kAggSlots + (c->fut_next++ % kAggSlots);  // upper half of h_agg/d_agg is the future ring
+    cudaError_t e = ev_get(c, &f->ev);
+    if (e != cudaSuccess) { delete f; return fail(cuda_status(e), "event creation failed: %s", cudaGetErrorString(e)); }
+    *out = f;
+    return BDF_OK;
+}
+
+// AggDev (device format) -> bdf_agg4 (ABI format: T::Native bit patterns)
+static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf_agg4* out) {
     memset(out, 0, sizeof *out);
-    wait_groups(c->s_compute, col, 0, n);
-    TRY(reduce_range(c, col, 0, n, 0));
-    CK(cudaMemcpyAsync(c->h_agg, c->d_agg, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
-    CK(cudaStreamSynchronize(c->s_compute));
-    const AggDev a = c->h_agg[0];
-    const int dtype = col->dtype;
     const int w = dtype_width(dtype);
     const uint64_t mask = w == 8 ? ~0ull : ((1ull << (8 * w)) - 1ull);
     if (dtype == BDF_F64) {
@@ -625,13 +690,47 @@ static int aggregate_all_dev(bdf_ctx* c, bdf_col* col, bool need_counts, bdf_agg
         uint32_t fb; memcpy(&fb, &f, 4);
         out->sum = fb;
     } else {
+        const uint64_t flip = (fused && dtype_is_signed_int(dtype)) ? (1ull << (8 * w - 1)) : 0ull;
         out->sum = a.sum_bits & mask;
-        out->min = a.min_bits & mask;
-        out->max = a.max_bits & mask;
+        out->min = (a.min_bits ^ flip) & mask;
+        out->max = (a.max_bits ^ flip) & mask;
     }
     out->count = (int64_t)a.count;
-    out->rows = col->total_len;
+    out->rows = rows;
     out->any_valid = a.count > 0;
+}
+
+static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
+    const int64_t n = (int64_t)col->chunks.size();
+    bdf_future* f = nullptr;
+    TRY(future_new(c, col->dtype, 0, col->total_len, &f));
+    wait_groups(c->s_compute, col, 0, n);
+    int st = reduce_range(c, col, 0, n, f->slot);
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) e = cudaMemcpyAsync(c->h_agg + f->slot, c->d_agg + f->slot, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute);
+    if (st == BDF_OK && e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
+    if (st != BDF_OK || e != cudaSuccess) {
+        ev_put(c, f->ev); delete f;
+        return st != BDF_OK ? st : fail(cuda_status(e), "aggregate failed: %s", cudaGetErrorString(e));
+    }
+    *fut = f;
+    return BDF_OK;
+}
+
+static int future_wait(bdf_ctx* c, bdf_future* f, bdf_agg4* out) {
+    cudaError_t e = cudaEventSynchronize(f->ev);
+    if (e == cudaSuccess && out) convert_agg(f->dtype, f->fused, c->h_agg[f->slot], f->rows, out);
+    ev_put(c, f->ev);
+    delete f;
+    if (e != cudaSuccess) return fail(cuda_status(e), "waiting for an aggregate failed: %s", cudaGetErrorString(e));
+    return BDF_OK;
+}
+
+static int aggregate_all_dev(bdf_ctx* c, bdf_col* col, bool need_counts, bdf_agg4* out) {
+    const int64_t n = (int64_t)col->chunks.size();
+    bdf_future* f = nullptr;
+    TRY(aggregate_all_dev_async(c, col, &f));
+    TRY(future_wait(c, f, out));
     if (need_counts) {
         TRY(ensure_null_counts(c, col));
         for (int64_t i = 0; i < n; i++)
@@ -719,7 +818,10 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
     if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ring) cudaFreeHost(c->ring);
+    if (c->dring) cudaFree(c->dring);
+    if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_agg) cudaFreeHost(c->h_agg);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_partials) cudaFree(c->d_partials);
@@ -759,14 +861,16 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
     c->ring_cap = (size_t)8 << 20;
     CK(cudaHostAlloc((void**)&c->ring, c->ring_cap, cudaHostAllocDefault));
-    CK(cudaHostAlloc((void**)&c->h_agg, kAggSlots * sizeof(AggDev), cudaHostAllocDefault));
+    CK(cudaMalloc((void**)&c->dring, c->ring_cap));
+    CK(cudaHostAlloc((void**)&c->h_agg, 2 * kAggSlots * sizeof(AggDev), cudaHostAllocDefault));
     CK(cudaHostAlloc((void**)&c->h_flag, sizeof(int), cudaHostAllocDefault));
     c->red_grid_cap = reduce_grid(c->sm_count);
     CK(cudaMalloc((void**)&c->d_partials, (size_t)c->red_grid_cap * sizeof(AggDev)));
-    CK(cudaMalloc((void**)&c->d_agg, kAggSlots * sizeof(AggDev)));
-    CK(cudaMalloc((void**)&c->d_ticket, sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&c->d_agg, 2 * kAggSlots * sizeof(AggDev)));
+    CK(cudaMalloc((void**)&c->d_stage, (size_t)c->sm_count * sizeof(AggDev)));
+    CK(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
-    CK(cudaMemset(c->d_ticket, 0, sizeof(unsigned int)));
+    CK(cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned int)));
     CK(cudaMemset(c->d_flag, 0, sizeof(int)));
     CK(cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev_t0));
@@ -838,6 +942,22 @@ int bdf_upload(bdf_ctx* c, int dtype, int64_t n_chunks, const bdf_view* in, int 
     return BDF_OK;
 }
 
+int bdf_upload_many(bdf_ctx* c, int64_t n_cols, const int32_t* dtypes, const int64_t* n_chunks, const bdf_view* const* in,
+                    int flags, bdf_col** out) {
+    ENTER(c);
+    if (n_cols < 0 || (n_cols && (!dtypes || !n_chunks || !in || !out))) return fail(BDF_INVALID, "bad arguments");
+    std::vector<UploadSpec> specs;
+    for (int64_t k = 0; k < n_cols; k++) {
+        TRY(check_dtype(dtypes[k]));
+        if (n_chunks[k] < 0 || (n_chunks[k] && !in[k])) return fail(BDF_INVALID, "bad arguments for column %lld", (long long)k);
+        specs.push_back(UploadSpec{dtypes[k], n_chunks[k], in[k]});
+    }
+    std::vector<bdf_col*> cols;
+    TRY(upload_many(c, specs, (flags & BDF_ASYNC) != 0, cols));
+    for (int64_t k = 0; k < n_cols; k++) out[k] = cols[k];
+    return BDF_OK;
+}
+
 int bdf_col_wait(bdf_ctx* c, const bdf_col* col) {
     ENTER(c);
     if (!col) return fail(BDF_INVALID, "null column");
@@ -899,6 +1019,44 @@ int bdf_avg_dev(bdf_ctx* c, const bdf_col* in, double* out, int32_t* is_some) {
     ENTER(c);
     if (!in || !out || !is_some) return fail(BDF_INVALID, "null argument");
     return avg_dev(c, const_cast<bdf_col*>(in), out, is_some);
+}
+
+int bdf_binary_agg_dev_async(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out, bdf_future** fut) {
+    ENTER(c);
+    if (!l || !r || !out || !fut) return fail(BDF_INVALID, "null argument");
+    return binary_dev(c, op, l, r, out, fut);
+}
+
+int bdf_binary_agg_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out, bdf_agg4* agg) {
+    ENTER(c);
+    if (!l || !r || !out || !agg) return fail(BDF_INVALID, "null argument");
+    bdf_future* f = nullptr;
+    TRY(binary_dev(c, op, l, r, out, &f));
+    return future_wait(c, f, agg);
+}
+
+int bdf_aggregate_all_dev_async(bdf_ctx* c, const bdf_col* in, bdf_future** fut) {
+    ENTER(c);
+    if (!in || !fut) return fail(BDF_INVALID, "null argument");
+    return aggregate_all_dev_async(c, const_cast<bdf_col*>(in), fut);
+}
+
+int bdf_future_wait(bdf_ctx* c, bdf_future* fut, bdf_agg4* out) {
+    ENTER(c);
+    if (!fut) return fail(BDF_INVALID, "null future");
+    return future_wait(c, fut, out);
+}
+
+int bdf_download_begin(bdf_ctx* c, const bdf_col* col, bdf_out* out) {
+    ENTER(c);
+    if (!col || (!out && !col->chunks.empty())) return fail(BDF_INVALID, "null argument");
+    return download_enqueue(c, const_cast<bdf_col*>(col), out);
+}
+
+int bdf_download_end(bdf_ctx* c, const bdf_col* col, bdf_out* out) {
+    ENTER(c);
+    if (!col || (!out && !col->chunks.empty())) return fail(BDF_INVALID, "null argument");
+    return download_finish(c, const_cast<bdf_col*>(col), out);
 }
 
 int bdf_download(bdf_ctx* c, const bdf_col* col, bdf_out* out) {
@@ -1075,12 +1233,12 @@ int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t
     }
     bdf_col* o = nullptr;
     TRY(col_alloc(c, dtype, plan, nullptr, &o));
-    o->counts_on_device = true;
+    o->counts_on_device = o->d_valid_counts != nullptr;
     const int tile = elems_per_tile(dtype);
-    void* hp = nullptr;
-    int st = ring_alloc(c, std::max<size_t>(1, (size_t)n_chunks) * sizeof(GenDesc), &hp);
+    void *hp = nullptr, *dp = nullptr;
+    int st = ring_alloc(c, (size_t)n_chunks * sizeof(GenDesc), &hp, &dp);
     cudaError_t e = cudaSuccess;
-    GenDesc* dd = nullptr;
+    GenDesc* dd = (GenDesc*)dp;
     if (st == BDF_OK) {
         GenDesc* hd = (GenDesc*)hp;
         int64_t tiles = 0, rows = 0;
@@ -1089,16 +1247,14 @@ int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t
             tiles += (chunk_lens[i] + tile - 1) / tile;
             rows += chunk_lens[i];
         }
-        e = cudaMallocAsync((void**)&dd, std::max<size_t>(1, (size_t)n_chunks) * sizeof(GenDesc), c->s_compute);
-        if (e == cudaSuccess && n_chunks) e = cudaMemcpyAsync(dd, hd, (size_t)n_chunks * sizeof(GenDesc), cudaMemcpyHostToDevice, c->s_compute);
+        if (n_chunks) e = cudaMemcpyAsync(dd, hd, (size_t)n_chunks * sizeof(GenDesc), cudaMemcpyHostToDevice, c->s_compute);
         if (e == cudaSuccess) {
             LaunchTimer t(c, BDF_K_GENERATE, dtype, rows, rows * dtype_width(dtype));
             e = launch_generate(dtype, kind, lo, hi, seed, col_id, null_mod, dd, (int)n_chunks, tiles, o->d_valid_counts, c->s_compute);
         }
-        if (dd) cudaFreeAsync(dd, c->s_compute);
         if (e == cudaSuccess) {
             Group g{0, n_chunks, nullptr};
-            e = cudaEventCreateWithFlags(&g.ev, cudaEventDisableTiming);
+            e = ev_get(c, &g.ev);
             if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
             o->groups.push_back(g);
         }

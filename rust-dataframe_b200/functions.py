@@ -233,6 +233,25 @@ class Column:
         return col
 
     @classmethod
+    def upload_many(cls, columns: Sequence[Chunks], ctx: Optional[N.Context] = None, asynchronous: bool = False) -> List["Column"]:
+        """Upload several columns with their chunks interleaved (a0,b0,a1,b1,...) -- one Vec<RecordBatch>."""
+        ctx = ctx or N.default_context()
+        k = len(columns)
+        dtypes = (C.c_int32 * k)(*[_dtype_of(col) for col in columns])
+        counts = (C.c_int64 * k)(*[len(col) for col in columns])
+        views = [N.make_views(col) for col in columns]
+        ptrs = (C.POINTER(N.View) * k)(*[C.cast(v, C.POINTER(N.View)) for v in views])
+        outs = (C.c_void_p * k)()
+        st = N.lib().bdf_upload_many(ctx.handle, k, dtypes, counts, ptrs, N.ASYNC if asynchronous else 0, outs)
+        N.raise_for_status(st)
+        cols = []
+        for i in range(k):
+            col = cls(ctx, C.c_void_p(outs[i]))
+            col._hold = (columns[i], views) if asynchronous else None
+            cols.append(col)
+        return cols
+
+    @classmethod
     def generate(cls, dtype: int, chunk_lens: Sequence[int], kind: int = 0, lo: float = 0.0, hi: float = 1.0,
                  seed: int = 20260924, col_id: int = 0, row0: int = 0, null_mod: int = 0,
                  ctx: Optional[N.Context] = None) -> "Column":
@@ -281,6 +300,26 @@ class Column:
     def atan2(self, o): return self._bin(N.ATAN2, o)
     def hypot(self, o): return self._bin(N.HYPOT, o)
     def log(self, o): return self._bin(N.LOG, o)
+
+    # -- fused operator + aggregate of the result (one pass) --
+    def binary_agg(self, op: int, other: "Column"):
+        """(self op other) materialised as a Column AND sum/min/max/count of it, from one kernel pass."""
+        h, a = C.c_void_p(), N.Agg4()
+        N.raise_for_status(N.lib().bdf_binary_agg_dev(self.ctx.handle, op, self.handle, other.handle, C.byref(h), C.byref(a)))
+        return Column(self.ctx, h), _agg4_to_dict(self.dtype, a)
+
+    def add_agg(self, o): return self.binary_agg(N.ADD, o)
+
+    def binary_agg_async(self, op: int, other: "Column"):
+        """Like binary_agg but returns (Column, AggFuture) without waiting for the GPU."""
+        h, f = C.c_void_p(), C.c_void_p()
+        N.raise_for_status(N.lib().bdf_binary_agg_dev_async(self.ctx.handle, op, self.handle, other.handle, C.byref(h), C.byref(f)))
+        return Column(self.ctx, h), AggFuture(self.ctx, f, self.dtype)
+
+    def aggregate_all_async(self) -> "AggFuture":
+        f = C.c_void_p()
+        N.raise_for_status(N.lib().bdf_aggregate_all_dev_async(self.ctx.handle, self.handle, C.byref(f)))
+        return AggFuture(self.ctx, f, self.dtype)
 
     def unary(self, op: int) -> "Column":
         h = C.c_void_p()
@@ -332,6 +371,18 @@ class Column:
         N.raise_for_status(N.lib().bdf_download(self.ctx.handle, self.handle, outs))
         return N.collect_outputs(dtype, outs, bufs)
 
+    def download_begin(self, into):
+        """Enqueue the device->host copies into `into` = alloc_outputs(...); pair with download_end(into)."""
+        outs, bufs = into
+        for i in range(len(bufs)):
+            outs[i].len = bufs[i][0].shape[0]
+        N.raise_for_status(N.lib().bdf_download_begin(self.ctx.handle, self.handle, outs))
+
+    def download_end(self, into) -> List[PrimitiveArray]:
+        outs, bufs = into
+        N.raise_for_status(N.lib().bdf_download_end(self.ctx.handle, self.handle, outs))
+        return N.collect_outputs(self.dtype, outs, bufs)
+
     def chunk_len(self, i: int) -> int:
         ln = C.c_int64()
         N.raise_for_status(N.lib().bdf_col_chunk_info(self.ctx.handle, self.handle, i, C.byref(ln), None, None))
@@ -345,5 +396,29 @@ class Column:
     def __del__(self):
         try:
             self.free()
+        except Exception:
+            pass
+
+
+class AggFuture:
+    """An aggregate whose kernels are enqueued; result() blocks until the value is on the host."""
+
+    def __init__(self, ctx: N.Context, handle: C.c_void_p, dtype: int):
+        self.ctx, self.handle, self.dtype = ctx, handle, dtype
+        self._value = None
+
+    def result(self) -> dict:
+        if self.handle is not None:
+            a = N.Agg4()
+            N.raise_for_status(N.lib().bdf_future_wait(self.ctx.handle, self.handle, C.byref(a)))
+            self.handle = None
+            self._value = _agg4_to_dict(self.dtype, a)
+        return self._value
+
+    def __del__(self):
+        try:
+            if self.handle is not None and self.ctx.handle:
+                N.lib().bdf_future_wait(self.ctx.handle, self.handle, None)
+                self.handle = None
         except Exception:
             pass

@@ -556,3 +556,78 @@ def test_full_size_int64_linearity_1e8(rdf, ctx, oracle):
     assert_same_array(got, want, what="nullable i64 chunk 3")
     for col in (a, b, c, d, an, cn, f):
         col.free()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# K5 fused operator + aggregate, async aggregates, split downloads
+
+@pytest.mark.parametrize("tname", ALL_TYPES)
+def test_fused_binary_aggregate_matches_two_pass(rdf, ctx, oracle, tname):
+    dtype = getattr(rdf, tname)
+    rng = np.random.default_rng(300 + dtype)
+    lens = [n for n in RAGGED if n > 0]
+    for null_a, null_b, sliced in [(0, 0, False), (0.1, 0.3, True)]:
+        a = make_column(rdf, rng, dtype, lens, null_a, sliced)
+        b = make_column(rdf, rng, dtype, lens, null_b, sliced, nonzero=True)
+        ca, cb = rdf.Column.upload(a), rdf.Column.upload(b)
+        for op, oop in ((rdf.native.ADD, oracle.ADD), (rdf.native.SUB, oracle.SUB), (rdf.native.MUL, oracle.MUL), (rdf.native.DIV, oracle.DIV)):
+            col, agg = ca.binary_agg(op, cb)
+            st, want = oracle.col_binary(oop, dtype, a, b)
+            for i, (g, w) in enumerate(zip(col.download(), want)):
+                assert_same_array(g, w, what=f"fused op {op} <{tname}> chunk {i}")
+            two_pass = col.aggregate_all()
+            st, cnt = oracle.aggregate(oracle.COUNT, dtype, want)
+            assert agg["count"] == two_pass["count"] == cnt and agg["rows"] == sum(lens)
+            if tname in INT_TYPES:
+                for key, aop in (("sum", oracle.SUM), ("min", oracle.MIN), ("max", oracle.MAX)):
+                    has_valid = [w for w in want if w.valid_mask().any()]
+                    exp = oracle.aggregate(aop, dtype, has_valid)[1]
+                    assert int(agg[key]) == int(two_pass[key]) == int(exp), (tname, op, key)
+            else:
+                exact, sum_abs = oracle.sum_exact(dtype, want)
+                eps = 2.0 ** -53 if tname == "F64" else 2.0 ** -24
+                assert abs(np.longdouble(agg["sum"]) - exact) <= 16 * np.log2(sum(lens)) * eps * sum_abs
+            col.free()
+        fut_col, fut = ca.binary_agg_async(rdf.native.ADD, cb)
+        again = fut_col.aggregate_all_async()
+        r1, r2 = fut.result(), again.result()
+        assert r1["count"] == r2["count"] and (tname not in INT_TYPES or int(r1["sum"]) == int(r2["sum"]))
+        for col in (ca, cb, fut_col):
+            col.free()
+
+
+def test_fused_aggregate_is_deterministic_and_rejects_math_ops(rdf, ctx):
+    lens = [1_000_003, 17, 2_000_000]
+    a = rdf.Column.generate(rdf.F64, lens, 0, -1e3, 1e3, col_id=0)
+    b = rdf.Column.generate(rdf.F64, lens, 0, -1e3, 1e3, col_id=1, null_mod=7)
+    sums = set()
+    for _ in range(3):
+        col, agg = a.add_agg(b)
+        sums.add(float(agg["sum"]).hex())
+        col.free()
+    assert len(sums) == 1
+    with pytest.raises(rdf.UnsupportedType):
+        a.binary_agg(rdf.native.ATAN2, b)
+
+
+def test_split_download_overlaps_and_matches(rdf, ctx, oracle):
+    rng = np.random.default_rng(77)
+    lens = [300_000, 5, 0, 123_457]
+    a = make_column(rdf, rng, rdf.F64, lens, 0.1, True)
+    b = make_column(rdf, rng, rdf.F64, lens, 0.0, False)
+    ca = rdf.Column.upload(a, asynchronous=True)
+    cb = rdf.Column.upload(b, asynchronous=True)
+    cc, fut = ca.binary_agg_async(rdf.native.MUL, cb)
+    into = rdf.native.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    cc.download_begin(into)
+    agg = fut.result()
+    got = cc.download_end(into)
+    st, want = oracle.col_binary(oracle.MUL, oracle.F64, a, b)
+    for g, w in zip(got, want):
+        assert_same_array(g, w, what="split download")
+    assert agg["count"] == oracle.aggregate(oracle.COUNT, oracle.F64, want)[1]
+    # sliced column straight back to the host through the split path (bitmap re-aligned on the device)
+    into2 = rdf.native.alloc_outputs(rdf.F64, lens, ctx)
+    ca.download_begin(into2)
+    for g, src in zip(ca.download_end(into2), a):
+        assert np.array_equal(g.valid_mask(), src.valid_mask()) and np.array_equal(g.value_slice(), src.value_slice())
