@@ -215,6 +215,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         return combine(float(s), ROWS)
 
     inflight = []
+    DEPTH = 1 if world == 1 else 2  # steps kept in flight by the host (the NCCL combine of step i runs under step i+1/i+2)
 
     def retire():
         c, fut = inflight.pop(0)
@@ -226,7 +227,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         """c = a + b materialised in HBM with sum(c) folded into the same pass (K5); the host keeps one step in
         flight: step i's scalar is fetched after step i+1 has been enqueued."""
         inflight.append(a.binary_agg_async(N.ADD, b))
-        return retire() if len(inflight) > 1 else None
+        return retire() if len(inflight) > DEPTH else None
 
     def barrier():
         ctx.synchronize()
@@ -327,7 +328,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "chunks": len(lens), "parallelism": f"shard{world}",
                    "l2": "inputs (2.4 GB working set per step) are larger than the 126 MB L2; no flush needed",
                    "fused": "sum(c) is computed by the add kernel while c is written (c is still materialised): 24 B/row",
-                   "host_pipelining": "one step in flight: step i's scalar is read after step i+1 is enqueued",
+                   "host_pipelining": f"{DEPTH} step(s) in flight: step i's scalar is read (and combined across ranks) after step i+{DEPTH} is enqueued",
                    "collective": "none" if world == 1 else "1 NCCL all-reduce of the partial (sum,count) per step"},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "check": {"sum": last[0], "count": last[1]},

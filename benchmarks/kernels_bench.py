@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Per-kernel roofline table for the SURVEY 8(d) configurations (device-resident data, CUDA-event timing on
+the library's compute stream via its launch records).  Not the headline benchmark (that is bench.py); this
+is the evidence that every kernel of the path, not only f64 add, runs near the HBM roofline.
+
+    python benchmarks/kernels_bench.py [--rows 100000000] [--json gpurun_out/kernels.json]
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import rust_dataframe_b200 as rdf  # noqa: E402
+from rust_dataframe_b200 import native as N  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    return float(json.load(open(p))["hbm_gbs"]) if os.path.exists(p) else 6650.0
+
+
+def timed(ctx, fn, reps=12):
+    """Run fn() reps times with profiling on; return per-kernel-kind (median ms, bytes, rows)."""
+    for _ in range(3):
+        out = fn()
+        for o in out if isinstance(out, (list, tuple)) else [out]:
+            if isinstance(o, rdf.Column):
+                o.free()
+    ctx.synchronize()
+    ctx.profile_read()
+    ctx.profile_enable(True)
+    for _ in range(reps):
+        out = fn()
+        for o in out if isinstance(out, (list, tuple)) else [out]:
+            if isinstance(o, rdf.Column):
+                o.free()
+    ctx.profile_enable(False)
+    recs = ctx.profile_read()
+    by = {}
+    for r in recs:
+        by.setdefault(r["kernel"], []).append(r)
+    return {k: (float(np.median([r["ms"] for r in v])), v[0]["bytes"], v[0]["rows"]) for k, v in by.items()}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=100_000_000)
+    ap.add_argument("--json", default=None)
+    args = ap.parse_args()
+    ctx = rdf.default_context()
+    chunk = 4_000_000
+    lens = [chunk] * (args.rows // chunk)
+    G = rdf.Column.generate
+    pk = peak()
+    rows_out = []
+
+    def report(name, config, res, kind):
+        ms, nbytes, rows = res[kind]
+        gbs = nbytes / ms / 1e6
+        rows_out.append({"case": name, "config": config, "kernel": kind, "ms": ms, "rows": rows, "bytes_per_row": nbytes / rows,
+                         "GBs": gbs, "frac_of_measured_peak": gbs / pk, "frac_of_8TBs": gbs / 8000.0, "rows_per_s": rows / ms * 1e3})
+        print(f"{name:44s} {ms:8.4f} ms  {nbytes / rows:7.3f} B/row  {gbs:8.1f} GB/s  {gbs / pk:5.3f} of measured  {rows / ms * 1e3:10.3e} rows/s", flush=True)
+
+    # ---- config 1/metric: f64 add, sum ----
+    a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0)
+    b = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=1)
+    c3 = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=2)
+    d = G(rdf.F64, lens, 1, col_id=3)
+    report("add f64 (no nulls)", "metric", timed(ctx, lambda: a.add(b)), "binary")
+    report("add f64 + fused sum (K5)", "metric", timed(ctx, lambda: a.binary_agg(N.ADD, b)[0]), "binary")
+    report("sum f64 (no nulls)", "metric", timed(ctx, lambda: a.sum()), "reduce")
+    # ---- config 2: chain add, mul, div, sin ----
+    report("multiply f64", "cfg2", timed(ctx, lambda: a.multiply(c3)), "binary")
+    report("divide f64 (zero check fused)", "cfg2", timed(ctx, lambda: a.divide(d)), "binary")
+    g = a.divide(d)
+    report("sin f64, |x| <~ 1e3", "cfg2", timed(ctx, lambda: g.sin()), "unary")
+    report("cos f64", "cfg2", timed(ctx, lambda: g.cos()), "unary")
+    report("tan f64", "cfg2", timed(ctx, lambda: g.tan()), "unary")
+    report("abs f64", "cfg2", timed(ctx, lambda: g.abs()), "unary")
+    g.free()
+    bn = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=4, null_mod=10)
+    dn = G(rdf.F64, lens, 1, col_id=5, null_mod=10)
+    report("add f64, 10% nulls on one input", "cfg2-nulls", timed(ctx, lambda: a.add(bn)), "binary")
+    report("divide f64, 10% nulls on both", "cfg2-nulls", timed(ctx, lambda: bn.divide(dn)), "binary")
+    report("sin f64, 10% nulls", "cfg2-nulls", timed(ctx, lambda: bn.sin()), "unary")
+    for col in (c3, d, bn, dn):
+        col.free()
+    # f32 trig
+    f32 = G(rdf.F32, lens, 0, -1e3, 1e3, col_id=6)
+    report("sin f32", "extra", timed(ctx, lambda: f32.sin()), "unary")
+    report("add f32", "extra", timed(ctx, lambda: f32.add(f32)), "binary")
+    f32.free()
+    # ---- config 3: int64 aggregates with 10% nulls ----
+    i64n = G(rdf.I64, lens, 3, col_id=7, null_mod=10)
+    i64 = G(rdf.I64, lens, 3, col_id=8)
+    report("sum/min/max/count i64, 10% nulls (4-in-1)", "cfg3", timed(ctx, lambda: i64n.aggregate_all()), "reduce")
+    report("sum/min/max/count i64, no nulls", "cfg3", timed(ctx, lambda: i64.aggregate_all()), "reduce")
+    report("add i64, 10% nulls", "cfg5", timed(ctx, lambda: i64n.add(i64)), "binary")
+    report("add i64 + fused 4-in-1 aggregate", "cfg5", timed(ctx, lambda: i64n.binary_agg(N.ADD, i64)[0]), "binary")
+    # ---- config 4: cast chain ----
+    i32n = G(rdf.I32, lens, 2, col_id=9, null_mod=10)
+    report("cast i32 -> f64, 10% nulls", "cfg4", timed(ctx, lambda: i32n.cast(rdf.F64)), "cast")
+    report("cast i64 -> f64", "cfg5", timed(ctx, lambda: i64.cast(rdf.F64)), "cast")
+    report("cast f64 -> i32 (fallible)", "cfg4", timed(ctx, lambda: a.cast(rdf.I32)), "cast")
+    report("cast f64 -> f32", "extra", timed(ctx, lambda: a.cast(rdf.F32)), "cast")
+    report("cast i64 -> i8 (fallible, narrow out)", "extra", timed(ctx, lambda: i64.cast(rdf.I8)), "cast")
+    i8 = i64.cast(rdf.I8)
+    report("add i8", "extra", timed(ctx, lambda: i8.add(i8)), "binary")
+    report("sum/min/max/count i8", "extra", timed(ctx, lambda: i8.aggregate_all()), "reduce")
+    if args.json:
+        with open(args.json, "w") as f:
+            json.dump({"rows": args.rows, "peak_GBs_measured": pk, "results": rows_out}, f, indent=1)
+
+
+if __name__ == "__main__":
+    main()

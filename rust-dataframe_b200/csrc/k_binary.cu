@@ -267,7 +267,7 @@ k_finish(const AggDev* __restrict__ parts, long long n_parts, AggDev* __restrict
         merge(fin, p);
     }
     fin = block_fold(fin);
-    if (threadIdx.x == 0) { *result = fin; *ticket = 0; }
+    if (threadIdx.x == 0) { *result = fin; __threadfence_system(); *ticket = 0; }  // result: device-mapped host memory
 }
 
 cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, int sm_count, AggDev* stage, unsigned int* ticket,

@@ -187,7 +187,8 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
     }
     block_reduce(acc, s_state);
     if (threadIdx.x == 0) {
-        acc.to_dev(result);
+        acc.to_dev(result);  // result may live in device-mapped host memory
+        __threadfence_system();
         *ticket = 0;  // ready for the next launch on this stream
     }
 }

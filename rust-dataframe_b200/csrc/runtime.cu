@@ -86,7 +86,7 @@ struct bdf_col {
 struct bdf_future {
     int dtype;
     int fused;       // 1: partials use order-preserving unsigned keys for min/max (k_binary AGG), 0: k_reduce format
-    int slot;        // index into h_agg / d_agg
+    int slot;        // index into h_agg
     int64_t rows;
     cudaEvent_t ev;
 };
@@ -101,21 +101,25 @@ struct bdf_ctx {
     int sm_count = 0, cc_major = 0, cc_minor = 0;
     size_t hbm_bytes = 0;
     cudaStream_t s_compute = nullptr, s_h2d = nullptr, s_d2h = nullptr;
+    cudaStream_t s_desc = nullptr;  // descriptor copies: run ahead of the compute stream, off its critical path
+    cudaStream_t s_fin = nullptr;   // k_finish of fused aggregates: overlaps the next operator
     std::mutex mu;
     // pinned staging: descriptor ring + small result area
     char* ring = nullptr;           // pinned host side of the descriptor ring
     char* dring = nullptr;          // device side, same offsets
     size_t ring_cap = 0, ring_head = 0;
     std::vector<cudaEvent_t> ev_pool;  // recycled cudaEventDisableTiming events
-    AggDev* h_agg = nullptr;        // pinned, kAggSlots entries
+    AggDev* h_agg = nullptr;        // pinned + device-mapped: kernels write results straight into it
+    AggDev* h_agg_dev = nullptr;    // device-side address of h_agg
     int* h_flag = nullptr;          // pinned
     // device scratch
     AggDev* d_partials = nullptr;
-    AggDev* d_agg = nullptr;        // kAggSlots entries
     unsigned int* d_ticket = nullptr;   // [0]: k_reduce, [1]: k_finish
     AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
-    int fut_next = 0;                   // ring cursor over the future half of h_agg / d_agg
+    int fut_next = 0;                   // ring cursor over the future half of h_agg
+    struct PartBuf { AggDev* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } part[3];
+    int part_next = 0;                  // per-tile partials of fused aggregates: 3 persistent buffers in rotation
     int red_grid_cap = 0;
     cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void* flush_buf = nullptr;
@@ -142,6 +146,7 @@ static int ring_alloc(bdf_ctx* c, size_t bytes, void** host, void** dev) {
     bytes = align_up(std::max<size_t>(bytes, 1), 256);
     if (bytes > c->ring_cap) return fail(BDF_OOM, "descriptor ring too small for %zu bytes", bytes);
     if (c->ring_head + bytes > c->ring_cap) {
+        CK(cudaStreamSynchronize(c->s_desc));
         CK(cudaStreamSynchronize(c->s_compute));  // everything that read the ring has finished
         c->ring_head = 0;
     }
@@ -156,6 +161,19 @@ static cudaError_t ev_get(bdf_ctx* c, cudaEvent_t* ev) {
     return cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
 }
 static void ev_put(bdf_ctx* c, cudaEvent_t ev) { if (ev) c->ev_pool.push_back(ev); }
+
+// Copy descriptors host ring -> device ring on the descriptor stream and make the compute stream wait for
+// them: the copy itself runs while the previous kernel is still busy.
+static cudaError_t desc_upload(bdf_ctx* c, void* dev, const void* host, size_t bytes) {
+    if (!bytes) return cudaSuccess;
+    cudaError_t e = cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, c->s_desc);
+    cudaEvent_t ev = nullptr;
+    if (e == cudaSuccess) e = ev_get(c, &ev);
+    if (e == cudaSuccess) e = cudaEventRecord(ev, c->s_desc);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_compute, ev, 0);
+    ev_put(c, ev);  // the wait has captured this record; re-recording later does not affect it
+    return e;
+}
 
 struct LaunchTimer {  // brackets one launch with events when profiling is on
     bdf_ctx* c;
@@ -298,7 +316,7 @@ static int64_t reduce_bytes(const bdf_col* col, int64_t begin, int64_t end) {
     return b;
 }
 
-// Launch one reduce over chunks [begin,end) of col into d_agg[slot].  Caller has made the stream wait.
+// Launch one reduce over chunks [begin,end) of col into h_agg[slot] (device-mapped host memory).  Caller has made the stream wait.
 static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t end, int slot) {
     const int64_t n = end - begin;
     const int tile = elems_per_tile(col->dtype);
@@ -313,10 +331,10 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
         rows += ch.len;
     }
     RedDesc* dd = (RedDesc*)dp;
-    if (n) CK(cudaMemcpyAsync(dd, hd, (size_t)n * sizeof(RedDesc), cudaMemcpyHostToDevice, c->s_compute));
+    CK(desc_upload(c, dd, hd, (size_t)n * sizeof(RedDesc)));
     {
         LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));
-        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->red_grid_cap, c->d_partials, c->d_ticket, c->d_agg + slot, c->s_compute));
+        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->red_grid_cap, c->d_partials, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
     }
     return BDF_OK;
 }
@@ -332,7 +350,6 @@ static int ensure_null_counts(bdf_ctx* c, bdf_col* col) {
     for (size_t k = 0; k < unknown.size(); k += kAggSlots) {
         const size_t m = std::min<size_t>(kAggSlots, unknown.size() - k);
         for (size_t j = 0; j < m; j++) TRY(reduce_range(c, col, unknown[k + j], unknown[k + j] + 1, (int)j));
-        CK(cudaMemcpyAsync(c->h_agg, c->d_agg, m * sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         for (size_t j = 0; j < m; j++) {
             const int64_t i = unknown[k + j];
@@ -523,13 +540,27 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
     cudaError_t e = cudaSuccess;
     // K5: aggregate of the output fused into the same pass -> one partial per tile, folded by k_finish
     AggDev* partials = nullptr;
+    bdf_ctx::PartBuf* pb = nullptr;
     int64_t total_tiles = 0, tile_base = 0;
     bdf_future* f = nullptr;
     if (fut && st == BDF_OK) {
         if (op > BDF_DIV) { col_release(c, o); return fail(BDF_UNSUPPORTED, "fused aggregate is available for add/subtract/multiply/divide"); }
         for (int64_t i = 0; i < n; i++) total_tiles += (l->chunks[i].len + tile - 1) / tile;
         st = future_new(c, dtype, 1, o->total_len, &f);
-        if (st == BDF_OK) e = cudaMallocAsync((void**)&partials, std::max<size_t>(1, (size_t)total_tiles) * sizeof(AggDev), c->s_compute);
+        if (st == BDF_OK) {
+            pb = &c->part[c->part_next++ % 3];
+            const size_t need = std::max<size_t>(1, (size_t)total_tiles);
+            if (pb->cap < need) {  // grow (rare): nothing may still be using the old buffer
+                cudaStreamSynchronize(c->s_fin); cudaStreamSynchronize(c->s_compute);
+                if (pb->p) cudaFree(pb->p);
+                pb->p = nullptr; pb->cap = 0;
+                e = cudaMalloc((void**)&pb->p, need * sizeof(AggDev));
+                if (e == cudaSuccess) pb->cap = need;
+            }
+            if (e == cudaSuccess && !pb->done) e = cudaEventCreateWithFlags(&pb->done, cudaEventDisableTiming);
+            if (e == cudaSuccess && pb->used) e = cudaStreamWaitEvent(c->s_compute, pb->done, 0);  // its previous k_finish has read it
+            partials = pb->p;
+        }
     }
     if (st == BDF_OK && e == cudaSuccess) {
         BinDesc* hd = (BinDesc*)hp;
@@ -549,7 +580,7 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
             wait_groups(c->s_compute, l, begin, end);
             wait_groups(c->s_compute, r, begin, end);
             if (end > begin) {
-                e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(BinDesc), cudaMemcpyHostToDevice, c->s_compute);
+                e = desc_upload(c, dd + begin, hd + begin, (size_t)(end - begin) * sizeof(BinDesc));
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, BDF_K_BINARY, dtype, rows, bytes);
                     e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->d_flag, c->s_compute, partials ? partials + tile_base : nullptr);
@@ -565,12 +596,14 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
             tile_base += tiles;
         }
         if (e == cudaSuccess && f) {
+            // fold the per-tile partials on the finish stream: the next operator on the compute stream does not wait
             c->launches++;
-            e = launch_finish(dtype_is_float(dtype), partials, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->d_agg + f->slot, c->s_compute);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_agg + f->slot, c->d_agg + f->slot, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute);
-            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
+            for (auto& g : o->groups) cudaStreamWaitEvent(c->s_fin, g.ev, 0);
+            e = launch_finish(dtype_is_float(dtype), partials, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->h_agg_dev + f->slot, c->s_fin);
+            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
+            if (e == cudaSuccess) e = cudaEventRecord(pb->done, c->s_fin);
+            pb->used = true;
         }
-        if (partials) cudaFreeAsync(partials, c->s_compute);
         if (e == cudaSuccess && op == BDF_DIV) {
             // DivideByZero must be returned INSTEAD of data: wait for the flag.
             e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
@@ -639,7 +672,7 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
             }
             wait_groups(c->s_compute, in, begin, end);
             if (end > begin) {
-                e = cudaMemcpyAsync(dd + begin, hd + begin, (size_t)(end - begin) * sizeof(UnDesc), cudaMemcpyHostToDevice, c->s_compute);
+                e = desc_upload(c, dd + begin, hd + begin, (size_t)(end - begin) * sizeof(UnDesc));
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, is_cast ? BDF_K_CAST : BDF_K_UNARY, to, rows, bytes);
                     e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->s_compute)
@@ -707,8 +740,7 @@ static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
     wait_groups(c->s_compute, col, 0, n);
     int st = reduce_range(c, col, 0, n, f->slot);
     cudaError_t e = cudaSuccess;
-    if (st == BDF_OK) e = cudaMemcpyAsync(c->h_agg + f->slot, c->d_agg + f->slot, sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute);
-    if (st == BDF_OK && e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
+    if (st == BDF_OK) e = cudaEventRecord(f->ev, c->s_compute);
     if (st != BDF_OK || e != cudaSuccess) {
         ev_put(c, f->ev); delete f;
         return st != BDF_OK ? st : fail(cuda_status(e), "aggregate failed: %s", cudaGetErrorString(e));
@@ -778,7 +810,6 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
     for (int64_t k = 0; k < n; k += kAggSlots) {
         const int64_t m = std::min<int64_t>(kAggSlots, n - k);
         for (int64_t j = 0; j < m; j++) TRY(reduce_range(c, col, k + j, k + j + 1, (int)j));
-        CK(cudaMemcpyAsync(c->h_agg, c->d_agg, (size_t)m * sizeof(AggDev), cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
         for (int64_t j = 0; j < m; j++) {
             const AggDev& a = c->h_agg[j];
@@ -817,15 +848,17 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_compute) cudaStreamSynchronize(c->s_compute);
     if (c->s_h2d) cudaStreamSynchronize(c->s_h2d);
     if (c->s_d2h) cudaStreamSynchronize(c->s_d2h);
+    if (c->s_desc) cudaStreamSynchronize(c->s_desc);
+    if (c->s_fin) cudaStreamSynchronize(c->s_fin);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+    for (auto& b : c->part) { if (b.p) cudaFree(b.p); if (b.done) cudaEventDestroy(b.done); }
     if (c->ring) cudaFreeHost(c->ring);
     if (c->dring) cudaFree(c->dring);
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_agg) cudaFreeHost(c->h_agg);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_partials) cudaFree(c->d_partials);
-    if (c->d_agg) cudaFree(c->d_agg);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->flush_buf) cudaFree(c->flush_buf);
@@ -835,6 +868,8 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_compute) cudaStreamDestroy(c->s_compute);
     if (c->s_h2d) cudaStreamDestroy(c->s_h2d);
     if (c->s_d2h) cudaStreamDestroy(c->s_d2h);
+    if (c->s_desc) cudaStreamDestroy(c->s_desc);
+    if (c->s_fin) cudaStreamDestroy(c->s_fin);
     delete c;
 }
 
@@ -855,6 +890,8 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaStreamCreateWithFlags(&c->s_compute, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&c->s_d2h, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_desc, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&c->s_fin, cudaStreamNonBlocking));
     cudaMemPool_t pool;
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = ~0ull;  // keep freed arenas cached: operators allocate their outputs per call
@@ -862,11 +899,11 @@ static int init_impl(bdf_ctx* c, int device) {
     c->ring_cap = (size_t)8 << 20;
     CK(cudaHostAlloc((void**)&c->ring, c->ring_cap, cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c->dring, c->ring_cap));
-    CK(cudaHostAlloc((void**)&c->h_agg, 2 * kAggSlots * sizeof(AggDev), cudaHostAllocDefault));
+    CK(cudaHostAlloc((void**)&c->h_agg, 2 * kAggSlots * sizeof(AggDev), cudaHostAllocMapped));
+    CK(cudaHostGetDevicePointer((void**)&c->h_agg_dev, c->h_agg, 0));
     CK(cudaHostAlloc((void**)&c->h_flag, sizeof(int), cudaHostAllocDefault));
     c->red_grid_cap = reduce_grid(c->sm_count);
     CK(cudaMalloc((void**)&c->d_partials, (size_t)c->red_grid_cap * sizeof(AggDev)));
-    CK(cudaMalloc((void**)&c->d_agg, 2 * kAggSlots * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_stage, (size_t)c->sm_count * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
@@ -895,6 +932,7 @@ int bdf_synchronize(bdf_ctx* c) {
     ENTER(c);
     CK(cudaStreamSynchronize(c->s_h2d));
     CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(c->s_fin));
     CK(cudaStreamSynchronize(c->s_d2h));
     return BDF_OK;
 }
@@ -1247,7 +1285,7 @@ int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t
             tiles += (chunk_lens[i] + tile - 1) / tile;
             rows += chunk_lens[i];
         }
-        if (n_chunks) e = cudaMemcpyAsync(dd, hd, (size_t)n_chunks * sizeof(GenDesc), cudaMemcpyHostToDevice, c->s_compute);
+        e = desc_upload(c, dd, hd, (size_t)n_chunks * sizeof(GenDesc));
         if (e == cudaSuccess) {
             LaunchTimer t(c, BDF_K_GENERATE, dtype, rows, rows * dtype_width(dtype));
             e = launch_generate(dtype, kind, lo, hi, seed, col_id, null_mod, dd, (int)n_chunks, tiles, o->d_valid_counts, c->s_compute);
