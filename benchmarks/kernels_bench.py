@@ -88,6 +88,8 @@ def main():
     bn = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=4, null_mod=10)
     dn = G(rdf.F64, lens, 1, col_id=5, null_mod=10)
     report("add f64, 10% nulls on one input", "cfg2-nulls", timed(ctx, lambda: a.add(bn)), "binary")
+    report("add f64, 10% nulls on both inputs", "cfg2-nulls", timed(ctx, lambda: bn.add(dn)), "binary")
+    report("divide f64, 10% nulls on divisor only", "cfg2-nulls", timed(ctx, lambda: a.divide(dn)), "binary")
     report("divide f64, 10% nulls on both", "cfg2-nulls", timed(ctx, lambda: bn.divide(dn)), "binary")
     report("sin f64, 10% nulls", "cfg2-nulls", timed(ctx, lambda: bn.sin()), "unary")
     for col in (c3, d, bn, dn):

@@ -33,6 +33,7 @@ __host__ __device__ inline bool dtype_is_signed_int(int t) { return t >= T_I8 &&
 constexpr int kThreads = 256;  // CTA size of every streaming kernel
 constexpr int kUnroll = 4;     // 16-byte vectors in flight per thread per array
 constexpr int kTileBytes = kThreads * kUnroll * 16;  // bytes of the widest array per tile (16 KiB)
+constexpr int kWarpsPerCta = kThreads / 32;          // kernels report valid-slot counts per warp: [tile][warp] u32
 
 // ---- 128-bit streaming loads/stores -----------------------------------------------------------
 // Inputs are read exactly once and outputs written exactly once: bypass L1 allocation so the small
@@ -109,6 +110,33 @@ __device__ __forceinline__ uint32_t load_bits(const uint32_t* __restrict__ v, in
     const uint32_t r = __funnelshift_r(lo, hi, sh);
     if constexpr (E == 32) return r;
     else return r & ((1u << E) - 1u);
+}
+
+// Batched form used on full tiles: issue the raw word loads of all U steps back to back (no consumer in
+// between, so all of them are in flight together with the value loads), extract the bits later.  Wrap the
+// issue in ONE uniform `if (bitmap present)`; per-step conditionals would make the compiler serialise the
+// loads (load -> wait -> shift, U times), which costs U memory latencies per tile.
+template <int E, int U>
+struct MaskRaw {
+    uint32_t lo[U], hi[U];
+    int sh[U];
+};
+template <int E, int U>
+__device__ __forceinline__ void mask_issue(MaskRaw<E, U>& r, const uint32_t* __restrict__ v, int64_t bit0, int64_t stride_bits) {
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int64_t bit = bit0 + (int64_t)j * stride_bits;
+        const int64_t w = bit >> 5;
+        r.sh[j] = (int)(bit & 31);
+        r.lo[j] = __ldg(v + w);
+        r.hi[j] = (r.sh[j] + E > 32) ? __ldg(v + w + 1) : 0u;
+    }
+}
+template <int E, int U>
+__device__ __forceinline__ uint32_t mask_get(const MaskRaw<E, U>& r, int j) {
+    const uint32_t x = __funnelshift_r(r.lo[j], r.hi[j], r.sh[j]);
+    if constexpr (E == 32) return x;
+    else return x & ((1u << E) - 1u);
 }
 
 // Each lane contributes E bits for elements [e0, e0+E) (e0 a multiple of E, bit offset 0 on output); the
@@ -199,23 +227,24 @@ struct AggDev {
 
 // ---- launchers (defined in k_*.cu) ---------------------------------------------------------------
 int elems_per_tile(int dtype);                 // tile size in elements for arrays of dtype
+int elems_per_tile_binary(int op, int dtype);  // K1 tile size (divide/libm binaries use shorter tiles)
 int elems_per_tile_cast(int from, int to);
 // tile_partials != nullptr (add/sub/mul/div only): also write one AggDev per tile with the aggregate of the
 // OUTPUT (K5); fold them with launch_finish.  Integer min/max partials are unsigned keys (value ^ sign flip).
 cudaError_t launch_binary(int op, int dtype, const BinDesc* d_descs, int n_chunks, int64_t total_tiles,
-                          unsigned long long* d_valid_counts, int* d_flags, cudaStream_t s, AggDev* tile_partials = nullptr);
+                          uint32_t* d_warp_counts, int* d_flags, cudaStream_t s, AggDev* tile_partials = nullptr);
 cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, int sm_count, AggDev* stage, unsigned int* ticket,
                           AggDev* result, cudaStream_t s);
 cudaError_t launch_unary(int op, int dtype, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
-                         unsigned long long* d_valid_counts, cudaStream_t s);
+                         uint32_t* d_warp_counts, cudaStream_t s);
 cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
-                        unsigned long long* d_valid_counts, cudaStream_t s);
+                        uint32_t* d_warp_counts, cudaStream_t s);
 int reduce_grid(int sm_count);
 cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, int grid,
                           AggDev* d_partials, unsigned int* d_ticket, AggDev* d_result, cudaStream_t s);
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
                             const GenDesc* d_descs, int n_chunks, int64_t total_tiles,
-                            unsigned long long* d_valid_counts, cudaStream_t s);
+                            uint32_t* d_warp_counts, cudaStream_t s);
 cudaError_t launch_fill(void* p, size_t bytes, cudaStream_t s);
 
 }  // namespace bdf

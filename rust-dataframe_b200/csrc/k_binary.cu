@@ -11,7 +11,7 @@
 //   * divide: a VALID slot with a zero divisor (ints and floats) raises the DivideByZero flag; null
 //     slots divide by 1; iN::MIN / -1 wraps;
 //   * math_op binaries: null slot -> payload 0;
-//   * validity = a AND b at bit offset 0, zero padding bits; valid slots are counted per chunk.
+//   * validity = a AND b at bit offset 0, zero padding bits; valid slots are counted per warp (plain stores).
 //
 // Roofline: HBM.  Algorithmic bytes/row = 3*sizeof(T) + (v_in + [v_in>0])/8  (24 B/row for f64, no nulls).
 #include "common.cuh"
@@ -107,14 +107,13 @@ template <typename T> struct FusedAgg<T, true> {
     }
 };
 
-template <typename T, int OP, bool AGG>
+template <typename T, int OP, bool AGG, int U>
 __global__ void __launch_bounds__(kThreads)
-k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __restrict__ valid_counts,
+k_binary(const BinDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ warp_counts,
          int* __restrict__ flags, AggDev* __restrict__ tile_partials, unsigned long long flip) {
     constexpr int E = 16 / (int)sizeof(T);
-    constexpr int TILE = kThreads * kUnroll * E;
+    constexpr int TILE = kThreads * U * E;
     constexpr uint32_t FULLMASK = (E == 32) ? 0xffffffffu : ((1u << E) - 1u);
-    __shared__ unsigned long long s_red[32];
 
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
@@ -134,24 +133,28 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
     if constexpr (AGG) agg.init();
 
     if (base + TILE <= len) {
-        // ---- full tile: 2 x kUnroll 16-byte loads in flight per thread before first use ----
-        Vec<T, E> a[kUnroll], b[kUnroll];
+        // ---- full tile: 2 x U 16-byte loads in flight per thread before first use ----
+        Vec<T, E> a[U], b[U];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
+        for (int j = 0; j < U; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             a[j].load(pa + e0);
             b[j].load(pb + e0);
         }
-        uint32_t m[kUnroll];
+        // validity words of all U steps: issued as two batches (one uniform branch each), consumed afterwards
+        MaskRaw<E, U> ra, rb;
+        const int64_t e_first = base + (int64_t)threadIdx.x * E;
+        if (va) mask_issue<E, U>(ra, va, offa + e_first, (int64_t)kThreads * E);
+        if (vb) mask_issue<E, U>(rb, vb, offb + e_first, (int64_t)kThreads * E);
+        uint32_t m[U];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
-            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+        for (int j = 0; j < U; j++) {
             m[j] = FULLMASK;
-            if (va) m[j] &= load_bits<E>(va, offa + e0);
-            if (vb) m[j] &= load_bits<E>(vb, offb + e0);
+            if (va) m[j] &= mask_get<E, U>(ra, j);
+            if (vb) m[j] &= mask_get<E, U>(rb, j);
         }
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
+        for (int j = 0; j < U; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             Vec<T, E> r;
 #pragma unroll
@@ -166,7 +169,7 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
     } else {
         // ---- tail tile of the chunk: element-wise guards ----
 #pragma unroll 1
-        for (int j = 0; j < kUnroll; j++) {
+        for (int j = 0; j < U; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             const uint32_t in_range = tail_mask<E>(e0, len);
             uint32_t m = in_range;
@@ -189,9 +192,13 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
     }
 
     if (vo || AGG) {
-        const unsigned long long total = block_sum_u64(nvalid, s_red);
-        if (threadIdx.x == 0 && vo) atomicAdd(&valid_counts[c], total);
+        // valid slots of this warp -> one plain store per warp (no atomics, no block barrier); the host sums
+        // the per-warp counts of a chunk when a null count is asked for
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        if ((threadIdx.x & 31) == 0 && vo) warp_counts[(int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)] = wvalid;
         if constexpr (AGG) {
+            __shared__ unsigned int s_cnt[kThreads / 32];
+            if ((threadIdx.x & 31) == 0) s_cnt[threadIdx.x >> 5] = wvalid;
             // fixed xor-shuffle tree inside each warp, then warp 0 folds the 8 warp results in warp order
             __shared__ FusedAgg<T> s_agg[kThreads / 32];
 #pragma unroll
@@ -202,6 +209,9 @@ k_binary(const BinDesc* __restrict__ descs, int n_chunks, unsigned long long* __
                 FusedAgg<T> t = s_agg[0];
 #pragma unroll
                 for (int w = 1; w < kThreads / 32; w++) t.merge(s_agg[w]);
+                unsigned long long total = 0;
+#pragma unroll
+                for (int w = 0; w < kThreads / 32; w++) total += s_cnt[w];
                 t.store(&tile_partials[blockIdx.x], total);
             }
         }
@@ -282,22 +292,27 @@ cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, i
 
 int elems_per_tile(int dtype) { return kTileBytes / dtype_width(dtype); }
 
+// Compute-heavy binaries (divide and the libm ones) keep fewer vectors in registers per thread: the extra
+// occupancy hides the long dependent instruction sequences better than deeper per-thread batching.
+template <int OP> struct UnrollOf { static constexpr int value = (OP > OP_DIV) ? 2 : kUnroll; };
+int elems_per_tile_binary(int op, int dtype) { return (op > OP_DIV ? kThreads * 2 * 16 : kTileBytes) / dtype_width(dtype); }
+
 struct AggArgs { AggDev* partials; unsigned long long flip; };
 
 template <typename T, int OP>
-static cudaError_t launch_one(const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags, cudaStream_t s, AggArgs ag) {
+static cudaError_t launch_one(const BinDesc* d, int n, int64_t tiles, uint32_t* vc, int* flags, cudaStream_t s, AggArgs ag) {
     if constexpr (OP <= OP_DIV) {
         if (ag.partials) {
-            k_binary<T, OP, true><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, ag.partials, ag.flip);
+            k_binary<T, OP, true, UnrollOf<OP>::value><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, ag.partials, ag.flip);
             return cudaGetLastError();
         }
     }
-    k_binary<T, OP, false><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, nullptr, 0ull);
+    k_binary<T, OP, false, UnrollOf<OP>::value><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc, flags, nullptr, 0ull);
     return cudaGetLastError();
 }
 
 template <typename T>
-static cudaError_t launch_wrapping(int op, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
+static cudaError_t launch_wrapping(int op, const BinDesc* d, int n, int64_t tiles, uint32_t* vc, int* flags,
                                    cudaStream_t s, AggArgs ag) {
     switch (op) {
         case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s, ag);
@@ -307,7 +322,7 @@ static cudaError_t launch_wrapping(int op, const BinDesc* d, int n, int64_t tile
 }
 
 template <typename T>
-static cudaError_t launch_float(int op, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
+static cudaError_t launch_float(int op, const BinDesc* d, int n, int64_t tiles, uint32_t* vc, int* flags,
                                 cudaStream_t s, AggArgs ag) {
     switch (op) {
         case OP_ADD: return launch_one<T, OP_ADD>(d, n, tiles, vc, flags, s, ag);
@@ -320,7 +335,7 @@ static cudaError_t launch_float(int op, const BinDesc* d, int n, int64_t tiles, 
     }
 }
 
-cudaError_t launch_binary(int op, int dtype, const BinDesc* d, int n, int64_t tiles, unsigned long long* vc, int* flags,
+cudaError_t launch_binary(int op, int dtype, const BinDesc* d, int n, int64_t tiles, uint32_t* vc, int* flags,
                           cudaStream_t s, AggDev* tile_partials) {
     const int bits = 8 * dtype_width(dtype);
     AggArgs ag{tile_partials, dtype_is_signed_int(dtype) ? (1ull << (bits - 1)) : 0ull};

@@ -73,12 +73,11 @@ __device__ __forceinline__ bool cast_one(F v, T& out) {
 
 template <typename F, typename T>
 __global__ void __launch_bounds__(kThreads)
-k_cast(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __restrict__ valid_counts) {
+k_cast(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ warp_counts) {
     constexpr int W = sizeof(F) > sizeof(T) ? (int)sizeof(F) : (int)sizeof(T);
     constexpr int E = 16 / W;
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr uint32_t FULLMASK = (1u << E) - 1u;
-    __shared__ unsigned long long s_red[32];
 
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
@@ -95,10 +94,11 @@ k_cast(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __res
         Vec<F, E> x[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+        MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+        if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
         uint32_t m[kUnroll];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++)
-            m[j] = vi ? load_bits<E>(vi, off + base + (int64_t)(j * kThreads + threadIdx.x) * E) : FULLMASK;
+        for (int j = 0; j < kUnroll; j++) m[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
@@ -141,8 +141,8 @@ k_cast(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __res
         }
     }
     if (vo) {
-        const unsigned long long total = block_sum_u64(nvalid, s_red);
-        if (threadIdx.x == 0) atomicAdd(&valid_counts[c], total);
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);  // per-warp count, plain store (no atomics)
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)] = wvalid;
     }
 }
 
@@ -152,13 +152,13 @@ int elems_per_tile_cast(int from, int to) {
 }
 
 template <typename F, typename T>
-static cudaError_t launch_one(const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+static cudaError_t launch_one(const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     k_cast<F, T><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc);
     return cudaGetLastError();
 }
 
 template <typename F>
-static cudaError_t launch_from(int to, const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+static cudaError_t launch_from(int to, const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     switch (to) {
         case T_I8: return launch_one<F, int8_t>(d, n, tiles, vc, s);
         case T_I16: return launch_one<F, int16_t>(d, n, tiles, vc, s);
@@ -174,7 +174,7 @@ static cudaError_t launch_from(int to, const UnDesc* d, int n, int64_t tiles, un
     }
 }
 
-cudaError_t launch_cast(int from, int to, const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+cudaError_t launch_cast(int from, int to, const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (from) {

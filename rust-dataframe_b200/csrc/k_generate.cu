@@ -40,10 +40,9 @@ __device__ __forceinline__ T gen_value(int kind, double lo, double span, uint64_
 template <typename T, bool IsFloat>
 __global__ void __launch_bounds__(kThreads)
 k_generate(const GenDesc* __restrict__ descs, int n_chunks, int kind, double lo, double span, uint64_t seed,
-           uint64_t colbits, uint32_t null_mod, unsigned long long* __restrict__ valid_counts) {
+           uint64_t colbits, uint32_t null_mod, uint32_t* __restrict__ warp_counts) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
-    __shared__ unsigned long long s_red[32];
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
     T* __restrict__ po = (T*)descs[c].out;
@@ -77,8 +76,8 @@ k_generate(const GenDesc* __restrict__ descs, int n_chunks, int kind, double lo,
         }
     }
     if (vo) {
-        const unsigned long long total = block_sum_u64(nvalid, s_red);
-        if (threadIdx.x == 0) atomicAdd(&valid_counts[c], total);
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)] = wvalid;
     }
 }
 
@@ -97,13 +96,13 @@ cudaError_t launch_fill(void* p, size_t bytes, cudaStream_t s) {
 
 template <typename T, bool F>
 static cudaError_t launch_one(int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
-                              const GenDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+                              const GenDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     k_generate<T, F><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, kind, lo, hi - lo, seed, col << 56, null_mod, vc);
     return cudaGetLastError();
 }
 
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
-                            const GenDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+                            const GenDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (dtype) {

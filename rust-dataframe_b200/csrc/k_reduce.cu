@@ -142,10 +142,11 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
             Vec<T, E> x[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+            MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+            if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
             uint32_t m[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++)
-                m[j] = vi ? load_bits<E>(vi, off + base + (int64_t)(j * kThreads + threadIdx.x) * E) : FULLMASK;
+            for (int j = 0; j < kUnroll; j++) m[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) {
 #pragma unroll

@@ -77,11 +77,10 @@ template <int OP> __device__ __forceinline__ int64_t un_apply(int64_t x) { retur
 
 template <typename T, int OP>
 __global__ void __launch_bounds__(kThreads)
-k_unary(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __restrict__ valid_counts) {
+k_unary(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ warp_counts) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr uint32_t FULLMASK = (1u << E) - 1u;
-    __shared__ unsigned long long s_red[32];
 
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
@@ -98,16 +97,20 @@ k_unary(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __re
         Vec<T, E> x[kUnroll];
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+        MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+        if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
         uint32_t m[kUnroll];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++)
-            m[j] = vi ? load_bits<E>(vi, off + base + (int64_t)(j * kThreads + threadIdx.x) * E) : FULLMASK;
+        for (int j = 0; j < kUnroll; j++) m[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             Vec<T, E> r;
 #pragma unroll
-            for (int e = 0; e < E; e++) r.e[e] = ((m[j] >> e) & 1u) ? un_apply<OP>(x[j].e[e]) : (T)0;
+            for (int e = 0; e < E; e++) {
+                const T y = un_apply<OP>(x[j].e[e]);  // computed for every lane (no divergence), selected afterwards
+                r.e[e] = ((m[j] >> e) & 1u) ? y : (T)0;
+            }
             r.store(po + e0);
             if (vo) {
                 store_bits<E>(vo, e0, m[j], true);
@@ -131,19 +134,19 @@ k_unary(const UnDesc* __restrict__ descs, int n_chunks, unsigned long long* __re
         }
     }
     if (vo) {
-        const unsigned long long total = block_sum_u64(nvalid, s_red);
-        if (threadIdx.x == 0) atomicAdd(&valid_counts[c], total);
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);  // per-warp count, plain store (no atomics)
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5)] = wvalid;
     }
 }
 
 template <typename T, int OP>
-static cudaError_t launch_one(const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+static cudaError_t launch_one(const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     k_unary<T, OP><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc);
     return cudaGetLastError();
 }
 
 template <typename T>
-static cudaError_t launch_float(int op, const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+static cudaError_t launch_float(int op, const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     switch (op) {
 #define BDF_CASE(OP) case OP: return launch_one<T, OP>(d, n, tiles, vc, s);
         BDF_CASE(UN_ABS) BDF_CASE(UN_SIN) BDF_CASE(UN_COS) BDF_CASE(UN_TAN) BDF_CASE(UN_ACOS) BDF_CASE(UN_ASIN)
@@ -155,7 +158,7 @@ static cudaError_t launch_float(int op, const UnDesc* d, int n, int64_t tiles, u
     }
 }
 
-cudaError_t launch_unary(int op, int dtype, const UnDesc* d, int n, int64_t tiles, unsigned long long* vc, cudaStream_t s) {
+cudaError_t launch_unary(int op, int dtype, const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     if (dtype == T_F64) return launch_float<double>(op, d, n, tiles, vc, s);

@@ -74,11 +74,13 @@ struct bdf_col {
     std::vector<DevChunk> chunks;
     char* arena_values = nullptr;
     char* arena_validity = nullptr;
-    unsigned long long* d_valid_counts = nullptr;  // per chunk, written by the producing kernel
-    bool counts_on_device = false;                 // d_valid_counts not yet mirrored into null_counts
+    uint32_t* d_warp_counts = nullptr;             // valid slots per warp per tile ([tile][8]), written by the producing kernel
+    int64_t tile_elems = 0;                        // tile size (elements) the producing kernel used
+    std::vector<int64_t> tile0;                    // column-global first tile of each chunk (n+1 entries)
+    bool counts_on_device = false;                 // d_warp_counts not yet folded into null_counts
     std::vector<int64_t> null_counts;              // -1 = unknown
     std::vector<Group> groups;
-    std::vector<unsigned long long> dl_counts;     // staging of d_valid_counts during a split download
+    std::vector<uint32_t> dl_counts;               // staging of d_warp_counts during a split download
     bdf_col* dl_tmp = nullptr;                     // re-aligned copy used by a split download of a sliced column
 };
 
@@ -206,7 +208,7 @@ static void col_release(bdf_ctx* c, bdf_col* col) {
     for (auto& g : col->groups) if (g.ev) cudaStreamWaitEvent(c->s_compute, g.ev, 0);
     if (col->arena_values) cudaFreeAsync(col->arena_values, c->s_compute);
     if (col->arena_validity) cudaFreeAsync(col->arena_validity, c->s_compute);
-    if (col->d_valid_counts) cudaFreeAsync(col->d_valid_counts, c->s_compute);
+    if (col->d_warp_counts) cudaFreeAsync(col->d_warp_counts, c->s_compute);
     col_destroy_host(c, col);
 }
 
@@ -216,8 +218,9 @@ struct ChunkPlan {
 };
 
 // Allocate arenas for a column with the given chunk plan (validity at bit offset `bit_off[i]`).
+// tile_elems > 0: the column will be produced by a kernel with that tile size (per-warp valid counts are kept).
 static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, const std::vector<int32_t>* bit_offs,
-                     bdf_col** out) {
+                     int64_t tile_elems, bdf_col** out) {
     bdf_col* col = new (std::nothrow) bdf_col();
     if (!col) return fail(BDF_OOM, "host allocation failed");
     col->dtype = dtype;
@@ -238,9 +241,14 @@ static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, 
     cudaError_t e = cudaSuccess;
     if (vbytes) e = cudaMallocAsync((void**)&col->arena_values, vbytes, c->s_compute);
     if (e == cudaSuccess && bbytes) e = cudaMallocAsync((void**)&col->arena_validity, bbytes, c->s_compute);
-    if (e == cudaSuccess && bbytes) e = cudaMallocAsync((void**)&col->d_valid_counts, n * sizeof(unsigned long long), c->s_compute);
+    col->tile_elems = tile_elems;
+    col->tile0.assign(n + 1, 0);
+    if (tile_elems > 0)
+        for (size_t i = 0; i < n; i++) col->tile0[i + 1] = col->tile0[i] + (plan[i].len + tile_elems - 1) / tile_elems;
+    const size_t n_tiles = (size_t)col->tile0[n];
+    if (e == cudaSuccess && bbytes && n_tiles)
+        e = cudaMallocAsync((void**)&col->d_warp_counts, n_tiles * kWarpsPerCta * sizeof(uint32_t), c->s_compute);
     if (e == cudaSuccess && bbytes) e = cudaMemsetAsync(col->arena_validity, 0, bbytes, c->s_compute);
-    if (e == cudaSuccess && bbytes) e = cudaMemsetAsync(col->d_valid_counts, 0, n * sizeof(unsigned long long), c->s_compute);
     if (e != cudaSuccess) {
         cudaGetLastError();
         col_release(c, col);
@@ -289,19 +297,30 @@ static std::vector<int64_t> plan_groups(int64_t n, std::initializer_list<const b
 
 static int64_t bitmap_bytes(int64_t len) { return (len + 7) / 8; }
 
+// Fold the per-warp valid counts of every chunk into null_counts (host side; chunk i owns tiles [tile0[i], tile0[i+1])).
+static void fold_counts(bdf_col* col, const uint32_t* counts) {
+    const size_t n = col->chunks.size();
+    for (size_t i = 0; i < n; i++) {
+        if (!col->chunks[i].validity) { col->null_counts[i] = 0; continue; }
+        int64_t valid = 0;
+        for (int64_t k = col->tile0[i] * kWarpsPerCta; k < col->tile0[i + 1] * kWarpsPerCta; k++) valid += counts[k];
+        col->null_counts[i] = col->chunks[i].len - valid;
+    }
+    col->counts_on_device = false;
+}
+
 // Mirror kernel-written valid counts into host null_counts (one small D2H + sync on the compute stream).
 static int fetch_counts(bdf_ctx* c, bdf_col* col) {
     if (!col->counts_on_device) return BDF_OK;
     const size_t n = col->chunks.size();
-    if (n) {
-        std::vector<unsigned long long> tmp(n);
+    const size_t total = (size_t)col->tile0[n] * kWarpsPerCta;
+    std::vector<uint32_t> tmp(std::max<size_t>(total, 1));
+    if (total) {
         wait_groups(c->s_compute, col, 0, (int64_t)n);
-        CK(cudaMemcpyAsync(tmp.data(), col->d_valid_counts, n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_compute));
+        CK(cudaMemcpyAsync(tmp.data(), col->d_warp_counts, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->s_compute));
         CK(cudaStreamSynchronize(c->s_compute));
-        for (size_t i = 0; i < n; i++)
-            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)tmp[i] : 0;
     }
-    col->counts_on_device = false;
+    fold_counts(col, tmp.data());
     return BDF_OK;
 }
 
@@ -384,7 +403,7 @@ static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool as
             plan[i] = {v.len, v.validity != nullptr};
             offs[i] = (int32_t)(v.offset & 7);
         }
-        int st = col_alloc(c, s.dtype, plan, &offs, &cols[k]);
+        int st = col_alloc(c, s.dtype, plan, &offs, 0, &cols[k]);
         if (st != BDF_OK) { cleanup(); return st; }
         for (int64_t i = 0; i < s.n; i++)
             cols[k]->null_counts[i] = s.views[i].validity ? (s.views[i].null_count >= 0 ? s.views[i].null_count : -1) : 0;
@@ -464,9 +483,9 @@ static int download_enqueue(bdf_ctx* c, bdf_col* col, bdf_out* out) {
             if (ch.validity) CK(cudaMemcpyAsync(out[i].validity, ch.validity, (size_t)bitmap_bytes(ch.len), cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
-    if (col->counts_on_device && n) {
-        col->dl_counts.resize((size_t)n);
-        CK(cudaMemcpyAsync(col->dl_counts.data(), col->d_valid_counts, (size_t)n * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_d2h));
+    if (col->counts_on_device && col->tile0[n] > 0) {
+        col->dl_counts.resize((size_t)col->tile0[n] * kWarpsPerCta);
+        CK(cudaMemcpyAsync(col->dl_counts.data(), col->d_warp_counts, col->dl_counts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->s_d2h));
     }
     return BDF_OK;
 }
@@ -481,10 +500,8 @@ static int download_finish(bdf_ctx* c, bdf_col* col, bdf_out* out) {
     }
     const int64_t n = (int64_t)col->chunks.size();
     CK(cudaStreamSynchronize(c->s_d2h));
-    if (col->counts_on_device && (int64_t)col->dl_counts.size() == n) {
-        for (int64_t i = 0; i < n; i++)
-            col->null_counts[i] = col->chunks[i].validity ? col->chunks[i].len - (int64_t)col->dl_counts[i] : 0;
-        col->counts_on_device = false;
+    if (col->counts_on_device && (int64_t)col->dl_counts.size() == col->tile0[n] * kWarpsPerCta) {
+        fold_counts(col, col->dl_counts.data());
         col->dl_counts.clear();
     }
     TRY(ensure_null_counts(c, col));
@@ -529,10 +546,10 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
     for (int64_t i = 0; i < n; i++)
         plan[i] = {l->chunks[i].len, op > BDF_DIV || l->chunks[i].validity || r->chunks[i].validity};
     bdf_col* o = nullptr;
-    TRY(col_alloc(c, dtype, plan, nullptr, &o));
-    o->counts_on_device = o->d_valid_counts != nullptr;
+    const int tile = elems_per_tile_binary(op, dtype);
+    TRY(col_alloc(c, dtype, plan, nullptr, tile, &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
 
-    const int tile = elems_per_tile(dtype);
     const int w = dtype_width(dtype);
     void *hp = nullptr, *dp = nullptr;
     int st = ring_alloc(c, (size_t)n * sizeof(BinDesc), &hp, &dp);
@@ -583,7 +600,7 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
                 e = desc_upload(c, dd + begin, hd + begin, (size_t)(end - begin) * sizeof(BinDesc));
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, BDF_K_BINARY, dtype, rows, bytes);
-                    e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->d_flag, c->s_compute, partials ? partials + tile_base : nullptr);
+                    e = launch_binary(op, dtype, dd + begin, (int)(end - begin), tiles, o->d_warp_counts ? o->d_warp_counts + o->tile0[begin] * kWarpsPerCta : nullptr, c->d_flag, c->s_compute, partials ? partials + tile_base : nullptr);
                 }
             }
             if (e == cudaSuccess) {
@@ -647,10 +664,10 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
     std::vector<ChunkPlan> plan((size_t)n);
     for (int64_t i = 0; i < n; i++) plan[i] = {in->chunks[i].len, in->chunks[i].validity != nullptr || fallible};
     bdf_col* o = nullptr;
-    TRY(col_alloc(c, to, plan, nullptr, &o));
-    o->counts_on_device = o->d_valid_counts != nullptr;
-
     const int tile = is_cast ? elems_per_tile_cast(from, to) : elems_per_tile(from);
+    TRY(col_alloc(c, to, plan, nullptr, tile, &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
+
     const int wf = dtype_width(from), wt = dtype_width(to);
     void *hp = nullptr, *dp = nullptr;
     int st = ring_alloc(c, (size_t)n * sizeof(UnDesc), &hp, &dp);
@@ -675,8 +692,8 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
                 e = desc_upload(c, dd + begin, hd + begin, (size_t)(end - begin) * sizeof(UnDesc));
                 if (e == cudaSuccess) {
                     LaunchTimer t(c, is_cast ? BDF_K_CAST : BDF_K_UNARY, to, rows, bytes);
-                    e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->s_compute)
-                                : launch_unary(op_or_to, from, dd + begin, (int)(end - begin), tiles, o->d_valid_counts ? o->d_valid_counts + begin : nullptr, c->s_compute);
+                    e = is_cast ? launch_cast(from, to, dd + begin, (int)(end - begin), tiles, o->d_warp_counts ? o->d_warp_counts + o->tile0[begin] * kWarpsPerCta : nullptr, c->s_compute)
+                                : launch_unary(op_or_to, from, dd + begin, (int)(end - begin), tiles, o->d_warp_counts ? o->d_warp_counts + o->tile0[begin] * kWarpsPerCta : nullptr, c->s_compute);
                 }
             }
             if (e == cudaSuccess) {
@@ -1270,9 +1287,9 @@ int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t
         plan[i] = {chunk_lens[i], null_mod != 0};
     }
     bdf_col* o = nullptr;
-    TRY(col_alloc(c, dtype, plan, nullptr, &o));
-    o->counts_on_device = o->d_valid_counts != nullptr;
     const int tile = elems_per_tile(dtype);
+    TRY(col_alloc(c, dtype, plan, nullptr, tile, &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
     void *hp = nullptr, *dp = nullptr;
     int st = ring_alloc(c, (size_t)n_chunks * sizeof(GenDesc), &hp, &dp);
     cudaError_t e = cudaSuccess;
@@ -1288,7 +1305,7 @@ int bdf_generate(bdf_ctx* c, int dtype, int kind, double lo, double hi, uint64_t
         e = desc_upload(c, dd, hd, (size_t)n_chunks * sizeof(GenDesc));
         if (e == cudaSuccess) {
             LaunchTimer t(c, BDF_K_GENERATE, dtype, rows, rows * dtype_width(dtype));
-            e = launch_generate(dtype, kind, lo, hi, seed, col_id, null_mod, dd, (int)n_chunks, tiles, o->d_valid_counts, c->s_compute);
+            e = launch_generate(dtype, kind, lo, hi, seed, col_id, null_mod, dd, (int)n_chunks, tiles, o->d_warp_counts, c->s_compute);
         }
         if (e == cudaSuccess) {
             Group g{0, n_chunks, nullptr};
