@@ -191,6 +191,73 @@ __global__ void __launch_bounds__(THREADS) k_add_sum_np(const double* __restrict
     if (threadIdx.x == 0) partials[blockIdx.x] = s;
 }
 
+// sum, NOT persistent: each CTA owns K consecutive tiles and writes one partial
+template <int THREADS, int U, int VB, int K>
+__global__ void __launch_bounds__(THREADS) k_sum_np(const double* __restrict__ a, long n_tiles, double* __restrict__ partials) {
+    using V = typename VecSel<VB>::T;
+    constexpr int N = VecSel<VB>::N;
+    constexpr long TILE = (long)THREADS * U * N;
+    __shared__ double smem[32];
+    double acc[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0.0;
+#pragma unroll 1
+    for (int kk = 0; kk < K; kk++) {
+        const long tile = (long)blockIdx.x * K + kk;
+        if (tile >= n_tiles) break;
+        const long base = tile * TILE;
+        V x[U];
+#pragma unroll
+        for (int j = 0; j < U; j++) ldv<VB>(x[j], a + base + (long)(j * THREADS + threadIdx.x) * N);
+#pragma unroll
+        for (int j = 0; j < U; j++)
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[k] = __dadd_rn(acc[k], x[j].d[k]);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) s += acc[k];
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
+// persistent sum with register double buffering: the loads of tile t+1 are issued before tile t is folded
+template <int THREADS, int U, int VB>
+__global__ void __launch_bounds__(THREADS) k_sum_pipe(const double* __restrict__ a, long n_tiles, double* __restrict__ partials) {
+    using V = typename VecSel<VB>::T;
+    constexpr int N = VecSel<VB>::N;
+    constexpr long TILE = (long)THREADS * U * N;
+    __shared__ double smem[32];
+    double acc[N];
+#pragma unroll
+    for (int k = 0; k < N; k++) acc[k] = 0.0;
+    V x[U], y[U];
+    long tile = blockIdx.x;
+    if (tile < n_tiles) {
+#pragma unroll
+        for (int j = 0; j < U; j++) ldv<VB>(x[j], a + tile * TILE + (long)(j * THREADS + threadIdx.x) * N);
+    }
+    while (tile < n_tiles) {
+        const long next = tile + gridDim.x;
+        if (next < n_tiles) {
+#pragma unroll
+            for (int j = 0; j < U; j++) ldv<VB>(y[j], a + next * TILE + (long)(j * THREADS + threadIdx.x) * N);
+        }
+#pragma unroll
+        for (int j = 0; j < U; j++)
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[k] = __dadd_rn(acc[k], x[j].d[k]);
+#pragma unroll
+        for (int j = 0; j < U; j++) x[j] = y[j];
+        tile = next;
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < N; k++) s += acc[k];
+    s = block_sum(s, smem);
+    if (threadIdx.x == 0) partials[blockIdx.x] = s;
+}
+
 // ---- harness -----------------------------------------------------------------------------------------
 static cudaEvent_t e0, e1;
 template <typename F>
@@ -250,6 +317,16 @@ int main(int argc, char** argv) {
         run(nm, B_ADD, [&] { k_add_sum_np<T, U, VB, K><<<(unsigned)((nt + K - 1) / K), T>>>(a, b, c, nt, partials); }); }
     ADDSUMNP(256, 4, 16, 1) ADDSUMNP(256, 4, 16, 2) ADDSUMNP(256, 4, 16, 4) ADDSUMNP(256, 4, 16, 8) ADDSUMNP(512, 4, 16, 1) ADDSUMNP(512, 4, 16, 2)
     ADDSUMNP(256, 2, 32, 1) ADDSUMNP(256, 2, 32, 4) ADDSUMNP(512, 2, 32, 1) ADDSUMNP(512, 2, 32, 2) ADDSUMNP(512, 2, 32, 4)
+
+#define SUMNP(T, U, VB, K) { constexpr long TILE = (long)T * U * (VB / 8); const long nt = rows / TILE; char nm[96]; \
+        snprintf(nm, 96, "sum non-persist T=%d U=%d VB=%d K=%d", T, U, VB, K); \
+        run(nm, B_SUM, [&] { k_sum_np<T, U, VB, K><<<(unsigned)((nt + K - 1) / K), T>>>(a, nt, partials); }); }
+    SUMNP(256, 4, 16, 1) SUMNP(256, 4, 16, 2) SUMNP(256, 4, 16, 4) SUMNP(256, 4, 16, 8) SUMNP(256, 8, 16, 1) SUMNP(256, 8, 16, 2) SUMNP(256, 8, 16, 4)
+    SUMNP(512, 4, 16, 1) SUMNP(512, 4, 16, 2) SUMNP(512, 8, 16, 1) SUMNP(256, 4, 32, 1) SUMNP(256, 4, 32, 2) SUMNP(256, 4, 32, 4) SUMNP(512, 4, 32, 1) SUMNP(512, 4, 32, 2)
+#define SUMPIPE(T, U, VB, CPS) { constexpr long TILE = (long)T * U * (VB / 8); const long nt = rows / TILE; char nm[96]; \
+        snprintf(nm, 96, "sum pipelined T=%d U=%d VB=%d grid=SMs x" #CPS, T, U, VB); \
+        run(nm, B_SUM, [&] { k_sum_pipe<T, U, VB><<<sms * CPS, T>>>(a, nt, partials); }); }
+    SUMPIPE(256, 4, 16, 4) SUMPIPE(256, 4, 16, 5) SUMPIPE(256, 4, 16, 6) SUMPIPE(256, 2, 32, 4) SUMPIPE(512, 4, 16, 2) SUMPIPE(256, 8, 16, 2) SUMPIPE(256, 8, 16, 4)
 
     // sequence as the product runs it: add, then sum over c (events around the sum only)
     {

@@ -217,11 +217,11 @@ struct GenDesc {
     int64_t len; int64_t tile0; int64_t row0;
 };
 
-// Result of the reduce kernel, in device memory.
+// Partial / final aggregate as the kernels produce it.
 struct AggDev {
-    unsigned long long sum_bits;  // ints: 64-bit wrapping sum (two's complement); floats: double bit pattern
-    unsigned long long min_bits;  // ints only: T widened to 64 bit (sign- or zero-extended)
-    unsigned long long max_bits;
+    unsigned long long sum_bits;  // ints: 64-bit wrapping sum; floats: double bit pattern
+    unsigned long long min_bits;  // ints only: order-preserving unsigned key of the minimum (identity ~0)
+    unsigned long long max_bits;  // ints only: order-preserving unsigned key of the maximum (identity 0)
     unsigned long long count;     // valid slots
 };
 
@@ -239,9 +239,11 @@ cudaError_t launch_unary(int op, int dtype, const UnDesc* d_descs, int n_chunks,
                          uint32_t* d_warp_counts, cudaStream_t s);
 cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
                         uint32_t* d_warp_counts, cudaStream_t s);
-int reduce_grid(int sm_count);
-cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, int grid,
-                          AggDev* d_partials, unsigned int* d_ticket, AggDev* d_result, cudaStream_t s);
+// K4: one AggDev partial per tile (integer min/max as unsigned keys: extended value ^ 2^63 for signed types);
+// fold with launch_finish.
+cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, AggDev* d_cta_partials,
+                          cudaStream_t s);
+int64_t reduce_partials(int dtype, int64_t tiles);  // number of partials launch_reduce writes
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
                             const GenDesc* d_descs, int n_chunks, int64_t total_tiles,
                             uint32_t* d_warp_counts, cudaStream_t s);

@@ -5,13 +5,15 @@
 //   * integers: wrapping 64-bit sum (truncated to T by the caller: wrapping add is associative, so the
 //     result is bit-identical to the reference's sequential fold), min, max, valid count;
 //   * floats: sum accumulated in double, valid count (the reference has no float min/max:
-//     T::Native: Ord).  Summation order is FIXED for a given device: tiles are dealt round-robin to a
-//     grid whose size depends only on the SM count, each thread folds its elements in index order,
-//     warp-shuffle tree, shared-memory tree over warps, then the last CTA (ticket) folds the per-CTA
-//     partials in CTA order.  No floating-point atomics anywhere => run-to-run deterministic.
+//     T::Native: Ord).  Summation order is FIXED: each thread folds the elements of its tile in index
+//     order, xor-shuffle tree inside the warp, warps in warp order, one partial per tile; k_finish folds
+//     the partials with a grid and a per-thread assignment that depend only on the tile count and the SM
+//     count.  No floating-point atomics anywhere => run-to-run deterministic.
 //     The reference folds strictly left-to-right; the difference is covered by the stated tolerance.
 //
 // Roofline: HBM, sizeof(T) + [nullable]/8 bytes/row (8 B/row for f64/i64, 8.125 with a bitmap).
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bdf {
@@ -24,111 +26,96 @@ BDF_REDINFO(uint32_t, false, false) BDF_REDINFO(uint64_t, false, false) BDF_REDI
 BDF_REDINFO(double, true, true)
 #undef BDF_REDINFO
 
-template <typename T> __device__ __forceinline__ T type_max() {
-    if constexpr (RedInfo<T>::is_signed) return (T)((1ull << (8 * sizeof(T) - 1)) - 1ull);
-    else return (T)~0ull;
-}
-template <typename T> __device__ __forceinline__ T type_min() {
-    if constexpr (RedInfo<T>::is_signed) return (T)(-(int64_t)((1ull << (8 * sizeof(T) - 1)) - 1ull) - 1);
-    else return (T)0;
-}
-
-// Running state of one thread / one CTA.
+// Running state of one thread / one CTA.  Integers: 64-bit wrapping sum of the sign-/zero-extended values
+// and min/max as order-preserving unsigned keys (extended value ^ 2^63 for signed types), so that the
+// type-agnostic k_finish can fold partials with plain unsigned compares.  Floats: sum in double.
 template <typename T, bool IsFloat = RedInfo<T>::is_float> struct RedState;
 
 template <typename T>
 struct RedState<T, false> {
-    unsigned long long sum; T mn, mx; unsigned long long cnt;
-    __device__ __forceinline__ void init() { sum = 0; mn = type_max<T>(); mx = type_min<T>(); cnt = 0; }
+    // narrow types fold a tile into a 32-bit accumulator (<= 64 elements of <= 16 bits per thread and tile),
+    // min/max are compared in T's own width and signedness; keys are formed once per CTA in to_dev
+    using Acc = typename std::conditional<(sizeof(T) <= 2), typename std::conditional<RedInfo<T>::is_signed, int, unsigned int>::type,
+                                          typename std::conditional<RedInfo<T>::is_signed, long long, unsigned long long>::type>::type;
+    static constexpr unsigned long long kFlip = RedInfo<T>::is_signed ? (1ull << 63) : 0ull;
+    unsigned long long sum; Acc acc; T mn, mx;
+    __device__ __forceinline__ void init() {
+        sum = 0; acc = 0;
+        mn = RedInfo<T>::is_signed ? (T)((1ull << (8 * sizeof(T) - 1)) - 1ull) : (T)~0ull;
+        mx = RedInfo<T>::is_signed ? (T)(-(long long)((1ull << (8 * sizeof(T) - 1)) - 1ull) - 1) : (T)0;
+    }
     __device__ __forceinline__ void add(T x, bool valid) {
-        if (valid) {
-            sum += (unsigned long long)(long long)x;  // sign- or zero-extension, then wrapping add
-            mn = x < mn ? x : mn;
-            mx = x > mx ? x : mx;
-        }
+        acc += valid ? (Acc)x : (Acc)0;
+        mn = (valid && x < mn) ? x : mn;
+        mx = (valid && x > mx) ? x : mx;
     }
-    __device__ __forceinline__ void merge(const RedState& o) {
-        sum += o.sum; mn = o.mn < mn ? o.mn : mn; mx = o.mx > mx ? o.mx : mx; cnt += o.cnt;
-    }
+    __device__ __forceinline__ void add_all_valid(T x) { acc += (Acc)x; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }
+    __device__ __forceinline__ void end_tile() { sum += (unsigned long long)(long long)acc; acc = 0; }  // sign-/zero-extend, wrap
+    __device__ __forceinline__ void merge(const RedState& o) { sum += o.sum; mn = o.mn < mn ? o.mn : mn; mx = o.mx > mx ? o.mx : mx; }
     __device__ __forceinline__ RedState shfl_xor(int o) const {
         RedState r;
+        r.acc = 0;
         r.sum = __shfl_xor_sync(0xffffffffu, sum, o);
-        r.mn = (T)__shfl_xor_sync(0xffffffffu, (long long)mn, o);
-        r.mx = (T)__shfl_xor_sync(0xffffffffu, (long long)mx, o);
-        r.cnt = __shfl_xor_sync(0xffffffffu, cnt, o);
+        if constexpr (sizeof(T) == 8) {
+            r.mn = (T)__shfl_xor_sync(0xffffffffu, (long long)mn, o);
+            r.mx = (T)__shfl_xor_sync(0xffffffffu, (long long)mx, o);
+        } else {
+            r.mn = (T)__shfl_xor_sync(0xffffffffu, (int)mn, o);
+            r.mx = (T)__shfl_xor_sync(0xffffffffu, (int)mx, o);
+        }
         return r;
     }
-    __device__ __forceinline__ void to_dev(AggDev* d) const {
-        d->sum_bits = sum; d->min_bits = (unsigned long long)(long long)mn; d->max_bits = (unsigned long long)(long long)mx;
+    __device__ __forceinline__ void to_dev(AggDev* d, unsigned long long cnt) const {
+        d->sum_bits = sum;
+        d->min_bits = (unsigned long long)(long long)mn ^ kFlip;  // order-preserving unsigned keys
+        d->max_bits = (unsigned long long)(long long)mx ^ kFlip;
         d->count = cnt;
-    }
-    __device__ __forceinline__ void from_dev(const AggDev* d) {
-        sum = __ldcg(&d->sum_bits); mn = (T)(long long)__ldcg(&d->min_bits); mx = (T)(long long)__ldcg(&d->max_bits);
-        cnt = __ldcg(&d->count);
     }
 };
 
 template <typename T>
 struct RedState<T, true> {
-    double sum; unsigned long long cnt;
-    __device__ __forceinline__ void init() { sum = 0.0; cnt = 0; }
+    double sum;
+    __device__ __forceinline__ void init() { sum = 0.0; }
     __device__ __forceinline__ void add(T x, bool valid) { sum = __dadd_rn(sum, valid ? (double)x : 0.0); }
-    __device__ __forceinline__ void merge(const RedState& o) { sum = __dadd_rn(sum, o.sum); cnt += o.cnt; }
+    __device__ __forceinline__ void add_all_valid(T x) { sum = __dadd_rn(sum, (double)x); }
+    __device__ __forceinline__ void end_tile() {}
+    __device__ __forceinline__ void merge(const RedState& o) { sum = __dadd_rn(sum, o.sum); }
     __device__ __forceinline__ RedState shfl_xor(int o) const {
         RedState r;
         r.sum = __shfl_xor_sync(0xffffffffu, sum, o);
-        r.cnt = __shfl_xor_sync(0xffffffffu, cnt, o);
         return r;
     }
-    __device__ __forceinline__ void to_dev(AggDev* d) const {
-        d->sum_bits = (unsigned long long)__double_as_longlong(sum); d->min_bits = 0; d->max_bits = 0; d->count = cnt;
-    }
-    __device__ __forceinline__ void from_dev(const AggDev* d) {
-        sum = __longlong_as_double((long long)__ldcg(&d->sum_bits)); cnt = __ldcg(&d->count);
+    __device__ __forceinline__ void to_dev(AggDev* d, unsigned long long cnt) const {
+        d->sum_bits = (unsigned long long)__double_as_longlong(sum); d->min_bits = ~0ull; d->max_bits = 0; d->count = cnt;
     }
 };
 
-// Deterministic block reduction: xor-shuffle tree inside each warp, then warp 0 folds the warp results
-// with the same tree.  Result valid in thread 0.
-template <typename S>
-__device__ __forceinline__ void block_reduce(S& st, S* smem /* >= kThreads/32 */) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { S other = st.shfl_xor(o); st.merge(other); }
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __syncthreads();  // smem may still be in use by a previous call
-    if (lane == 0) smem[warp] = st;
-    __syncthreads();
-    if (warp == 0) {
-        S v; v.init();
-        if (lane < kThreads / 32) v = smem[lane];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) { S other = v.shfl_xor(o); v.merge(other); }
-        st = v;
-    }
-}
-
-template <typename T>
+// K consecutive tiles per CTA, not persistent (measured on the read-only f64 stream: 7.2 TB/s for K <= 2,
+// 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  Floats use K = 1; integers
+// K = 4 to amortise the heavier 3-value block reduction.  One partial per CTA in CTA order; launch_finish
+// (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
+template <typename T, int K>
 __global__ void __launch_bounds__(kThreads)
-k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ partials,
-         unsigned int* __restrict__ ticket, AggDev* __restrict__ result) {
+k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ cta_partials) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
-    constexpr uint32_t FULLMASK = (1u << E) - 1u;
     using S = RedState<T>;
-    __shared__ S s_state[kThreads / 32];
-    __shared__ bool s_last;
+    __shared__ S s_state[kWarpsPerCta];
+    __shared__ unsigned int s_cnt[kWarpsPerCta];
 
     S st; st.init();
     unsigned int cnt = 0;
-
-    int c = 0;
-    int64_t c_tile0 = 0, c_tile_end = -1;
+    int c = -1;
+    int64_t c_tile0 = 0, c_tile_end = -1, len = 0, off = 0;
     const T* __restrict__ pi = nullptr;
     const uint32_t* __restrict__ vi = nullptr;
-    int64_t len = 0, off = 0;
 
-    for (int64_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        if (tile >= c_tile_end) {  // moved into another chunk (tiles are visited in increasing order)
+#pragma unroll 1
+    for (int kk = 0; kk < K; kk++) {
+        const int64_t tile = (int64_t)blockIdx.x * K + kk;
+        if (tile >= total_tiles) break;
+        if (tile >= c_tile_end) {  // first tile, or moved into the next chunk
             c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
             pi = (const T*)descs[c].in;
             vi = descs[c].vin;
@@ -142,16 +129,22 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
             Vec<T, E> x[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
-            MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
-            if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
-            uint32_t m[kUnroll];
+            if (vi) {
+                MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+                mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) m[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
+                for (int j = 0; j < kUnroll; j++) {
+                    const uint32_t m = mask_get<E, kUnroll>(rv, j);
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) {
+                    for (int e = 0; e < E; e++) st.add(x[j].e[e], (m >> e) & 1u);
+                    cnt += __popc(m);
+                }
+            } else {
 #pragma unroll
-                for (int e = 0; e < E; e++) st.add(x[j].e[e], (m[j] >> e) & 1u);
-                cnt += __popc(m[j]);
+                for (int j = 0; j < kUnroll; j++)
+#pragma unroll
+                    for (int e = 0; e < E; e++) st.add_all_valid(x[j].e[e]);
+                cnt += kUnroll * E;
             }
         } else {
 #pragma unroll 1
@@ -166,70 +159,52 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
                 cnt += __popc(m);
             }
         }
+        st.end_tile();
     }
-    st.cnt = cnt;
-
-    block_reduce(st, s_state);
-    if (threadIdx.x == 0) {
-        st.to_dev(&partials[blockIdx.x]);
-        __threadfence();
-        const unsigned int t = atomicAdd(ticket, 1u);
-        s_last = (t == gridDim.x - 1);
-    }
+    // fixed xor-shuffle tree inside each warp, then thread 0 folds the warp results in warp order
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { S other = st.shfl_xor(o); st.merge(other); }
+    const unsigned int wcnt = __reduce_add_sync(0xffffffffu, cnt);
+    if ((threadIdx.x & 31) == 0) { s_state[threadIdx.x >> 5] = st; s_cnt[threadIdx.x >> 5] = wcnt; }
     __syncthreads();
-    if (!s_last) return;
-
-    // Last CTA to finish: fold the per-CTA partials in CTA order (fixed order => deterministic).
-    __threadfence();
-    S acc; acc.init();
-    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
-        S p; p.init(); p.from_dev(&partials[i]);
-        acc.merge(p);
-    }
-    block_reduce(acc, s_state);
     if (threadIdx.x == 0) {
-        acc.to_dev(result);  // result may live in device-mapped host memory
-        __threadfence_system();
-        *ticket = 0;  // ready for the next launch on this stream
+        S t = s_state[0];
+        unsigned long long total = s_cnt[0];
+#pragma unroll
+        for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_state[w]); total += s_cnt[w]; }
+        t.to_dev(&cta_partials[blockIdx.x], total);
     }
 }
 
-template <typename T>
-static int occupancy_grid(int sm_count) {
-    int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_reduce<T>, kThreads, 0) != cudaSuccess || per_sm < 1)
-        per_sm = 4;
-    if (per_sm > 8) per_sm = 8;
-    return sm_count * per_sm;
+constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 1;
+int64_t reduce_partials(int dtype, int64_t tiles) {
+    const int k = dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt;
+    return (tiles + k - 1) / k;
 }
 
-int reduce_grid(int sm_count) { return sm_count * 8; }  // upper bound used to size the partials buffer
-
 template <typename T>
-static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, int grid_cap, AggDev* partials, unsigned int* ticket,
-                              AggDev* result, cudaStream_t s) {
-    static int grid_for_device = 0;  // one device per process (one process per GPU)
-    if (grid_for_device == 0) grid_for_device = occupancy_grid<T>(grid_cap / 8);
-    int64_t grid = grid_for_device;
-    if (grid > tiles) grid = tiles;
-    if (grid < 1) grid = 1;
-    k_reduce<T><<<(unsigned)grid, kThreads, 0, s>>>(d, n, tiles, partials, ticket, result);
+static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+    constexpr int K = RedInfo<T>::is_float ? kReduceTilesFloat : kReduceTilesInt;
+    k_reduce<T, K><<<(unsigned)((tiles + K - 1) / K), kThreads, 0, s>>>(d, n, tiles, partials);
     return cudaGetLastError();
 }
 
-cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, int grid_cap, AggDev* partials,
-                          unsigned int* ticket, AggDev* result, cudaStream_t s) {
+// Per-tile partials of chunks described by d (k_finish folds them; with tiles == 0 nothing is launched and
+// k_finish produces the identity).
+cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+    if (tiles <= 0) return cudaSuccess;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (dtype) {
-        case T_I8: return launch_one<int8_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_I16: return launch_one<int16_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_I32: return launch_one<int32_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_I64: return launch_one<int64_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_U8: return launch_one<uint8_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_U16: return launch_one<uint16_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_U32: return launch_one<uint32_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_U64: return launch_one<uint64_t>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_F32: return launch_one<float>(d, n, tiles, grid_cap, partials, ticket, result, s);
-        case T_F64: return launch_one<double>(d, n, tiles, grid_cap, partials, ticket, result, s);
+        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, s);
+        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, s);
+        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, s);
+        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, s);
+        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, s);
+        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, s);
+        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, s);
+        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, s);
+        case T_F32: return launch_one<float>(d, n, tiles, partials, s);
+        case T_F64: return launch_one<double>(d, n, tiles, partials, s);
         default: return cudaErrorInvalidValue;
     }
 }

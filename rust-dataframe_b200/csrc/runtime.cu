@@ -87,7 +87,7 @@ struct bdf_col {
 // Result of an aggregate that is still in flight (or done): a pinned slot + the event that guards it.
 struct bdf_future {
     int dtype;
-    int fused;       // 1: partials use order-preserving unsigned keys for min/max (k_binary AGG), 0: k_reduce format
+    int fused;       // which kernel produced the keys: 1 = k_binary AGG, 2 = k_reduce (see convert_agg)
     int slot;        // index into h_agg
     int64_t rows;
     cudaEvent_t ev;
@@ -115,14 +115,15 @@ struct bdf_ctx {
     AggDev* h_agg_dev = nullptr;    // device-side address of h_agg
     int* h_flag = nullptr;          // pinned
     // device scratch
-    AggDev* d_partials = nullptr;
+    AggDev* d_partials = nullptr;       // per-tile partials of k_reduce (compute stream only)
+    size_t red_part_cap = 0;
+    AggDev* d_stage2 = nullptr;         // k_finish staging for the k_reduce path
     unsigned int* d_ticket = nullptr;   // [0]: k_reduce, [1]: k_finish
     AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
     int fut_next = 0;                   // ring cursor over the future half of h_agg
     struct PartBuf { AggDev* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } part[3];
     int part_next = 0;                  // per-tile partials of fused aggregates: 3 persistent buffers in rotation
-    int red_grid_cap = 0;
     cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -351,10 +352,20 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
     }
     RedDesc* dd = (RedDesc*)dp;
     CK(desc_upload(c, dd, hd, (size_t)n * sizeof(RedDesc)));
+    if ((size_t)tiles > c->red_part_cap) {  // grow the per-tile partials buffer (rare): drain its users first
+        CK(cudaStreamSynchronize(c->s_compute));
+        if (c->d_partials) CK(cudaFree(c->d_partials));
+        c->d_partials = nullptr; c->red_part_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)tiles * 2, 65536);
+        CK(cudaMalloc((void**)&c->d_partials, cap * sizeof(AggDev)));
+        c->red_part_cap = cap;
+    }
     {
         LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));
-        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->red_grid_cap, c->d_partials, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
+        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->s_compute));
     }
+    c->launches++;
+    CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
     return BDF_OK;
 }
 
@@ -740,7 +751,8 @@ static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf
         uint32_t fb; memcpy(&fb, &f, 4);
         out->sum = fb;
     } else {
-        const uint64_t flip = (fused && dtype_is_signed_int(dtype)) ? (1ull << (8 * w - 1)) : 0ull;
+        // k_binary AGG (fused == 1) keys flip the sign bit of T; k_reduce (fused == 2) keys flip bit 63 of the extended value
+        const uint64_t flip = !dtype_is_signed_int(dtype) ? 0ull : (fused == 1 ? (1ull << (8 * w - 1)) : (1ull << 63));
         out->sum = a.sum_bits & mask;
         out->min = (a.min_bits ^ flip) & mask;
         out->max = (a.max_bits ^ flip) & mask;
@@ -753,7 +765,7 @@ static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf
 static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
     const int64_t n = (int64_t)col->chunks.size();
     bdf_future* f = nullptr;
-    TRY(future_new(c, col->dtype, 0, col->total_len, &f));
+    TRY(future_new(c, col->dtype, 2, col->total_len, &f));
     wait_groups(c->s_compute, col, 0, n);
     int st = reduce_range(c, col, 0, n, f->slot);
     cudaError_t e = cudaSuccess;
@@ -876,6 +888,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->h_agg) cudaFreeHost(c->h_agg);
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->d_partials) cudaFree(c->d_partials);
+    if (c->d_stage2) cudaFree(c->d_stage2);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->flush_buf) cudaFree(c->flush_buf);
@@ -919,8 +932,7 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaHostAlloc((void**)&c->h_agg, 2 * kAggSlots * sizeof(AggDev), cudaHostAllocMapped));
     CK(cudaHostGetDevicePointer((void**)&c->h_agg_dev, c->h_agg, 0));
     CK(cudaHostAlloc((void**)&c->h_flag, sizeof(int), cudaHostAllocDefault));
-    c->red_grid_cap = reduce_grid(c->sm_count);
-    CK(cudaMalloc((void**)&c->d_partials, (size_t)c->red_grid_cap * sizeof(AggDev)));
+    CK(cudaMalloc((void**)&c->d_stage2, (size_t)c->sm_count * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_stage, (size_t)c->sm_count * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
