@@ -31,6 +31,12 @@ for case in cases:
         elif case == "sum_f64":
             a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0)
             a.sum()
+        elif case == "cast_i32_f64":
+            a = G(rdf.I32, lens, 2, col_id=9, null_mod=10)
+            a.cast(rdf.F64).free()
+        elif case == "add_i64_agg":
+            a = G(rdf.I64, lens, 3, col_id=7, null_mod=10); b = G(rdf.I64, lens, 3, col_id=8)
+            a.binary_agg(N.ADD, b)[0].free()
         elif case == "add_sum_fused":
             a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0); b = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=1)
             a.binary_agg(N.ADD, b)[0].free()

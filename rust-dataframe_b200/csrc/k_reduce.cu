@@ -92,7 +92,7 @@ struct RedState<T, true> {
 };
 
 // K consecutive tiles per CTA, not persistent (measured on the read-only f64 stream: 7.2 TB/s for K <= 2,
-// 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  Floats use K = 1; integers
+// 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  Floats use K = 2; integers
 // K = 4 to amortise the heavier 3-value block reduction.  One partial per CTA in CTA order; launch_finish
 // (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
 template <typename T, int K>
@@ -176,7 +176,7 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
     }
 }
 
-constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 1;
+constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 2;
 int64_t reduce_partials(int dtype, int64_t tiles) {
     const int k = dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt;
     return (tiles + k - 1) / k;

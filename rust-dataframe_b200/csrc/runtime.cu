@@ -361,11 +361,11 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
         c->red_part_cap = cap;
     }
     {
-        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));
+        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // k_reduce + k_finish
         CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->s_compute));
+        c->launches++;
+        CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
     }
-    c->launches++;
-    CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
     return BDF_OK;
 }
 
