@@ -96,6 +96,32 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(seen), "samples": len(win)}
 
 
+def bind_to_gpu_numa_node(device_index: int):
+    """Pin this process (and therefore its pinned host buffers, by first touch) to the NUMA node the GPU hangs off.
+    Pure placement: host<->device copies then do not cross the inter-socket link.  Best effort."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = f"/sys/bus/pci/devices/{bus[-12:].lower()}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -440,6 +466,7 @@ def main():
         run_reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
         return
     rank, world, local = dist_setup(args.gpus)
+    bind_to_gpu_numa_node(local)
     try:
         run_gpu_arm(args, rank, world, local)
     finally:
