@@ -1,0 +1,37 @@
+"""Small ragged shapes through every kernel once (for compute-sanitizer memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+import rust_dataframe_b200 as rdf
+from rust_dataframe_b200 import native as N
+
+rng = np.random.default_rng(1)
+lens = [0, 1, 33, 2047, 2049, 5000]
+P = rdf.PrimitiveArray
+for dtype in (rdf.I8, rdf.I16, rdf.I32, rdf.I64, rdf.U8, rdf.F32, rdf.F64):
+    npdt = rdf.NP_DTYPES[dtype]
+    def col(nulls, nz=False):
+        out = []
+        for k, n in enumerate(lens):
+            v = (rng.uniform(1, 100, n + 9) if npdt.kind == "f" else rng.integers(1, 100, n + 9)).astype(npdt)
+            a = P.from_numpy(v, rng.random(n + 9) > 0.2) if nulls else P.from_numpy(v)
+            a.null_count = -1 if nulls else 0
+            out.append(a.slice(3 + k, n))
+        return out
+    a, b = col(True), col(False)
+    for fn in (rdf.ScalarFunctions.add, rdf.ScalarFunctions.multiply, rdf.ScalarFunctions.divide):
+        fn(a, b)
+    rdf.AggregateFunctions.all([c for c in a if c.length])
+    rdf.AggregateFunctions.count(a)
+    for to in (rdf.I8, rdf.U32, rdf.F64, rdf.I64):
+        rdf.cast(a, to)
+    if dtype in (rdf.F32, rdf.F64):
+        rdf.ScalarFunctions.sin(a); rdf.ScalarFunctions.tan(b); rdf.ScalarFunctions.atan2(a[3], b[3])
+    ca, cb = rdf.Column.upload_many([a, b], asynchronous=True)
+    cc, fut = ca.binary_agg_async(N.ADD, cb)
+    fut.result(); cc.download(); ca.download()
+    g = rdf.Column.generate(dtype, lens, kind=2 if npdt.kind != "f" else 0, null_mod=3)
+    g.download(); g.aggregate_all()
+    if dtype not in (rdf.I64,):
+        rdf.AggregateFunctions.avg([c for c in a if c.length])
+print("sanitize cases done")

@@ -631,3 +631,27 @@ def test_split_download_overlaps_and_matches(rdf, ctx, oracle):
     ca.download_begin(into2)
     for g, src in zip(ca.download_end(into2), a):
         assert np.array_equal(g.valid_mask(), src.valid_mask()) and np.array_equal(g.value_slice(), src.value_slice())
+
+
+def test_concurrent_host_threads_share_one_context(rdf, ctx, oracle):
+    """The reference calls arrive from rayon workers / user threads; one bdf_ctx must serialise them safely."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    rng = np.random.default_rng(88)
+    cols = [(make_column(rdf, rng, rdf.I64, [5000, 33, 20000], 0.1, True), make_column(rdf, rng, rdf.I64, [5000, 33, 20000], 0.2, False))
+            for _ in range(8)]
+    want = [oracle.col_binary(oracle.ADD, oracle.I64, a, b)[1] for a, b in cols]
+    wsum = [int(oracle.aggregate(oracle.SUM, oracle.I64, w)[1]) for w in want]
+
+    def work(k):
+        a, b = cols[k % len(cols)]
+        out = rdf.ScalarFunctions.add(a, b)
+        s = rdf.AggregateFunctions.sum(out)
+        return k % len(cols), out, int(s)
+
+    with ThreadPoolExecutor(8) as ex:
+        results = list(ex.map(work, range(64)))
+    for k, out, s in results:
+        assert s == wsum[k]
+        for g, w in zip(out, want[k]):
+            assert_same_array(g, w, what=f"threaded add {k}")
