@@ -116,6 +116,18 @@ def main():
     i8 = i64.cast(rdf.I8)
     report("add i8", "extra", timed(ctx, lambda: i8.add(i8)), "binary")
     report("sum/min/max/count i8", "extra", timed(ctx, lambda: i8.aggregate_all()), "reduce")
+    # ---- N2 (next row): BooleanFilter compare + ChunkedArray::filter ----
+    report("compare f64 > scalar", "N2", timed(ctx, lambda: a.gt(0.0)), "compare")
+    report("compare f64 > f64", "N2", timed(ctx, lambda: a.gt(b)), "compare")
+    m_half = a.gt(0.0)
+    m_rare = a.gt(980.0)
+    an = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=11, null_mod=10)
+    for name, fn in (("filter f64, 50% kept", lambda: a.filter(m_half)), ("filter f64, 1% kept", lambda: a.filter(m_rare)),
+                     ("filter f64 10% nulls, 50% kept", lambda: an.filter(m_half)), ("filter i32 10% nulls, 50% kept", lambda: i32n.filter(m_half))):
+        res = timed(ctx, fn)
+        ms, nbytes, rows = res["filter"]   # median over both launches (count+scan, scatter): report their sum
+        recs_ms = ms
+        report(name + " [per launch median]", "N2", res, "filter")
     if args.json:
         with open(args.json, "w") as f:
             json.dump({"rows": args.rows, "peak_GBs_measured": pk, "results": rows_out}, f, indent=1)

@@ -65,6 +65,12 @@ typedef enum {
 
 typedef enum { BDF_SUM = 0, BDF_MIN, BDF_MAX, BDF_COUNT, BDF_NAGG } bdf_aggop;
 
+/* SURVEY 8(f) N2 (the step after the hot path): boolean columns are Arrow BooleanArrays -- `values` is a bit-packed
+ * LSB-first bitmap whose `offset` counts bits -- identified by dtype BDF_BOOL in bdf_upload / bdf_col_describe. */
+#define BDF_BOOL 10
+typedef enum { BDF_GT = 0, BDF_GE, BDF_EQ, BDF_NE, BDF_LT, BDF_LE } bdf_cmpop;
+typedef enum { BDF_AND = 0, BDF_OR, BDF_NOT } bdf_boolop;
+
 typedef enum {
     BDF_OK = 0, BDF_LENGTH_MISMATCH = 1, BDF_DIVIDE_BY_ZERO = 2, BDF_UNSUPPORTED = 3, BDF_CUDA = 4,
     BDF_NCCL = 5 /* reserved */, BDF_OOM = 6, BDF_WOULD_PANIC = 7, BDF_INVALID = 8
@@ -148,6 +154,16 @@ int  bdf_aggregate_dev(bdf_ctx* ctx, int op, const bdf_col* in, void* out_scalar
 int  bdf_aggregate_all_dev(bdf_ctx* ctx, const bdf_col* in, bdf_agg4* out);
 int  bdf_avg_dev(bdf_ctx* ctx, const bdf_col* in, double* out, int32_t* is_some);
 int  bdf_download(bdf_ctx* ctx, const bdf_col* col, bdf_out* out /* n_chunks entries */);
+/* ---- N2: BooleanFilter comparisons / boolean kernels / filter on device columns ------------------------------
+ * bdf_compare_dev  BooleanFilter::{Gt,Ge,Eq,Ne,Lt,Le} (src/expression.rs:820-852): both sides are cast to Float64, then
+ *                  compared (IEEE, computed under nulls); validity = AND.  right == NULL compares with `scalar`
+ *                  (BooleanInput::Scalar broadcast, :783-802).  Result: a BDF_BOOL column.
+ * bdf_boolean_dev  arrow compute::{and,or,not} on boolean columns (values op values, validity AND); b ignored for NOT.
+ * bdf_filter_dev   ChunkedArray::filter (src/table.rs:97-107): arrow compute::filter per chunk pair; a slot is kept
+ *                  iff the mask is valid and true there.  Result chunk lengths are data dependent (bdf_col_chunk_info). */
+int  bdf_compare_dev(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, double scalar, bdf_col** out);
+int  bdf_boolean_dev(bdf_ctx* ctx, int op, const bdf_col* a, const bdf_col* b, bdf_col** out);
+int  bdf_filter_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* mask, bdf_col** out);
 /* Split download: _begin enqueues the device->host copies (they start as soon as each chunk group is
  * ready), _end waits for them and fills len / null_count / has_validity.  Same `out` array for both. */
 int  bdf_download_begin(bdf_ctx* ctx, const bdf_col* col, bdf_out* out);
@@ -173,7 +189,7 @@ typedef struct {
     int64_t bytes;    /* algorithmic bytes of the launch (SURVEY 8(d) per-row figure x rows) */
     float   ms;       /* device time between the bracketing events */
 } bdf_launch_record;
-typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG } bdf_kernel_id;
+typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER } bdf_kernel_id;
 int     bdf_profile_enable(bdf_ctx* ctx, int on);
 int     bdf_profile_read(bdf_ctx* ctx, bdf_launch_record* buf, int64_t cap, int64_t* n); /* syncs; drains */
 int64_t bdf_launch_count(bdf_ctx* ctx);           /* kernels launched since bdf_init */

@@ -543,6 +543,87 @@ int orc_sum_exact(int dtype, int64_t n, const orc_view* chunks, long double* sum
 }
 
 /* ------------------------------------------------------------------------------------------------ */
+/* N2: BooleanFilter comparisons, boolean kernels, filter (see oracle.h).                             */
+
+int orc_compare(int op, int ltype, const orc_view* l, int rtype, const orc_view* r, int use_scalar, double scalar, orc_out* out) {
+    if (op < ORC_GT || op > ORC_LE || ltype < 0 || ltype >= ORC_NTYPES) return ORC_UNSUPPORTED;
+    if (!use_scalar && (r == NULL || rtype < 0 || rtype >= ORC_NTYPES)) return ORC_UNSUPPORTED;
+    if (!use_scalar && l->len != r->len) return ORC_LENGTH_MISMATCH;
+    const int64_t n = l->len;
+    const int has_v = l->validity != NULL || (!use_scalar && r->validity != NULL);
+    out_begin(out, n, has_v);
+    memset(out->values, 0, (size_t)((n + 7) / 8));
+    uint8_t* bits = (uint8_t*)out->values;
+    for (int64_t i = 0; i < n; i++) {
+        /* cast(.., Float64): numeric_cast appends NULL (payload 0) for null slots; a Float64 input is cloned */
+        const double a = (ltype != ORC_F64 && !view_valid(l, i)) ? 0.0 : load_as_f64(ltype, l->values, l->offset + i);
+        const double b = use_scalar ? scalar
+                         : (rtype != ORC_F64 && !view_valid(r, i)) ? 0.0 : load_as_f64(rtype, r->values, r->offset + i);
+        int t;
+        switch (op) {
+            case ORC_GT: t = a > b; break;
+            case ORC_GE: t = a >= b; break;
+            case ORC_EQ: t = a == b; break;
+            case ORC_NE: t = a != b; break;
+            case ORC_LT: t = a < b; break;
+            default: t = a <= b; break;
+        }
+        if (t) bit_set(bits, i);
+        if (has_v) {
+            const int valid = view_valid(l, i) && (use_scalar || view_valid(r, i));
+            if (valid) bit_set(out->validity, i); else out->null_count++;
+        }
+    }
+    return ORC_OK;
+}
+
+int orc_bool(int op, const orc_view* a, const orc_view* b, orc_out* out) {
+    if (op < ORC_AND || op > ORC_NOT) return ORC_UNSUPPORTED;
+    if (op != ORC_NOT && a->len != b->len) return ORC_LENGTH_MISMATCH;
+    const int64_t n = a->len;
+    const int has_v = a->validity != NULL || (op != ORC_NOT && b->validity != NULL);
+    out_begin(out, n, has_v);
+    memset(out->values, 0, (size_t)((n + 7) / 8));
+    for (int64_t i = 0; i < n; i++) {
+        const int x = bit_get((const uint8_t*)a->values, a->offset + i);
+        const int y = op == ORC_NOT ? 0 : bit_get((const uint8_t*)b->values, b->offset + i);
+        const int t = op == ORC_AND ? (x & y) : op == ORC_OR ? (x | y) : !x;
+        if (t) bit_set((uint8_t*)out->values, i);
+        if (has_v) {
+            const int valid = view_valid(a, i) && (op == ORC_NOT || view_valid(b, i));
+            if (valid) bit_set(out->validity, i); else out->null_count++;
+        }
+    }
+    return ORC_OK;
+}
+
+int orc_filter(int dtype, const orc_view* values, const orc_view* mask, orc_out* out) {
+    if (values->len != mask->len) return ORC_LENGTH_MISMATCH;
+    const int w = dtype == ORC_BOOL ? 0 : orc_width(dtype);
+    if (dtype != ORC_BOOL && w == 0) return ORC_UNSUPPORTED;
+    const int64_t n = values->len;
+    int64_t k = 0;
+    out->null_count = 0;
+    out->has_validity = values->validity != NULL;
+    if (out->validity) memset(out->validity, 0, (size_t)((n + 7) / 8));
+    if (dtype == ORC_BOOL) memset(out->values, 0, (size_t)((n + 7) / 8));
+    for (int64_t i = 0; i < n; i++) {
+        if (!view_valid(mask, i) || !bit_get((const uint8_t*)mask->values, mask->offset + i)) continue;  /* null mask = false */
+        if (dtype == ORC_BOOL) {
+            if (bit_get((const uint8_t*)values->values, values->offset + i)) bit_set((uint8_t*)out->values, k);
+        } else {
+            memcpy((char*)out->values + k * w, (const char*)values->values + (values->offset + i) * w, (size_t)w);
+        }
+        if (values->validity) {
+            if (view_valid(values, i)) bit_set(out->validity, k); else out->null_count++;
+        }
+        k++;
+    }
+    out->len = k;
+    return ORC_OK;
+}
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Counter-based generator.                                                             */
 
 uint64_t orc_splitmix64(uint64_t x) {

@@ -102,6 +102,25 @@ int orc_avg(int dtype, int64_t n, const orc_view* chunks, double* out, int32_t* 
 /* Float-sum bounds: long-double Neumaier-compensated sum and sum of |x| over valid slots. */
 int orc_sum_exact(int dtype, int64_t n, const orc_view* chunks, long double* sum, long double* sum_abs);
 
+/* ---- the step right after the hot path -- BooleanFilter::eval_to_array + ChunkedArray::filter ----
+ * Boolean arrays are bit-packed (Arrow BooleanArray): `values` is an LSB-first bitmap, offset in bits.
+ *   orc_compare   BooleanFilter::{Gt,Ge,Eq,Ne,Lt,Le} (src/expression.rs:820-852): both sides are cast to Float64
+ *                 (numeric_cast, `as f64`), then arrow compute::{gt,gt_eq,eq,neq,lt,lt_eq} on Float64Arrays: IEEE
+ *                 comparison per slot (computed under nulls), validity = AND, absent if neither side has one.
+ *                 A NULL right view with `use_scalar` broadcasts BooleanInput::Scalar (vec![v; len], :783-802).
+ *   orc_bool      arrow compute::{and,or,not} on BooleanArrays: values op values, validity AND.  (The reference's
+ *                 And/Or arms reinterpret Float64 buffers as bitmaps -- expression.rs:808-819 -- which is not
+ *                 restated; Not casts to Boolean first.)
+ *   orc_filter    arrow compute::filter(array, mask) per chunk (src/table.rs:97-107): keeps slot i iff the mask is
+ *                 valid and true there; values and validity of kept slots are compacted in order.
+ * No reference test pins any of this ("parity unpinned"); pyarrow cross-checks it in tests/test_oracle_golden.py. */
+enum { ORC_GT = 0, ORC_GE, ORC_EQ, ORC_NE, ORC_LT, ORC_LE };
+enum { ORC_AND = 0, ORC_OR, ORC_NOT };
+#define ORC_BOOL 10
+int orc_compare(int op, int ltype, const orc_view* l, int rtype, const orc_view* r, int use_scalar, double scalar, orc_out* out);
+int orc_bool(int op, const orc_view* a, const orc_view* b, orc_out* out);
+int orc_filter(int dtype, const orc_view* values, const orc_view* mask, orc_out* out);
+
 /* Counter-based synthetic data; the CUDA generator in the product reproduces it bit-for-bit.
  * kind 0: real uniform [lo,hi)   1: real +-[1,2)   2: integer, full range of the type
  * kind 3: integer uniform [-2^40, 2^40) (truncated to the type)

@@ -171,6 +171,82 @@ def sum_exact(dtype: int, chunks: Sequence):
     return np.longdouble(s.value), np.longdouble(sa.value)
 
 
+GT, GE, EQ, NE, LT, LE = range(6)
+AND, OR, NOT = range(3)
+BOOL = 10
+
+
+def _bool_out(n: int):
+    out = (Out * 1)()
+    v = np.zeros((n + 7) // 8, dtype=np.uint8)
+    b = np.zeros((n + 7) // 8, dtype=np.uint8)
+    out[0].values = v.ctypes.data if v.size else 0
+    out[0].validity = b.ctypes.data if b.size else 0
+    return out, v, b
+
+
+@dataclass
+class OracleBoolArray:
+    """Arrow BooleanArray: bit-packed values + optional validity."""
+    values: np.ndarray
+    validity: Optional[np.ndarray]
+    length: int
+    null_count: int
+    dtype = BOOL
+    offset = 0
+
+    def value_bits(self) -> np.ndarray:
+        return np.unpackbits(self.values, bitorder="little")[: self.length].astype(bool)
+
+    def valid_mask(self) -> np.ndarray:
+        if self.validity is None:
+            return np.ones(self.length, dtype=bool)
+        return np.unpackbits(self.validity, bitorder="little")[: self.length].astype(bool)
+
+
+def compare(op: int, left, right=None, scalar: Optional[float] = None):
+    """BooleanFilter::{Gt,..}: one chunk.  right=None + scalar broadcasts a BooleanInput::Scalar."""
+    L = lib()
+    L.orc_compare.argtypes = [C.c_int, C.c_int, C.POINTER(View), C.c_int, C.POINTER(View), C.c_int, C.c_double, C.POINTER(Out)]
+    out, v, b = _bool_out(left.length)
+    use_scalar = right is None
+    st = L.orc_compare(op, left.dtype, _views([left]), 0 if use_scalar else right.dtype, None if use_scalar else _views([right]),
+                       1 if use_scalar else 0, float(scalar or 0.0), out)
+    if st != OK:
+        return st, None
+    return st, OracleBoolArray(v, b if out[0].has_validity else None, int(out[0].len), int(out[0].null_count))
+
+
+def boolean(op: int, a, b=None):
+    L = lib()
+    L.orc_bool.argtypes = [C.c_int, C.POINTER(View), C.POINTER(View), C.POINTER(Out)]
+    out, v, bb = _bool_out(a.length)
+    st = L.orc_bool(op, _views([a]), None if b is None else _views([b]), out)
+    if st != OK:
+        return st, None
+    return st, OracleBoolArray(v, bb if out[0].has_validity else None, int(out[0].len), int(out[0].null_count))
+
+
+def filter_chunk(values, mask):
+    """arrow::compute::filter for one chunk; values may be a primitive chunk or an OracleBoolArray."""
+    L = lib()
+    L.orc_filter.argtypes = [C.c_int, C.POINTER(View), C.POINTER(View), C.POINTER(Out)]
+    n = values.length
+    out = (Out * 1)()
+    is_bool = values.dtype == BOOL
+    v = np.zeros((n + 7) // 8, dtype=np.uint8) if is_bool else np.zeros(n, dtype=NP_DTYPES[values.dtype])
+    b = np.zeros((n + 7) // 8, dtype=np.uint8)
+    out[0].values = v.ctypes.data if v.size else 0
+    out[0].validity = b.ctypes.data if b.size else 0
+    st = L.orc_filter(values.dtype, _views([values]), _views([mask]), out)
+    if st != OK:
+        return st, None
+    k = int(out[0].len)
+    if is_bool:
+        return st, OracleBoolArray(v[: (k + 7) // 8], b[: (k + 7) // 8] if out[0].has_validity else None, k, int(out[0].null_count))
+    return st, OracleArray(values.dtype, v[:k], b[: (k + 7) // 8] if out[0].has_validity else None, int(out[0].null_count))
+
+
 def generate(dtype: int, kind: int, lo: float, hi: float, seed: int, col: int, row0: int, length: int,
              null_mod: int = 0) -> OracleArray:
     v = np.zeros(length, dtype=NP_DTYPES[dtype])

@@ -20,8 +20,11 @@ ADD, SUB, MUL, DIV, ATAN2, HYPOT, LOG = range(7)
 SUM, MIN, MAX, COUNT = range(4)
 OK, LENGTH_MISMATCH, DIVIDE_BY_ZERO, UNSUPPORTED, CUDA, NCCL, OOM, WOULD_PANIC, INVALID = range(9)
 ASYNC = 1
-K_BINARY, K_UNARY, K_CAST, K_REDUCE, K_GENERATE, K_AVG = range(6)
-KERNEL_NAMES = ["binary", "unary", "cast", "reduce", "generate", "avg"]
+K_BINARY, K_UNARY, K_CAST, K_REDUCE, K_GENERATE, K_AVG, K_COMPARE, K_FILTER = range(8)
+KERNEL_NAMES = ["binary", "unary", "cast", "reduce", "generate", "avg", "compare", "filter"]
+GT, GE, EQ, NE, LT, LE = range(6)
+AND, OR, NOT = range(3)
+BOOL = 10
 
 
 class View(C.Structure):
@@ -107,6 +110,9 @@ def lib() -> C.CDLL:
         "bdf_aggregate_dev": ([vp, C.c_int, vp, vp, P(i32)], C.c_int),
         "bdf_aggregate_all_dev": ([vp, vp, P(Agg4)], C.c_int),
         "bdf_avg_dev": ([vp, vp, P(C.c_double), P(i32)], C.c_int),
+        "bdf_compare_dev": ([vp, C.c_int, vp, vp, C.c_double, P(vp)], C.c_int),
+        "bdf_boolean_dev": ([vp, C.c_int, vp, vp, P(vp)], C.c_int),
+        "bdf_filter_dev": ([vp, vp, vp, P(vp)], C.c_int),
         "bdf_download": ([vp, vp, P(Out)], C.c_int),
         "bdf_download_begin": ([vp, vp, P(Out)], C.c_int),
         "bdf_download_end": ([vp, vp, P(Out)], C.c_int),
@@ -139,7 +145,7 @@ EXPORTED_SYMBOLS = [
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
     "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_upload_many", "bdf_col_wait", "bdf_col_describe",
     "bdf_col_chunk_info", "bdf_binary_dev", "bdf_unary_dev", "bdf_cast_dev", "bdf_aggregate_dev",
-    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
+    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_compare_dev", "bdf_boolean_dev", "bdf_filter_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
     "bdf_binary_agg_dev", "bdf_binary_agg_dev_async", "bdf_aggregate_all_dev_async", "bdf_future_wait", "bdf_col_free", "bdf_profile_enable", "bdf_profile_read",
     "bdf_launch_count", "bdf_timer_start", "bdf_timer_stop", "bdf_flush_l2", "bdf_generate",
 ]
@@ -290,6 +296,15 @@ def alloc_outputs(dtype: int, lens: Sequence[int], ctx: Optional[Context] = None
     """Caller-side output buffers (the Rust shim uses MutableBuffer::new): returns (Out[], [(values, bitmap)])."""
     outs = (Out * max(len(lens), 1))()
     bufs = []
+    if dtype == BOOL:  # bit-packed values
+        for i, n in enumerate(lens):
+            v = np.zeros((n + 7) // 8, dtype=np.uint8)
+            b = np.zeros((n + 7) // 8, dtype=np.uint8)
+            outs[i].values = v.ctypes.data if v.size else None
+            outs[i].validity = b.ctypes.data if b.size else None
+            outs[i].len = n
+            bufs.append((v, b, None))
+        return outs, bufs
     for i, n in enumerate(lens):
         if pinned:
             w = width_of(dtype)
@@ -311,6 +326,13 @@ def alloc_outputs(dtype: int, lens: Sequence[int], ctx: Optional[Context] = None
 
 def collect_outputs(dtype: int, outs, bufs) -> List[PrimitiveArray]:
     res = []
+    if dtype == BOOL:
+        from .arrays import BooleanArray
+
+        for i, (v, b, keep) in enumerate(bufs):
+            has_v = bool(outs[i].has_validity)
+            res.append(BooleanArray(v, b if has_v else None, 0, int(outs[i].len), int(outs[i].null_count) if has_v else 0))
+        return res
     for i, (v, b, keep) in enumerate(bufs):
         has_v = bool(outs[i].has_validity)
         res.append(PrimitiveArray(dtype, v, b if has_v else None, 0, int(outs[i].len),

@@ -156,5 +156,43 @@ class PrimitiveArray:
         return f"PrimitiveArray<{DTYPE_NAMES[self.dtype]}>(len={self.length}, offset={self.offset}, nulls={self.null_count})"
 
 
+class BooleanArray:
+    """Arrow BooleanArray chunk: bit-packed values (LSB first) + optional validity; `offset` counts bits."""
+
+    dtype = 10  # BDF_BOOL
+    __slots__ = ("values", "validity", "offset", "length", "null_count")
+
+    def __init__(self, values: np.ndarray, validity: Optional[np.ndarray] = None, offset: int = 0, length: int = 0,
+                 null_count: int = -1):
+        self.values = np.ascontiguousarray(values, dtype=np.uint8)
+        self.validity = None if validity is None else np.ascontiguousarray(validity, dtype=np.uint8)
+        self.offset, self.length = int(offset), int(length)
+        self.null_count = 0 if self.validity is None else int(null_count)
+
+    @classmethod
+    def from_numpy(cls, bits: np.ndarray, mask: Optional[np.ndarray] = None) -> "BooleanArray":
+        bits = np.asarray(bits, dtype=bool)
+        validity = None if mask is None else pack_validity(mask)
+        return cls(pack_validity(bits), validity, 0, bits.shape[0], 0 if mask is None else int((~np.asarray(mask, bool)).sum()))
+
+    def slice(self, offset: int, length: int) -> "BooleanArray":
+        return BooleanArray(self.values, self.validity, self.offset + offset, length, -1)
+
+    def value_bits(self) -> np.ndarray:
+        return np.unpackbits(self.values, bitorder="little")[self.offset:self.offset + self.length].astype(bool)
+
+    def valid_mask(self) -> np.ndarray:
+        if self.validity is None:
+            return np.ones(self.length, dtype=bool)
+        return np.unpackbits(self.validity, bitorder="little")[self.offset:self.offset + self.length].astype(bool)
+
+    def to_pylist(self) -> List:
+        v, m = self.value_bits(), self.valid_mask()
+        return [bool(v[i]) if m[i] else None for i in range(self.length)]
+
+    def __len__(self) -> int:
+        return self.length
+
+
 def chunk_lengths(chunks: Sequence[PrimitiveArray]) -> List[int]:
     return [c.length for c in chunks]

@@ -1,0 +1,382 @@
+// k_filter.cu -- SURVEY 8(f) N2, the step right after the hot path in a lazy pipeline:
+//   BooleanFilter::{Gt,Ge,Eq,Ne,Lt,Le}   reference src/expression.rs:820-852 -> arrow compute::{gt,gt_eq,eq,neq,lt,lt_eq}
+//                                         on Float64Arrays (both sides are cast to Float64 first)      -> k_compare
+//   compute::{and,or,not} on BooleanArrays (expression.rs:803-819; values op values, validity AND)    -> k_boolean
+//   ChunkedArray::filter -> arrow compute::filter per chunk (src/table.rs:97-107)                      -> k_filter_*
+// Boolean columns are Arrow BooleanArrays: bit-packed values (LSB first) + optional validity bitmap.
+//
+// Filter = stream compaction, three launches over ALL chunks of the column:
+//   1. k_filter_count   one warp per tile: popcount of (mask values AND mask validity)       (reads bitmaps only)
+//   2. k_filter_scan    one CTA per chunk: exclusive scan of its tile counts -> tile offsets, chunk totals
+//   3. k_filter_scatter one CTA per tile: per-step block scan of the per-thread counts, selected values are
+//      written in order at out[tile offset + rank]; kept validity bits are compacted per 32-slot word
+//      (each lane compacts its E bits, the 32/E lanes of a word OR them together) and OR-ed into the output
+//      bitmap with at most two atomics per 32 input slots.
+// Roofline: HBM, w x (1 + selectivity) + bitmaps bytes/row for the scatter; 16 B/row for a compare.
+#include "common.cuh"
+
+namespace bdf {
+
+enum : int { CMP_GT = 0, CMP_GE, CMP_EQ, CMP_NE, CMP_LT, CMP_LE };
+enum : int { BOOL_AND = 0, BOOL_OR, BOOL_NOT };
+
+template <int OP>
+__device__ __forceinline__ bool cmp_apply(double a, double b) {
+    if constexpr (OP == CMP_GT) return a > b;
+    else if constexpr (OP == CMP_GE) return a >= b;
+    else if constexpr (OP == CMP_EQ) return a == b;
+    else if constexpr (OP == CMP_NE) return a != b;
+    else if constexpr (OP == CMP_LT) return a < b;
+    else return a <= b;
+}
+
+// ---- compare: f64 (op) f64 | scalar -> boolean values + validity ---------------------------------------------
+template <int OP, bool SCALAR>
+__global__ void __launch_bounds__(kThreads)
+k_compare(const BinDesc* __restrict__ descs, int n_chunks, double scalar, uint32_t* __restrict__ warp_counts) {
+    constexpr int E = 2;
+    constexpr int TILE = kThreads * kUnroll * E;
+    const int64_t tile = blockIdx.x;
+    const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+    const double* __restrict__ pa = (const double*)descs[c].a;
+    const double* __restrict__ pb = (const double*)descs[c].b;
+    uint32_t* __restrict__ po = (uint32_t*)descs[c].out;   // boolean VALUES bitmap
+    const uint32_t* __restrict__ va = descs[c].va;
+    const uint32_t* __restrict__ vb = descs[c].vb;
+    uint32_t* __restrict__ vo = descs[c].vout;
+    const int64_t len = descs[c].len;
+    const int64_t offa = descs[c].offa, offb = descs[c].offb;
+    const int64_t base = (tile - descs[c].tile0) * TILE;
+    unsigned int nvalid = 0;
+    if (base + TILE <= len) {
+        Vec<double, E> a[kUnroll], b[kUnroll];
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+            a[j].load(pa + e0);
+            if constexpr (!SCALAR) b[j].load(pb + e0);
+        }
+        MaskRaw<E, kUnroll> ra, rb;
+        const int64_t e_first = base + (int64_t)threadIdx.x * E;
+        if (va) mask_issue<E, kUnroll>(ra, va, offa + e_first, (int64_t)kThreads * E);
+        if (vb) mask_issue<E, kUnroll>(rb, vb, offb + e_first, (int64_t)kThreads * E);
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+            uint32_t bits = 0;
+#pragma unroll
+            for (int e = 0; e < E; e++) bits |= (cmp_apply<OP>(a[j].e[e], SCALAR ? scalar : b[j].e[e]) ? 1u : 0u) << e;
+            store_bits<E>(po, e0, bits, true);
+            if (vo) {
+                uint32_t m = 3u;
+                if (va) m &= mask_get<E, kUnroll>(ra, j);
+                if (vb) m &= mask_get<E, kUnroll>(rb, j);
+                store_bits<E>(vo, e0, m, true);
+                nvalid += __popc(m);
+            }
+        }
+    } else {
+#pragma unroll 1
+        for (int j = 0; j < kUnroll; j++) {
+            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+            const uint32_t in_range = tail_mask<E>(e0, len);
+            uint32_t bits = 0, m = in_range;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if ((in_range >> e) & 1u) bits |= (cmp_apply<OP>(pa[e0 + e], SCALAR ? scalar : pb[e0 + e]) ? 1u : 0u) << e;
+            if (in_range) {
+                if (va) m &= load_bits<E>(va, offa + e0);
+                if (vb) m &= load_bits<E>(vb, offb + e0);
+            }
+            store_bits<E>(po, e0, bits, in_range != 0);
+            if (vo) {
+                store_bits<E>(vo, e0, m, in_range != 0);
+                nvalid += __popc(m);
+            }
+        }
+    }
+    if (vo) {
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+    }
+}
+
+// ---- and / or / not on boolean columns: one 32-slot word per thread and step ------------------------------------
+// BinDesc reuse: a/b = VALUES bitmaps of the inputs (offa/offb = their bit offsets), va/vb = validity bitmaps whose
+// bit offsets travel in the (otherwise unused for this kernel) high halves: see BoolDesc below.
+struct BoolDesc {
+    const uint32_t* a; const uint32_t* b; uint32_t* out;
+    const uint32_t* va; const uint32_t* vb; uint32_t* vout;
+    int64_t len; int64_t tile0;
+    int32_t offa, offb, voffa, voffb;
+};
+constexpr int kBoolTile = kThreads * kUnroll * 32;  // slots per tile
+
+template <int OP>
+__global__ void __launch_bounds__(kThreads)
+k_boolean(const BoolDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ warp_counts) {
+    const int64_t tile = blockIdx.x;
+    const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+    const BoolDesc d = descs[c];
+    const int64_t base = (tile - d.tile0) * kBoolTile;
+    unsigned int nvalid = 0;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * 32;
+        const uint32_t in_range = tail_mask<32>(e0, d.len);
+        if (in_range) {
+            const uint32_t x = load_bits<32>(d.a, d.offa + e0);
+            const uint32_t y = (OP == BOOL_NOT) ? 0u : load_bits<32>(d.b, d.offb + e0);
+            const uint32_t r = (OP == BOOL_AND) ? (x & y) : (OP == BOOL_OR) ? (x | y) : ~x;
+            d.out[e0 >> 5] = r & in_range;
+            if (d.vout) {
+                uint32_t m = in_range;
+                if (d.va) m &= load_bits<32>(d.va, d.voffa + e0);
+                if (OP != BOOL_NOT && d.vb) m &= load_bits<32>(d.vb, d.voffb + e0);
+                d.vout[e0 >> 5] = m;
+                nvalid += __popc(m);
+            }
+        }
+    }
+    if (d.vout) {
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+    }
+}
+
+// ---- filter -----------------------------------------------------------------------------------------------------
+struct FilterDesc {
+    const void* in; void* out;                     // values
+    const uint32_t* vin; uint32_t* vout;           // validity of the values (vout zero-initialised)
+    const uint32_t* mval; const uint32_t* mvalid;  // mask values / mask validity (nullptr = all valid)
+    int64_t len; int64_t tile0;
+    int32_t off, moff, mvoff, pad;
+};
+
+// 1. one warp per tile: selected slots of the tile
+__global__ void __launch_bounds__(kThreads)
+k_filter_count(const FilterDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, int tile_elems, unsigned int* __restrict__ tile_counts) {
+    const int64_t tile = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
+    if (tile >= total_tiles) return;
+    const int lane = threadIdx.x & 31;
+    const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+    const uint32_t* __restrict__ mval = descs[c].mval;
+    const uint32_t* __restrict__ mvalid = descs[c].mvalid;
+    const int64_t len = descs[c].len;
+    const int64_t moff = descs[c].moff, mvoff = descs[c].mvoff;
+    const int64_t base = (tile - descs[c].tile0) * tile_elems;
+    unsigned int n = 0;
+    for (int64_t e0 = base + (int64_t)lane * 32; e0 < base + tile_elems && e0 < len; e0 += 32 * 32) {
+        uint32_t sel = load_bits<32>(mval, moff + e0) & tail_mask<32>(e0, len);
+        if (mvalid) sel &= load_bits<32>(mvalid, mvoff + e0);
+        n += __popc(sel);
+    }
+    n = __reduce_add_sync(0xffffffffu, n);
+    if (lane == 0) tile_counts[tile] = n;
+}
+
+// 2. one CTA per chunk: exclusive scan of the chunk's tile counts
+__global__ void __launch_bounds__(kThreads)
+k_filter_scan(const FilterDesc* __restrict__ descs, int tile_elems, const unsigned int* __restrict__ tile_counts,
+              long long* __restrict__ tile_offsets, long long* __restrict__ chunk_totals) {
+    __shared__ long long s_warp[kWarpsPerCta];
+    __shared__ long long s_carry;
+    const int c = blockIdx.x;
+    const int64_t t0 = descs[c].tile0;
+    const int64_t nt = (descs[c].len + tile_elems - 1) / tile_elems;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t i0 = 0; i0 < nt; i0 += kThreads) {
+        const int64_t i = i0 + threadIdx.x;
+        const long long v = i < nt ? (long long)tile_counts[t0 + i] : 0;
+        long long incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        long long wbase = 0;
+        for (int w = 0; w < warp; w++) wbase += s_warp[w];
+        const long long carry = s_carry;
+        if (i < nt) tile_offsets[t0 + i] = carry + wbase + incl - v;
+        __syncthreads();
+        if (threadIdx.x == kThreads - 1) s_carry = carry + wbase + incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) chunk_totals[c] = s_carry;
+}
+
+// 3. scatter
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long long* __restrict__ tile_offsets) {
+    constexpr int E = 16 / (int)sizeof(T);
+    constexpr int G = 32 / E;  // lanes per 32-slot word
+    constexpr int TILE = kThreads * kUnroll * E;
+    constexpr uint32_t FULLMASK = (1u << E) - 1u;
+    __shared__ unsigned int s_warp[kWarpsPerCta];
+
+    const int64_t tile = blockIdx.x;
+    const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+    const T* __restrict__ pi = (const T*)descs[c].in;
+    T* __restrict__ po = (T*)descs[c].out;
+    const uint32_t* __restrict__ vi = descs[c].vin;
+    uint32_t* __restrict__ vo = descs[c].vout;
+    const uint32_t* __restrict__ mval = descs[c].mval;
+    const uint32_t* __restrict__ mvalid = descs[c].mvalid;
+    const int64_t len = descs[c].len;
+    const int64_t off = descs[c].off, moff = descs[c].moff, mvoff = descs[c].mvoff;
+    const int64_t base = (tile - descs[c].tile0) * TILE;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool full = base + TILE <= len;
+    long long out_pos = tile_offsets[tile];  // first output slot of this tile, then of each step
+
+    Vec<T, E> x[kUnroll];
+    uint32_t sel[kUnroll], val[kUnroll];
+    if (full) {
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+        MaskRaw<E, kUnroll> rm, rmv, rv;
+        const int64_t e_first = base + (int64_t)threadIdx.x * E;
+        mask_issue<E, kUnroll>(rm, mval, moff + e_first, (int64_t)kThreads * E);
+        if (mvalid) mask_issue<E, kUnroll>(rmv, mvalid, mvoff + e_first, (int64_t)kThreads * E);
+        if (vi) mask_issue<E, kUnroll>(rv, vi, off + e_first, (int64_t)kThreads * E);
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            sel[j] = mask_get<E, kUnroll>(rm, j);
+            if (mvalid) sel[j] &= mask_get<E, kUnroll>(rmv, j);
+            val[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
+        }
+    } else {
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+            const uint32_t in_range = tail_mask<E>(e0, len);
+            sel[j] = 0; val[j] = FULLMASK;
+            if (in_range) {
+                sel[j] = load_bits<E>(mval, moff + e0) & in_range;
+                if (mvalid) sel[j] &= load_bits<E>(mvalid, mvoff + e0);
+                if (vi) val[j] = load_bits<E>(vi, off + e0);
+#pragma unroll
+                for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) x[j].e[e] = pi[e0 + e];
+            }
+        }
+    }
+
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        // exclusive scan of the per-thread counts over the 256 threads of this step (thread order = slot order)
+        const unsigned int cnt = __popc(sel[j]);
+        unsigned int incl = cnt;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        __syncthreads();  // s_warp from the previous step has been consumed
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        unsigned int wbase = 0, step_total = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; w++) { const unsigned int t = s_warp[w]; if (w < warp) wbase += t; step_total += t; }
+        const long long my_pos = out_pos + wbase + incl - cnt;
+        // values: selected slots in order
+        long long p = my_pos;
+#pragma unroll
+        for (int e = 0; e < E; e++)
+            if ((sel[j] >> e) & 1u) po[p++] = x[j].e[e];
+        // validity: compact this lane's E bits, OR the 32/E lanes of the word together, two atomics at most
+        if (vo) {
+            uint32_t cbits = 0;
+            int k = 0;
+#pragma unroll
+            for (int e = 0; e < E; e++)
+                if ((sel[j] >> e) & 1u) { cbits |= ((val[j] >> e) & 1u) << k; k++; }
+            const long long word_pos = __shfl_sync(0xffffffffu, my_pos, lane & ~(G - 1));  // leader's position
+            uint32_t wbits = cbits << (unsigned)(my_pos - word_pos);                       // < 32 selected per word
+            unsigned int wcnt = cnt;
+#pragma unroll
+            for (int o = 1; o < G; o <<= 1) { wbits |= __shfl_xor_sync(0xffffffffu, wbits, o); wcnt += __shfl_xor_sync(0xffffffffu, wcnt, o); }
+            if ((lane & (G - 1)) == 0 && wbits) {
+                const int sh = (int)(word_pos & 31);
+                atomicOr(&vo[word_pos >> 5], wbits << sh);
+                if (sh && sh + (int)wcnt > 32) atomicOr(&vo[(word_pos >> 5) + 1], wbits >> (32 - sh));
+            }
+        }
+        out_pos += step_total;
+    }
+}
+
+// ---- launchers -------------------------------------------------------------------------------------------------
+template <int OP>
+static cudaError_t cmp_one(const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s) {
+    if (scalar_rhs) k_compare<OP, true><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, scalar, wc);
+    else k_compare<OP, false><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, scalar, wc);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s) {
+    if (tiles <= 0) return cudaSuccess;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    switch (op) {
+        case CMP_GT: return cmp_one<CMP_GT>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_GE: return cmp_one<CMP_GE>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_EQ: return cmp_one<CMP_EQ>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_NE: return cmp_one<CMP_NE>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_LT: return cmp_one<CMP_LT>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_LE: return cmp_one<CMP_LE>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+int bool_tile_elems() { return kBoolTile; }
+
+cudaError_t launch_boolean(int op, const void* d, int n, int64_t tiles, uint32_t* wc, cudaStream_t s) {
+    if (tiles <= 0) return cudaSuccess;
+    if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const BoolDesc* bd = (const BoolDesc*)d;
+    switch (op) {
+        case BOOL_AND: k_boolean<BOOL_AND><<<(unsigned)tiles, kThreads, 0, s>>>(bd, n, wc); break;
+        case BOOL_OR: k_boolean<BOOL_OR><<<(unsigned)tiles, kThreads, 0, s>>>(bd, n, wc); break;
+        case BOOL_NOT: k_boolean<BOOL_NOT><<<(unsigned)tiles, kThreads, 0, s>>>(bd, n, wc); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter_count(const void* d, int n, int64_t tiles, int tile_elems, unsigned int* tile_counts, long long* tile_offsets,
+                                long long* chunk_totals, cudaStream_t s) {
+    const FilterDesc* fd = (const FilterDesc*)d;
+    if (tiles > 0) {
+        if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+        k_filter_count<<<(unsigned)((tiles + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, 0, s>>>(fd, n, tiles, tile_elems, tile_counts);
+    }
+    if (n > 0) k_filter_scan<<<(unsigned)n, kThreads, 0, s>>>(fd, tile_elems, tile_counts, tile_offsets, chunk_totals);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_filter_scatter(int dtype, const void* d, int n, int64_t tiles, const long long* tile_offsets, cudaStream_t s) {
+    if (tiles <= 0) return cudaSuccess;
+    const FilterDesc* fd = (const FilterDesc*)d;
+    switch (dtype_width(dtype)) {  // a move of opaque w-byte values: one instantiation per width
+        case 1: k_filter_scatter<uint8_t><<<(unsigned)tiles, kThreads, 0, s>>>(fd, n, tile_offsets); break;
+        case 2: k_filter_scatter<uint16_t><<<(unsigned)tiles, kThreads, 0, s>>>(fd, n, tile_offsets); break;
+        case 4: k_filter_scatter<uint32_t><<<(unsigned)tiles, kThreads, 0, s>>>(fd, n, tile_offsets); break;
+        default: k_filter_scatter<uint64_t><<<(unsigned)tiles, kThreads, 0, s>>>(fd, n, tile_offsets); break;
+    }
+    return cudaGetLastError();
+}
+
+size_t filter_desc_size() { return sizeof(FilterDesc); }
+size_t bool_desc_size() { return sizeof(BoolDesc); }
+
+// host-side fillers (the runtime does not see the struct layouts)
+void fill_filter_desc(void* base, int64_t i, const void* in, void* out, const uint32_t* vin, uint32_t* vout, const uint32_t* mval,
+                      const uint32_t* mvalid, int64_t len, int64_t tile0, int off, int moff, int mvoff) {
+    FilterDesc* d = (FilterDesc*)base + i;
+    *d = FilterDesc{in, out, vin, vout, mval, mvalid, len, tile0, off, moff, mvoff, 0};
+}
+void fill_bool_desc(void* base, int64_t i, const uint32_t* a, const uint32_t* b, uint32_t* out, const uint32_t* va, const uint32_t* vb,
+                    uint32_t* vout, int64_t len, int64_t tile0, int offa, int offb, int voffa, int voffb) {
+    BoolDesc* d = (BoolDesc*)base + i;
+    *d = BoolDesc{a, b, out, va, vb, vout, len, tile0, offa, offb, voffa, voffb};
+}
+
+}  // namespace bdf

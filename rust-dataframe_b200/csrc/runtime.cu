@@ -65,7 +65,8 @@ struct DevChunk {
     char* values;
     uint32_t* validity;  // nullptr = no bitmap
     int64_t len;
-    int32_t bit_off;
+    int32_t bit_off;      // residual bit offset of the validity bitmap
+    int32_t val_bit_off;  // boolean columns only: residual bit offset of the VALUES bitmap
 };
 
 struct bdf_col {
@@ -137,6 +138,12 @@ static constexpr int kAggSlots = 4096;
 
 // ---------------------------------------------------------------------------------------------------
 // small helpers
+
+static constexpr int kBool = 10;  // BDF_BOOL: bit-packed boolean column (N2)
+
+static inline size_t value_bytes(int dtype, int64_t len, int bit_off) {
+    return dtype == kBool ? (size_t)((len + bit_off + 7) / 8) : (size_t)len * dtype_width(dtype);
+}
 
 static int check_dtype(int t) {
     if (t < 0 || t >= BDF_NTYPES) return fail(BDF_INVALID, "invalid dtype %d", t);
@@ -231,7 +238,7 @@ static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, 
     size_t vbytes = 0, bbytes = 0;
     for (size_t i = 0; i < n; i++) {
         voff[i] = vbytes;
-        vbytes += align_up((size_t)plan[i].len * w, 256);
+        vbytes += align_up(value_bytes(dtype, plan[i].len, bit_offs ? (*bit_offs)[i] : 0) + (dtype == kBool ? 8 : 0), 256);
         boff[i] = bbytes;
         if (plan[i].has_validity) {
             const int bo = bit_offs ? (*bit_offs)[i] : 0;
@@ -263,6 +270,7 @@ static int col_alloc(bdf_ctx* c, int dtype, const std::vector<ChunkPlan>& plan, 
         ch.validity = plan[i].has_validity ? (uint32_t*)(col->arena_validity + boff[i]) : nullptr;
         ch.len = plan[i].len;
         ch.bit_off = bit_offs ? (*bit_offs)[i] : 0;
+        ch.val_bit_off = (dtype == kBool && bit_offs) ? (*bit_offs)[i] : 0;
     }
     *out = col;
     return BDF_OK;
@@ -432,8 +440,10 @@ static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool as
             const DevChunk& ch = cols[k]->chunks[i];
             const int w = dtype_width(specs[k].dtype);
             if (v.len) {
-                e = cudaMemcpyAsync(ch.values, (const char*)v.values + v.offset * w, (size_t)v.len * w, cudaMemcpyHostToDevice, c->s_h2d);
-                pending += (size_t)v.len * w;
+                const bool is_bool = specs[k].dtype == kBool;
+                const size_t vb = value_bytes(specs[k].dtype, v.len, (int)(v.offset & 7));
+                e = cudaMemcpyAsync(ch.values, (const char*)v.values + (is_bool ? (v.offset >> 3) : v.offset * w), vb, cudaMemcpyHostToDevice, c->s_h2d);
+                pending += vb;
                 if (e == cudaSuccess && v.validity)
                     e = cudaMemcpyAsync(ch.validity, v.validity + (v.offset >> 3), (size_t)((v.len + (v.offset & 7) + 7) / 8),
                                         cudaMemcpyHostToDevice, c->s_h2d);
@@ -468,7 +478,7 @@ static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out);  // identity c
 // on the d2h stream behind the group events; finish waits for them and fills in the metadata.
 static int download_enqueue(bdf_ctx* c, bdf_col* col, bdf_out* out) {
     bool misaligned = false;
-    for (auto& ch : col->chunks) misaligned = misaligned || (ch.validity && ch.bit_off != 0);
+    for (auto& ch : col->chunks) misaligned = misaligned || (ch.validity && ch.bit_off != 0) || ch.val_bit_off != 0;
     if (misaligned) {  // an uploaded slice downloaded as-is: shift its bitmap to offset 0 first
         bdf_col* tmp = nullptr;
         TRY(realign(c, col, &tmp));
@@ -490,7 +500,7 @@ static int download_enqueue(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         for (int64_t i = g.begin; i < g.end; i++) {
             const DevChunk& ch = col->chunks[i];
             if (!ch.len) continue;
-            CK(cudaMemcpyAsync(out[i].values, ch.values, (size_t)ch.len * w, cudaMemcpyDeviceToHost, c->s_d2h));
+            CK(cudaMemcpyAsync(out[i].values, ch.values, value_bytes(col->dtype, ch.len, 0), cudaMemcpyDeviceToHost, c->s_d2h));
             if (ch.validity) CK(cudaMemcpyAsync(out[i].validity, ch.validity, (size_t)bitmap_bytes(ch.len), cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
@@ -547,6 +557,7 @@ static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future
 static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out, bdf_future** fut = nullptr) {
     if (op < 0 || op >= BDF_NBINARY) return fail(BDF_INVALID, "invalid binary op %d", op);
     if (l->dtype != r->dtype) return fail(BDF_INVALID, "binary op on columns of different types (%d, %d)", l->dtype, r->dtype);
+    if (l->dtype == kBool) return fail(BDF_UNSUPPORTED, "arithmetic on a boolean column");
     const int dtype = l->dtype;
     if (op > BDF_DIV && !dtype_is_float(dtype)) return fail(BDF_UNSUPPORTED, "atan2/hypot/log need a float column (T::Native: Float)");
     const int64_t n = std::min<int64_t>((int64_t)l->chunks.size(), (int64_t)r->chunks.size());  // zip()
@@ -658,6 +669,7 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
 static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bdf_col** out) {
     const int from = in->dtype;
     int to = from;
+    if (from == kBool) return fail(BDF_UNSUPPORTED, "numeric function on a boolean column");
     if (is_cast) {
         to = op_or_to;
         TRY(check_dtype(to));
@@ -725,7 +737,11 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
     return BDF_OK;
 }
 
-static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out) { return map_dev(c, true, in->dtype, in, out); }
+static int boolean_dev(bdf_ctx* c, int op, const bdf_col* a, const bdf_col* b, bdf_col** out);
+static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out) {
+    if (in->dtype == kBool) return boolean_dev(c, 1 /* OR: x | x = x, validity AND itself */, in, in, out);
+    return map_dev(c, true, in->dtype, in, out);
+}
 
 static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out) {
     bdf_future* f = new (std::nothrow) bdf_future();
@@ -763,6 +779,7 @@ static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf
 }
 
 static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
+    if (col->dtype == kBool) return fail(BDF_UNSUPPORTED, "aggregate of a boolean column");
     const int64_t n = (int64_t)col->chunks.size();
     bdf_future* f = nullptr;
     TRY(future_new(c, col->dtype, 2, col->total_len, &f));
@@ -854,6 +871,200 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
     }
     *is_some = count != 0;
     *out = mean;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// N2: BooleanFilter comparisons, boolean kernels, filter (k_filter.cu)
+
+namespace bdf {
+cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s);
+int bool_tile_elems();
+cudaError_t launch_boolean(int op, const void* d, int n, int64_t tiles, uint32_t* wc, cudaStream_t s);
+cudaError_t launch_filter_count(const void* d, int n, int64_t tiles, int tile_elems, unsigned int* tile_counts, long long* tile_offsets,
+                                long long* chunk_totals, cudaStream_t s);
+cudaError_t launch_filter_scatter(int dtype, const void* d, int n, int64_t tiles, const long long* tile_offsets, cudaStream_t s);
+size_t filter_desc_size();
+size_t bool_desc_size();
+void fill_filter_desc(void* base, int64_t i, const void* in, void* out, const uint32_t* vin, uint32_t* vout, const uint32_t* mval,
+                      const uint32_t* mvalid, int64_t len, int64_t tile0, int off, int moff, int mvoff);
+void fill_bool_desc(void* base, int64_t i, const uint32_t* a, const uint32_t* b, uint32_t* out, const uint32_t* va, const uint32_t* vb,
+                    uint32_t* vout, int64_t len, int64_t tile0, int offa, int offb, int voffa, int voffb);
+}  // namespace bdf
+
+static cudaError_t finish_single_group(bdf_ctx* c, bdf_col* o) {
+    Group g{0, (int64_t)o->chunks.size(), nullptr};
+    cudaError_t e = ev_get(c, &g.ev);
+    if (e == cudaSuccess) e = cudaEventRecord(g.ev, c->s_compute);
+    o->groups.push_back(g);
+    return e;
+}
+
+// BooleanFilter::{Gt,..,Le}: cast both sides to Float64 (as the reference does, expression.rs:820-845), compare.
+static int compare_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, double scalar, bdf_col** out) {
+    if (op < 0 || op > 5) return fail(BDF_INVALID, "invalid comparison op %d", op);
+    if (l->dtype == kBool || (r && r->dtype == kBool)) return fail(BDF_UNSUPPORTED, "comparison of boolean columns is not part of this path");
+    bdf_col *lc = nullptr, *rc = nullptr;  // Float64 casts (owned here)
+    auto cleanup = [&]() { col_release(c, lc); col_release(c, rc); };
+    if (l->dtype != BDF_F64) { TRY(map_dev(c, true, BDF_F64, l, &lc)); l = lc; }
+    if (r && r->dtype != BDF_F64) { int st = map_dev(c, true, BDF_F64, r, &rc); if (st != BDF_OK) { cleanup(); return st; } r = rc; }
+    const int64_t n = r ? std::min<int64_t>((int64_t)l->chunks.size(), (int64_t)r->chunks.size()) : (int64_t)l->chunks.size();
+    for (int64_t i = 0; r && i < n; i++)
+        if (l->chunks[i].len != r->chunks[i].len) { cleanup(); return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length"); }
+    std::vector<ChunkPlan> plan((size_t)n);
+    for (int64_t i = 0; i < n; i++) plan[i] = {l->chunks[i].len, l->chunks[i].validity != nullptr || (r && r->chunks[i].validity != nullptr)};
+    const int tile = elems_per_tile(BDF_F64);
+    bdf_col* o = nullptr;
+    int st = col_alloc(c, kBool, plan, nullptr, tile, &o);
+    if (st != BDF_OK) { cleanup(); return st; }
+    o->counts_on_device = o->d_warp_counts != nullptr;
+    void *hp = nullptr, *dp = nullptr;
+    st = ring_alloc(c, (size_t)n * sizeof(BinDesc), &hp, &dp);
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) {
+        BinDesc* hd = (BinDesc*)hp;
+        int64_t tiles = 0, rows = 0, bytes = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const DevChunk& a = l->chunks[i];
+            const DevChunk* b = r ? &r->chunks[i] : nullptr;
+            const DevChunk& oc = o->chunks[i];
+            hd[i] = BinDesc{a.values, b ? b->values : nullptr, oc.values, a.validity, b ? b->validity : nullptr, oc.validity, a.len, tiles,
+                            a.bit_off, b ? b->bit_off : 0};
+            tiles += (a.len + tile - 1) / tile;
+            rows += a.len;
+            bytes += (b ? 16 : 8) * a.len + bitmap_bytes(a.len) * (1 + (a.validity ? 1 : 0) + (b && b->validity ? 1 : 0) + (oc.validity ? 1 : 0));
+        }
+        wait_groups(c->s_compute, l, 0, n);
+        if (r) wait_groups(c->s_compute, r, 0, n);
+        e = desc_upload(c, dp, hd, (size_t)n * sizeof(BinDesc));
+        if (e == cudaSuccess) {
+            LaunchTimer t(c, BDF_K_COMPARE, kBool, rows, bytes);
+            e = launch_compare(op, (const BinDesc*)dp, (int)n, tiles, r == nullptr, scalar, o->d_warp_counts, c->s_compute);
+        }
+        if (e == cudaSuccess) e = finish_single_group(c, o);
+    }
+    cleanup();
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "compare failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+static int boolean_dev(bdf_ctx* c, int op, const bdf_col* a, const bdf_col* b, bdf_col** out) {
+    if (op < 0 || op > 2) return fail(BDF_INVALID, "invalid boolean op %d", op);
+    if (a->dtype != kBool || (op != 2 && (!b || b->dtype != kBool))) return fail(BDF_UNSUPPORTED, "and/or/not need boolean columns");
+    if (op == 2) b = nullptr;
+    const int64_t n = b ? std::min<int64_t>((int64_t)a->chunks.size(), (int64_t)b->chunks.size()) : (int64_t)a->chunks.size();
+    for (int64_t i = 0; b && i < n; i++)
+        if (a->chunks[i].len != b->chunks[i].len) return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length");
+    std::vector<ChunkPlan> plan((size_t)n);
+    for (int64_t i = 0; i < n; i++) plan[i] = {a->chunks[i].len, a->chunks[i].validity != nullptr || (b && b->chunks[i].validity != nullptr)};
+    const int tile = bool_tile_elems();
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, kBool, plan, nullptr, tile, &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
+    void *hp = nullptr, *dp = nullptr;
+    int st = ring_alloc(c, (size_t)n * bool_desc_size(), &hp, &dp);
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) {
+        int64_t tiles = 0, rows = 0;
+        for (int64_t i = 0; i < n; i++) {
+            const DevChunk& x = a->chunks[i];
+            const DevChunk* y = b ? &b->chunks[i] : nullptr;
+            const DevChunk& oc = o->chunks[i];
+            fill_bool_desc(hp, i, (const uint32_t*)x.values, y ? (const uint32_t*)y->values : nullptr, (uint32_t*)oc.values, x.validity,
+                           y ? y->validity : nullptr, oc.validity, x.len, tiles, x.val_bit_off, y ? y->val_bit_off : 0, x.bit_off, y ? y->bit_off : 0);
+            tiles += (x.len + tile - 1) / tile;
+            rows += x.len;
+        }
+        wait_groups(c->s_compute, a, 0, n);
+        if (b) wait_groups(c->s_compute, b, 0, n);
+        e = desc_upload(c, dp, hp, (size_t)n * bool_desc_size());
+        if (e == cudaSuccess) {
+            LaunchTimer t(c, BDF_K_COMPARE, kBool, rows, rows / 8 * (b ? 3 : 2));
+            e = launch_boolean(op, dp, (int)n, tiles, o->d_warp_counts, c->s_compute);
+        }
+        if (e == cudaSuccess) e = finish_single_group(c, o);
+    }
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "boolean op failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+// ChunkedArray::filter: arrow compute::filter(chunk, mask chunk) for every chunk pair (src/table.rs:97-107).
+static int filter_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* mask, bdf_col** out) {
+    if (mask->dtype != kBool) return fail(BDF_INVALID, "the filter mask must be a boolean column");
+    if (values->dtype == kBool) return fail(BDF_UNSUPPORTED, "filtering a boolean column is not part of this path");
+    const int64_t n = std::min<int64_t>((int64_t)values->chunks.size(), (int64_t)mask->chunks.size());  // zip()
+    for (int64_t i = 0; i < n; i++)
+        if (values->chunks[i].len != mask->chunks[i].len)
+            return fail(BDF_LENGTH_MISMATCH, "Filter array must have the same length as the data");
+    const int dtype = values->dtype;
+    const int tile = elems_per_tile(dtype);
+    int64_t tiles = 0, rows = 0;
+    std::vector<int64_t> tile0((size_t)n + 1, 0);
+    for (int64_t i = 0; i < n; i++) { tile0[i] = tiles; tiles += (values->chunks[i].len + tile - 1) / tile; rows += values->chunks[i].len; }
+    void *hp = nullptr, *dp = nullptr;
+    TRY(ring_alloc(c, (size_t)n * filter_desc_size(), &hp, &dp));
+    unsigned int* d_counts = nullptr; long long *d_offsets = nullptr, *d_totals = nullptr;
+    CK(cudaMallocAsync((void**)&d_counts, std::max<size_t>(1, (size_t)tiles) * sizeof(unsigned int), c->s_compute));
+    CK(cudaMallocAsync((void**)&d_offsets, std::max<size_t>(1, (size_t)tiles) * sizeof(long long), c->s_compute));
+    CK(cudaMallocAsync((void**)&d_totals, std::max<size_t>(1, (size_t)n) * sizeof(long long), c->s_compute));
+    auto free_scratch = [&]() { cudaFreeAsync(d_counts, c->s_compute); cudaFreeAsync(d_offsets, c->s_compute); cudaFreeAsync(d_totals, c->s_compute); };
+    // pass 1: counts + scan (output pointers are not needed yet)
+    for (int64_t i = 0; i < n; i++) {
+        const DevChunk &v = values->chunks[i], &m = mask->chunks[i];
+        fill_filter_desc(hp, i, v.values, nullptr, v.validity, nullptr, (const uint32_t*)m.values, m.validity, v.len, tile0[i], v.bit_off, m.val_bit_off, m.bit_off);
+    }
+    wait_groups(c->s_compute, values, 0, n);
+    wait_groups(c->s_compute, mask, 0, n);
+    cudaError_t e = desc_upload(c, dp, hp, (size_t)n * filter_desc_size());
+    std::vector<long long> totals((size_t)std::max<int64_t>(n, 1), 0);
+    if (e == cudaSuccess) {
+        LaunchTimer t(c, BDF_K_FILTER, dtype, rows, rows / 4);
+        c->launches++;  // count + scan
+        e = launch_filter_count(dp, (int)n, tiles, tile, d_counts, d_offsets, d_totals, c->s_compute);
+    }
+    if (e == cudaSuccess && n) e = cudaMemcpyAsync(totals.data(), d_totals, (size_t)n * sizeof(long long), cudaMemcpyDeviceToHost, c->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);  // output lengths are needed to size the result
+    if (e != cudaSuccess) { cudaGetLastError(); free_scratch(); return fail(cuda_status(e), "filter (count) failed: %s", cudaGetErrorString(e)); }
+    std::vector<ChunkPlan> plan((size_t)n);
+    int64_t kept = 0;
+    for (int64_t i = 0; i < n; i++) { plan[i] = {(int64_t)totals[i], values->chunks[i].validity != nullptr}; kept += totals[i]; }
+    bdf_col* o = nullptr;
+    int st = col_alloc(c, dtype, plan, nullptr, 0, &o);
+    if (st != BDF_OK) { free_scratch(); return st; }
+    for (int64_t i = 0; i < n; i++) o->null_counts[i] = o->chunks[i].validity ? -1 : 0;  // counted on demand
+    // pass 2: scatter
+    void *hp2 = nullptr, *dp2 = nullptr;
+    st = ring_alloc(c, (size_t)n * filter_desc_size(), &hp2, &dp2);
+    if (st == BDF_OK) {
+        for (int64_t i = 0; i < n; i++) {
+            const DevChunk &v = values->chunks[i], &m = mask->chunks[i], &oc = o->chunks[i];
+            fill_filter_desc(hp2, i, v.values, oc.values, v.validity, oc.validity, (const uint32_t*)m.values, m.validity, v.len, tile0[i], v.bit_off, m.val_bit_off, m.bit_off);
+        }
+        e = desc_upload(c, dp2, hp2, (size_t)n * filter_desc_size());
+        if (e == cudaSuccess) {
+            const int w = dtype_width(dtype);
+            LaunchTimer t(c, BDF_K_FILTER, dtype, rows, rows * w + kept * w + rows / 4);
+            e = launch_filter_scatter(dtype, dp2, (int)n, tiles, d_offsets, c->s_compute);
+        }
+        if (e == cudaSuccess) e = finish_single_group(c, o);
+    }
+    free_scratch();
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "filter (scatter) failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
     return BDF_OK;
 }
 
@@ -1001,7 +1212,7 @@ int bdf_host_unregister(bdf_ctx* c, void* p) {
 
 int bdf_upload(bdf_ctx* c, int dtype, int64_t n_chunks, const bdf_view* in, int flags, bdf_col** out) {
     ENTER(c);
-    TRY(check_dtype(dtype));
+    if (dtype != kBool) TRY(check_dtype(dtype));
     if (!out || n_chunks < 0 || (n_chunks && !in)) return fail(BDF_INVALID, "bad arguments");
     std::vector<bdf_col*> cols;
     TRY(upload_many(c, {UploadSpec{dtype, n_chunks, in}}, (flags & BDF_ASYNC) != 0, cols));
@@ -1015,7 +1226,7 @@ int bdf_upload_many(bdf_ctx* c, int64_t n_cols, const int32_t* dtypes, const int
     if (n_cols < 0 || (n_cols && (!dtypes || !n_chunks || !in || !out))) return fail(BDF_INVALID, "bad arguments");
     std::vector<UploadSpec> specs;
     for (int64_t k = 0; k < n_cols; k++) {
-        TRY(check_dtype(dtypes[k]));
+        if (dtypes[k] != kBool) TRY(check_dtype(dtypes[k]));
         if (n_chunks[k] < 0 || (n_chunks[k] && !in[k])) return fail(BDF_INVALID, "bad arguments for column %lld", (long long)k);
         specs.push_back(UploadSpec{dtypes[k], n_chunks[k], in[k]});
     }
@@ -1112,6 +1323,24 @@ int bdf_future_wait(bdf_ctx* c, bdf_future* fut, bdf_agg4* out) {
     ENTER(c);
     if (!fut) return fail(BDF_INVALID, "null future");
     return future_wait(c, fut, out);
+}
+
+int bdf_compare_dev(bdf_ctx* c, int op, const bdf_col* left, const bdf_col* right, double scalar, bdf_col** out) {
+    ENTER(c);
+    if (!left || !out) return fail(BDF_INVALID, "null argument");
+    return compare_dev(c, op, left, right, scalar, out);
+}
+
+int bdf_boolean_dev(bdf_ctx* c, int op, const bdf_col* a, const bdf_col* b, bdf_col** out) {
+    ENTER(c);
+    if (!a || !out) return fail(BDF_INVALID, "null argument");
+    return boolean_dev(c, op, a, b, out);
+}
+
+int bdf_filter_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* mask, bdf_col** out) {
+    ENTER(c);
+    if (!values || !mask || !out) return fail(BDF_INVALID, "null argument");
+    return filter_dev(c, values, mask, out);
 }
 
 int bdf_download_begin(bdf_ctx* c, const bdf_col* col, bdf_out* out) {

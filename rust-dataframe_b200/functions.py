@@ -321,6 +321,40 @@ class Column:
         N.raise_for_status(N.lib().bdf_aggregate_all_dev_async(self.ctx.handle, self.handle, C.byref(f)))
         return AggFuture(self.ctx, f, self.dtype)
 
+    # -- N2: BooleanFilter comparisons, boolean kernels, filter --
+    def compare(self, op: int, other) -> "Column":
+        """BooleanFilter::{Gt,Ge,Eq,Ne,Lt,Le}: both sides cast to Float64, compared; `other` is a Column or a scalar
+        (BooleanInput::Scalar).  Returns a boolean mask column."""
+        h = C.c_void_p()
+        if isinstance(other, Column):
+            st = N.lib().bdf_compare_dev(self.ctx.handle, op, self.handle, other.handle, 0.0, C.byref(h))
+        else:
+            st = N.lib().bdf_compare_dev(self.ctx.handle, op, self.handle, None, float(other), C.byref(h))
+        N.raise_for_status(st)
+        return Column(self.ctx, h)
+
+    def gt(self, o): return self.compare(N.GT, o)
+    def ge(self, o): return self.compare(N.GE, o)
+    def eq(self, o): return self.compare(N.EQ, o)
+    def ne(self, o): return self.compare(N.NE, o)
+    def lt(self, o): return self.compare(N.LT, o)
+    def le(self, o): return self.compare(N.LE, o)
+
+    def _boolean(self, op: int, other: Optional["Column"]) -> "Column":
+        h = C.c_void_p()
+        N.raise_for_status(N.lib().bdf_boolean_dev(self.ctx.handle, op, self.handle, other.handle if other is not None else None, C.byref(h)))
+        return Column(self.ctx, h)
+
+    def logical_and(self, o): return self._boolean(N.AND, o)
+    def logical_or(self, o): return self._boolean(N.OR, o)
+    def logical_not(self): return self._boolean(N.NOT, None)
+
+    def filter(self, mask: "Column") -> "Column":
+        """ChunkedArray::filter: keep the slots where the boolean mask column is valid and true."""
+        h = C.c_void_p()
+        N.raise_for_status(N.lib().bdf_filter_dev(self.ctx.handle, self.handle, mask.handle, C.byref(h)))
+        return Column(self.ctx, h)
+
     def unary(self, op: int) -> "Column":
         h = C.c_void_p()
         N.raise_for_status(N.lib().bdf_unary_dev(self.ctx.handle, op, self.handle, C.byref(h)))
@@ -338,7 +372,7 @@ class Column:
 
     def aggregate(self, op: int):
         dtype = self.dtype
-        out = np.zeros(1, dtype=np.int64 if op == N.COUNT else NP_DTYPES[dtype])
+        out = np.zeros(1, dtype=np.int64 if (op == N.COUNT or dtype == N.BOOL) else NP_DTYPES[dtype])
         some = C.c_int32(0)
         N.raise_for_status(N.lib().bdf_aggregate_dev(self.ctx.handle, op, self.handle, out.ctypes.data, C.byref(some)))
         return out[0] if some.value else None
@@ -366,8 +400,9 @@ class Column:
         else:
             lens = [self.chunk_len(i) for i in range(n)]
             outs, bufs = N.alloc_outputs(dtype, lens, self.ctx, pinned)
-        for i in range(n):
-            outs[i].len = bufs[i][0].shape[0]
+        if dtype != N.BOOL:
+            for i in range(n):
+                outs[i].len = bufs[i][0].shape[0]
         N.raise_for_status(N.lib().bdf_download(self.ctx.handle, self.handle, outs))
         return N.collect_outputs(dtype, outs, bufs)
 

@@ -331,3 +331,56 @@ def test_generator_is_counter_based(oracle):
     assert i.values.min() >= -2 ** 40 and i.values.max() < 2 ** 40
     h = oracle.lib().orc_splitmix64(0)
     assert h == 0xE220A8397B1DCDAF  # published splitmix64 test vector (first output for seed 0)
+
+
+# ---- 4. N2 (next row): BooleanFilter comparisons, boolean kernels, filter -- cross-checked with pyarrow -----------
+
+def test_compare_bool_filter_match_pyarrow(oracle):
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    rng = np.random.default_rng(21)
+    n = 3001
+    x = rng.integers(-50, 50, n).astype(np.int32)
+    y = rng.uniform(-50, 50, n)
+    y[:5] = [np.nan, np.inf, -np.inf, 0.0, -0.0]
+    x[3:5] = 0
+    mx, my = rng.random(n) > 0.2, rng.random(n) > 0.1
+    cx, cy = Chunk(x, oracle.I32, mx), Chunk(y, oracle.F64, my)
+    pax, pay = pa.array(x, mask=~mx).cast(pa.float64()), pa.array(y, mask=~my)
+    ops = [(oracle.GT, pc.greater), (oracle.GE, pc.greater_equal), (oracle.EQ, pc.equal), (oracle.NE, pc.not_equal),
+           (oracle.LT, pc.less), (oracle.LE, pc.less_equal)]
+    masks = []
+    for op, fn in ops:
+        st, m = oracle.compare(op, cx, cy)
+        assert st == oracle.OK
+        want = fn(pax, pay)
+        assert np.array_equal(m.valid_mask(), mx & my) and m.null_count == want.null_count
+        assert np.array_equal(m.value_bits()[m.valid_mask()], want.drop_null().to_numpy(zero_copy_only=False))
+        st, ms = oracle.compare(op, cx, None, scalar=3.0)   # BooleanInput::Scalar broadcast
+        wants = fn(pax, pa.scalar(3.0))
+        assert np.array_equal(ms.value_bits()[ms.valid_mask()], wants.drop_null().to_numpy(zero_copy_only=False))
+        masks.append(m)
+    # boolean kernels: values op values, validity AND (arrow-rs compute::and / or / not)
+    a, b = masks[0], masks[3]
+    for op, npop in ((oracle.AND, np.logical_and), (oracle.OR, np.logical_or)):
+        st, r = oracle.boolean(op, a, b)
+        assert np.array_equal(r.valid_mask(), a.valid_mask() & b.valid_mask())
+        v = r.valid_mask()
+        assert np.array_equal(r.value_bits()[v], npop(a.value_bits(), b.value_bits())[v])
+    st, r = oracle.boolean(oracle.NOT, a)
+    assert np.array_equal(r.value_bits()[r.valid_mask()], ~a.value_bits()[a.valid_mask()])
+    # filter: null mask slots count as false; kept slots keep their validity
+    for values, pav in ((cx, pa.array(x, mask=~mx)), (cy, pay)):
+        st, f = oracle.filter_chunk(values, a)
+        pam = pa.array(a.value_bits(), mask=~a.valid_mask())
+        want = pc.filter(pav, pam, null_selection_behavior="drop")
+        assert f.length == len(want) and f.null_count == want.null_count
+        assert np.array_equal(f.valid_mask(), ~np.asarray(want.is_null()))
+        wv = want.to_numpy(zero_copy_only=False)
+        got = f.values[f.valid_mask()]
+        assert np.array_equal(got, wv[~np.asarray(want.is_null())].astype(got.dtype), equal_nan=True)
+    st, fb = oracle.filter_chunk(b, a)   # filtering a boolean column
+    sel = a.value_bits() & a.valid_mask()
+    assert fb.length == int(sel.sum()) and np.array_equal(fb.value_bits(), b.value_bits()[sel])
+    assert oracle.filter_chunk(cx, Chunk(np.zeros(1, np.uint8), oracle.BOOL, None, 0, 5))[0] == oracle.LENGTH_MISMATCH
