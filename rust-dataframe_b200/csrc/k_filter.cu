@@ -214,7 +214,7 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
     constexpr int G = 32 / E;  // lanes per 32-slot word
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr uint32_t FULLMASK = (1u << E) - 1u;
-    __shared__ unsigned int s_warp[kWarpsPerCta];
+    __shared__ unsigned int s_tot[kUnroll][kWarpsPerCta];
 
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
@@ -229,7 +229,7 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
     const int64_t base = (tile - descs[c].tile0) * TILE;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const bool full = base + TILE <= len;
-    long long out_pos = tile_offsets[tile];  // first output slot of this tile, then of each step
+    const long long out_pos = tile_offsets[tile];  // first output slot of this tile
 
     Vec<T, E> x[kUnroll];
     uint32_t sel[kUnroll], val[kUnroll];
@@ -263,20 +263,26 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
         }
     }
 
+    // Output position of every slot: slots are ordered (step j, thread, element).  Warp-inclusive scans of the
+    // per-thread counts of all steps first (registers only), ONE barrier to publish the per-(step, warp) totals,
+    // then every thread derives its bases from the 32 totals.
+    unsigned int cnt[kUnroll], incl[kUnroll];
 #pragma unroll
     for (int j = 0; j < kUnroll; j++) {
-        // exclusive scan of the per-thread counts over the 256 threads of this step (thread order = slot order)
-        const unsigned int cnt = __popc(sel[j]);
-        unsigned int incl = cnt;
+        cnt[j] = __popc(sel[j]);
+        incl[j] = cnt[j];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-        __syncthreads();  // s_warp from the previous step has been consumed
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl[j], o); if (lane >= o) incl[j] += u; }
+        if (lane == 31) s_tot[j][warp] = incl[j];
+    }
+    __syncthreads();
+    long long step_pos = out_pos;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
         unsigned int wbase = 0, step_total = 0;
 #pragma unroll
-        for (int w = 0; w < kWarpsPerCta; w++) { const unsigned int t = s_warp[w]; if (w < warp) wbase += t; step_total += t; }
-        const long long my_pos = out_pos + wbase + incl - cnt;
+        for (int w = 0; w < kWarpsPerCta; w++) { const unsigned int t = s_tot[j][w]; if (w < warp) wbase += t; step_total += t; }
+        const long long my_pos = step_pos + wbase + incl[j] - cnt[j];
         // values: selected slots in order
         long long p = my_pos;
 #pragma unroll
@@ -291,7 +297,7 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
                 if ((sel[j] >> e) & 1u) { cbits |= ((val[j] >> e) & 1u) << k; k++; }
             const long long word_pos = __shfl_sync(0xffffffffu, my_pos, lane & ~(G - 1));  // leader's position
             uint32_t wbits = cbits << (unsigned)(my_pos - word_pos);                       // < 32 selected per word
-            unsigned int wcnt = cnt;
+            unsigned int wcnt = cnt[j];
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) { wbits |= __shfl_xor_sync(0xffffffffu, wbits, o); wcnt += __shfl_xor_sync(0xffffffffu, wcnt, o); }
             if ((lane & (G - 1)) == 0 && wbits) {
@@ -300,7 +306,7 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
                 if (sh && sh + (int)wcnt > 32) atomicOr(&vo[(word_pos >> 5) + 1], wbits >> (32 - sh));
             }
         }
-        out_pos += step_total;
+        step_pos += step_total;
     }
 }
 
