@@ -335,7 +335,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         ms = float(t.item())
 
     # ---- e2e: host buffers in pinned memory, copies inside the timed region ----
-    e2e = None if args.skip_e2e else run_e2e(args, ctx, rdf, lens, row0, world, local, combine, dist)
+    e2e = None if args.skip_e2e else run_e2e(args, ctx, rdf, lens, a, b, world, local, combine, dist)
 
     if rank != 0:
         return
@@ -381,18 +381,16 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(args, ctx, rdf, lens, row0, world, local, combine, dist):
+def run_e2e(args, ctx, rdf, lens, dev_a, dev_b, world, local, combine, dist):
     """Same step through the public API with host buffers (pinned), H2D + D2H inside the timed region."""
-    from oracle import pyoracle as orc  # only to fill the host input buffers with the same synthetic data
     from rust_dataframe_b200 import native as N
 
     steps = max(3, min(args.steps, 8))
-    host_a, host_b = [], []
-    for i, n in enumerate(lens):
-        va = orc.generate(orc.F64, 0, -1e3, 1e3, SEED, 0, row0 + i * CHUNK, n).values
-        vb = orc.generate(orc.F64, 0, -1e3, 1e3, SEED, 1, row0 + i * CHUNK, n).values
-        host_a.append(ctx.pinned_array(rdf.F64, va))
-        host_b.append(ctx.pinned_array(rdf.F64, vb))
+    # host copies of the same synthetic columns, in pinned memory (what the Rust shim would hand over as Arrow buffers)
+    bufs_a = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    bufs_b = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    host_a = dev_a.download(into=bufs_a)
+    host_b = dev_b.download(into=bufs_b)
     out_bufs = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
 
     def step():
@@ -417,8 +415,9 @@ def run_e2e(args, ctx, rdf, lens, row0, world, local, combine, dist):
         step()
     barrier()
     ctx.timer_start()
+    last = None
     for _ in range(steps):
-        step()
+        last = step()
     ms = ctx.timer_stop()
     barrier()
     if world > 1:
@@ -430,6 +429,7 @@ def run_e2e(args, ctx, rdf, lens, row0, world, local, combine, dist):
     h2d = 2 * 8 * ROWS
     d2h = 8 * ROWS + 8
     return {"value": ROWS * world * steps / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+            "check_sum": last[0] if last else None,
             "ms_per_step": ms / steps, "steps": steps,
             "api": "Column.upload_many([a,b]) [pinned host, async] -> binary_agg_async(ADD) -> download_begin/end(c) [pinned host] + scalar",
             "pcie_GBs": (h2d + d2h) / (ms / steps * 1e-3) / 1e9}

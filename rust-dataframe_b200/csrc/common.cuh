@@ -172,28 +172,6 @@ __device__ __forceinline__ int find_chunk(const Desc* __restrict__ descs, int n_
     return lo;
 }
 
-// ---- warp / block reductions -------------------------------------------------------------------
-template <typename T, typename F>
-__device__ __forceinline__ T warp_reduce(T v, F f) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v = f(v, __shfl_xor_sync(0xffffffffu, v, o));
-    return v;
-}
-
-// Block-wide sum of a per-thread count (all threads call; result valid in thread 0).
-__device__ __forceinline__ unsigned long long block_sum_u64(unsigned long long v, unsigned long long* smem /* >= 32 */) {
-    v = warp_reduce(v, [](unsigned long long a, unsigned long long b) { return a + b; });
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) smem[warp] = v;
-    __syncthreads();
-    unsigned long long r = 0;
-    if (warp == 0) {
-        r = (lane < (int)(blockDim.x >> 5)) ? smem[lane] : 0ull;
-        r = warp_reduce(r, [](unsigned long long a, unsigned long long b) { return a + b; });
-    }
-    return r;
-}
-
 // ---- descriptors (one per chunk, device-resident array sorted by tile0) ------------------------
 struct BinDesc {
     const void* a; const void* b; void* out;
@@ -227,7 +205,8 @@ struct AggDev {
 
 // ---- launchers (defined in k_*.cu) ---------------------------------------------------------------
 int elems_per_tile(int dtype);                 // tile size in elements for arrays of dtype
-int elems_per_tile_binary(int op, int dtype);  // K1 tile size (divide/libm binaries use shorter tiles)
+int elems_per_tile_binary(int op, int dtype);
+int elems_per_tile_unary(int op, int dtype);   // K2 tile size (libm-class functions use shorter tiles)  // K1 tile size (divide/libm binaries use shorter tiles)
 int elems_per_tile_cast(int from, int to);
 // tile_partials != nullptr (add/sub/mul/div only): also write one AggDev per tile with the aggregate of the
 // OUTPUT (K5); fold them with launch_finish.  Integer min/max partials are unsigned keys (value ^ sign flip).

@@ -75,11 +75,18 @@ template <int OP> __device__ __forceinline__ int16_t un_apply(int16_t x) { retur
 template <int OP> __device__ __forceinline__ int32_t un_apply(int32_t x) { return (int32_t)(x < 0 ? 0u - (uint32_t)x : (uint32_t)x); }
 template <int OP> __device__ __forceinline__ int64_t un_apply(int64_t x) { return (int64_t)(x < 0 ? 0ull - (uint64_t)x : (uint64_t)x); }
 
-template <typename T, int OP>
+// libm-class functions are long dependent instruction sequences: keep fewer vectors per thread so that more CTAs
+// fit per SM (measured on f64 sin); the cheap ones (abs, ceil, floor, round, sqrt, degrees, radians) stream with kUnroll.
+__host__ __device__ constexpr bool unary_is_heavy(int op) {
+    return !(op == UN_ABS || op == UN_CEIL || op == UN_FLOOR || op == UN_ROUND || op == UN_SQRT || op == UN_DEGREES || op == UN_RADIANS);
+}
+template <int OP> struct UnaryUnroll { static constexpr int value = kUnroll; };  // measured f64 sin: U=2 0.36 ms, U=4 0.305 ms, U=8 0.298 ms (tan slower): keep 4
+
+template <typename T, int OP, int U>
 __global__ void __launch_bounds__(kThreads)
 k_unary(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ warp_counts) {
     constexpr int E = 16 / (int)sizeof(T);
-    constexpr int TILE = kThreads * kUnroll * E;
+    constexpr int TILE = kThreads * U * E;
     constexpr uint32_t FULLMASK = (1u << E) - 1u;
 
     const int64_t tile = blockIdx.x;
@@ -94,16 +101,16 @@ k_unary(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ w
 
     unsigned int nvalid = 0;
     if (base + TILE <= len) {
-        Vec<T, E> x[kUnroll];
+        Vec<T, E> x[U];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
-        MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
-        if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
-        uint32_t m[kUnroll];
+        for (int j = 0; j < U; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+        MaskRaw<E, U> rv;  // validity words of all steps in one batch (see common.cuh)
+        if (vi) mask_issue<E, U>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
+        uint32_t m[U];
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) m[j] = vi ? mask_get<E, kUnroll>(rv, j) : FULLMASK;
+        for (int j = 0; j < U; j++) m[j] = vi ? mask_get<E, U>(rv, j) : FULLMASK;
 #pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
+        for (int j = 0; j < U; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             Vec<T, E> r;
 #pragma unroll
@@ -119,7 +126,7 @@ k_unary(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ w
         }
     } else {
 #pragma unroll 1
-        for (int j = 0; j < kUnroll; j++) {
+        for (int j = 0; j < U; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             const uint32_t in_range = tail_mask<E>(e0, len);
             uint32_t m = in_range;
@@ -141,7 +148,7 @@ k_unary(const UnDesc* __restrict__ descs, int n_chunks, uint32_t* __restrict__ w
 
 template <typename T, int OP>
 static cudaError_t launch_one(const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
-    k_unary<T, OP><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc);
+    k_unary<T, OP, UnaryUnroll<OP>::value><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, vc);
     return cudaGetLastError();
 }
 
@@ -157,6 +164,8 @@ static cudaError_t launch_float(int op, const UnDesc* d, int n, int64_t tiles, u
         default: return cudaErrorInvalidValue;
     }
 }
+
+int elems_per_tile_unary(int op, int dtype) { return kTileBytes / dtype_width(dtype); }
 
 cudaError_t launch_unary(int op, int dtype, const UnDesc* d, int n, int64_t tiles, uint32_t* vc, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;

@@ -687,7 +687,7 @@ static int map_dev(bdf_ctx* c, bool is_cast, int op_or_to, const bdf_col* in, bd
     std::vector<ChunkPlan> plan((size_t)n);
     for (int64_t i = 0; i < n; i++) plan[i] = {in->chunks[i].len, in->chunks[i].validity != nullptr || fallible};
     bdf_col* o = nullptr;
-    const int tile = is_cast ? elems_per_tile_cast(from, to) : elems_per_tile(from);
+    const int tile = is_cast ? elems_per_tile_cast(from, to) : elems_per_tile_unary(op_or_to, from);
     TRY(col_alloc(c, to, plan, nullptr, tile, &o));
     o->counts_on_device = o->d_warp_counts != nullptr;
 
@@ -1137,7 +1137,7 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaDeviceGetDefaultMemPool(&pool, device));
     uint64_t keep = ~0ull;  // keep freed arenas cached: operators allocate their outputs per call
     CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
-    c->ring_cap = (size_t)8 << 20;
+    c->ring_cap = (size_t)32 << 20;  // ~400k chunk descriptors per operator call
     CK(cudaHostAlloc((void**)&c->ring, c->ring_cap, cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c->dring, c->ring_cap));
     CK(cudaHostAlloc((void**)&c->h_agg, 2 * kAggSlots * sizeof(AggDev), cudaHostAllocMapped));
