@@ -37,6 +37,14 @@ for case in cases:
         elif case == "add_i64_agg":
             a = G(rdf.I64, lens, 3, col_id=7, null_mod=10); b = G(rdf.I64, lens, 3, col_id=8)
             a.binary_agg(N.ADD, b)[0].free()
+        elif case == "filter_rare":
+            a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0)
+            m = a.gt(980.0)
+            a.filter(m).free()
+        elif case == "filter_half":
+            a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0)
+            m = a.gt(0.0)
+            a.filter(m).free()
         elif case == "add_sum_fused":
             a = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=0); b = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=1)
             a.binary_agg(N.ADD, b)[0].free()

@@ -214,7 +214,7 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
     constexpr int G = 32 / E;  // lanes per 32-slot word
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr uint32_t FULLMASK = (1u << E) - 1u;
-    __shared__ unsigned int s_tot[kUnroll][kWarpsPerCta];
+    __shared__ unsigned int s_tot[kUnroll * kWarpsPerCta];
 
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
@@ -264,8 +264,8 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
     }
 
     // Output position of every slot: slots are ordered (step j, thread, element).  Warp-inclusive scans of the
-    // per-thread counts of all steps first (registers only), ONE barrier to publish the per-(step, warp) totals,
-    // then every thread derives its bases from the 32 totals.
+    // per-thread counts of all steps (registers only), barrier, warp 0 turns the kUnroll x 8 per-(step, warp) totals
+    // into exclusive bases with one more warp scan, barrier; positions inside the tile are 32-bit.
     unsigned int cnt[kUnroll], incl[kUnroll];
 #pragma unroll
     for (int j = 0; j < kUnroll; j++) {
@@ -273,21 +273,27 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
         incl[j] = cnt[j];
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl[j], o); if (lane >= o) incl[j] += u; }
-        if (lane == 31) s_tot[j][warp] = incl[j];
+        if (lane == 31) s_tot[j * kWarpsPerCta + warp] = incl[j];
     }
     __syncthreads();
-    long long step_pos = out_pos;
+    static_assert(kUnroll * kWarpsPerCta == 32, "one warp scans the per-(step, warp) totals");
+    if (warp == 0) {
+        const unsigned int v = s_tot[lane];
+        unsigned int in2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, in2, o); if (lane >= o) in2 += u; }
+        s_tot[lane] = in2 - v;  // exclusive base of (step, warp) inside the tile
+    }
+    __syncthreads();
+    T* __restrict__ pt = po + out_pos;                                   // this tile's slice of the output values
+    const int64_t vbit0 = out_pos;                                      // ... and of the output validity bits
 #pragma unroll
     for (int j = 0; j < kUnroll; j++) {
-        unsigned int wbase = 0, step_total = 0;
-#pragma unroll
-        for (int w = 0; w < kWarpsPerCta; w++) { const unsigned int t = s_tot[j][w]; if (w < warp) wbase += t; step_total += t; }
-        const long long my_pos = step_pos + wbase + incl[j] - cnt[j];
-        // values: selected slots in order
-        long long p = my_pos;
+        const unsigned int my_pos = s_tot[j * kWarpsPerCta + warp] + incl[j] - cnt[j];
+        unsigned int p = my_pos;
 #pragma unroll
         for (int e = 0; e < E; e++)
-            if ((sel[j] >> e) & 1u) po[p++] = x[j].e[e];
+            if ((sel[j] >> e) & 1u) pt[p++] = x[j].e[e];
         // validity: compact this lane's E bits, OR the 32/E lanes of the word together, two atomics at most
         if (vo) {
             uint32_t cbits = 0;
@@ -295,18 +301,18 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
 #pragma unroll
             for (int e = 0; e < E; e++)
                 if ((sel[j] >> e) & 1u) { cbits |= ((val[j] >> e) & 1u) << k; k++; }
-            const long long word_pos = __shfl_sync(0xffffffffu, my_pos, lane & ~(G - 1));  // leader's position
-            uint32_t wbits = cbits << (unsigned)(my_pos - word_pos);                       // < 32 selected per word
+            const unsigned int word_pos = __shfl_sync(0xffffffffu, my_pos, lane & ~(G - 1));  // leader's position
+            uint32_t wbits = cbits << (my_pos - word_pos);                                    // < 32 selected per word
             unsigned int wcnt = cnt[j];
 #pragma unroll
             for (int o = 1; o < G; o <<= 1) { wbits |= __shfl_xor_sync(0xffffffffu, wbits, o); wcnt += __shfl_xor_sync(0xffffffffu, wcnt, o); }
             if ((lane & (G - 1)) == 0 && wbits) {
-                const int sh = (int)(word_pos & 31);
-                atomicOr(&vo[word_pos >> 5], wbits << sh);
-                if (sh && sh + (int)wcnt > 32) atomicOr(&vo[(word_pos >> 5) + 1], wbits >> (32 - sh));
+                const int64_t bit = vbit0 + word_pos;
+                const int sh = (int)(bit & 31);
+                atomicOr(&vo[bit >> 5], wbits << sh);
+                if (sh && sh + (int)wcnt > 32) atomicOr(&vo[(bit >> 5) + 1], wbits >> (32 - sh));
             }
         }
-        step_pos += step_total;
     }
 }
 

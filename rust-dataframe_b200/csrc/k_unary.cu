@@ -75,8 +75,8 @@ template <int OP> __device__ __forceinline__ int16_t un_apply(int16_t x) { retur
 template <int OP> __device__ __forceinline__ int32_t un_apply(int32_t x) { return (int32_t)(x < 0 ? 0u - (uint32_t)x : (uint32_t)x); }
 template <int OP> __device__ __forceinline__ int64_t un_apply(int64_t x) { return (int64_t)(x < 0 ? 0ull - (uint64_t)x : (uint64_t)x); }
 
-// libm-class functions are long dependent instruction sequences: keep fewer vectors per thread so that more CTAs
-// fit per SM (measured on f64 sin); the cheap ones (abs, ceil, floor, round, sqrt, degrees, radians) stream with kUnroll.
+// Vectors kept in flight per thread.  The libm-class functions are long dependent instruction sequences, so the
+// unroll trades occupancy against per-thread ILP; it was measured rather than guessed (see UnaryUnroll).
 __host__ __device__ constexpr bool unary_is_heavy(int op) {
     return !(op == UN_ABS || op == UN_CEIL || op == UN_FLOOR || op == UN_ROUND || op == UN_SQRT || op == UN_DEGREES || op == UN_RADIANS);
 }
