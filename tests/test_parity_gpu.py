@@ -655,3 +655,33 @@ def test_concurrent_host_threads_share_one_context(rdf, ctx, oracle):
         assert s == wsum[k]
         for g, w in zip(out, want[k]):
             assert_same_array(g, w, what=f"threaded add {k}")
+
+
+def test_c_abi_argument_validation(rdf, ctx):
+    """Bad arguments come back as status codes with a message -- nothing aborts, nothing is silently computed."""
+    import ctypes as C
+
+    N = rdf.native
+    L = N.lib()
+    a = rdf.PrimitiveArray.from_numpy(np.arange(100, dtype=np.int32), np.arange(100) % 3 != 0)
+    views = N.make_views([a])
+    outs, bufs = N.alloc_outputs(rdf.I32, [100], ctx)
+    assert L.bdf_binary(ctx.handle, N.ADD, 99, 1, views, 1, views, outs) == N.INVALID and b"dtype" in L.bdf_last_error()
+    assert L.bdf_binary(ctx.handle, 99, rdf.I32, 1, views, 1, views, outs) == N.INVALID
+    assert L.bdf_binary(None, N.ADD, rdf.I32, 1, views, 1, views, outs) == N.INVALID
+    outs[0].len = 50                                         # capacity does not match the result length
+    assert L.bdf_binary(ctx.handle, N.ADD, rdf.I32, 1, views, 1, views, outs) == N.INVALID and b"capacity" in L.bdf_last_error()
+    outs[0].len = 100
+    keep = outs[0].validity
+    outs[0].validity = None                                  # the result has nulls but nowhere to put the bitmap
+    assert L.bdf_binary(ctx.handle, N.ADD, rdf.I32, 1, views, 1, views, outs) == N.INVALID and b"validity" in L.bdf_last_error()
+    outs[0].validity = keep
+    assert L.bdf_binary(ctx.handle, N.ADD, rdf.I32, 1, views, 1, views, outs) == N.OK and outs[0].null_count == 34
+    h = C.c_void_p()
+    assert L.bdf_upload(ctx.handle, rdf.I32, -1, views, 0, C.byref(h)) == N.INVALID
+    assert L.bdf_cast(ctx.handle, rdf.I32, 42, 1, views, outs) == N.INVALID
+    some, out = C.c_int32(0), np.zeros(1, np.int64)
+    assert L.bdf_aggregate(ctx.handle, 9, rdf.I32, 1, views, out.ctypes.data, C.byref(some)) == N.INVALID
+    assert L.bdf_aggregate(ctx.handle, N.SUM, rdf.I32, 1, views, None, C.byref(some)) == N.INVALID
+    # the context still works after all of that
+    assert rdf.AggregateFunctions.count([a]) == 66
