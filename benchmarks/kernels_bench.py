@@ -121,6 +121,8 @@ def main():
     # ---- N2 (next row): BooleanFilter compare + ChunkedArray::filter ----
     report("compare f64 > scalar", "N2", timed(ctx, lambda: a.gt(0.0)), "compare")
     report("compare f64 > f64", "N2", timed(ctx, lambda: a.gt(b)), "compare")
+    report("compare i32 (10% nulls) > scalar, cast fused", "N2", timed(ctx, lambda: i32n.gt(0.0)), "compare")
+    report("compare i64 > f64 column, cast fused", "N2", timed(ctx, lambda: i64.gt(a)), "compare")
     m_half = a.gt(0.0)
     m_rare = a.gt(980.0)
     an = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=11, null_mod=10)

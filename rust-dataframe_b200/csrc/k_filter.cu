@@ -30,16 +30,77 @@ __device__ __forceinline__ bool cmp_apply(double a, double b) {
     else return a <= b;
 }
 
-// ---- compare: f64 (op) f64 | scalar -> boolean values + validity ---------------------------------------------
+// ---- compare: cast(left, Float64) (op) cast(right, Float64) | scalar -> boolean values + validity ------------------
+// The reference materialises both casts (arrow::compute::cast(.., Float64), expression.rs:823-824) and then compares
+// the Float64Arrays; here the cast is fused into the load (any of the 10 numeric types, 2 elements per lane and step,
+// fully coalesced), so an Int32 column costs 4 B/row instead of 4 + 8 (cast) + 8 (compare) B/row.  Values are
+// computed under nulls exactly as the two-step form would: a non-Float64 null slot compares as 0.0 (the cast's
+// payload), a Float64 input is used as is.
+// All kUnroll steps of one input in two phases, each under ONE uniform switch on the column type: raw_issue only
+// issues the loads (2 elements per lane and step, 2..16 bytes, coalesced), raw_convert turns them into doubles later,
+// so the loads of both inputs and the validity words are all in flight before anything waits.
+template <int U>
+__device__ __forceinline__ void raw_issue(int t, const void* __restrict__ p, int64_t e_first, int64_t stride, uint4 (&q)[U]) {
+    switch (dtype_width(t)) {
+        case 8:
+#pragma unroll
+            for (int j = 0; j < U; j++) q[j] = ld_stream16((const char*)p + (e_first + (int64_t)j * stride) * 8);
+            break;
+        case 4:
+#pragma unroll
+            for (int j = 0; j < U; j++) { const uint2 d = ld_stream8((const char*)p + (e_first + (int64_t)j * stride) * 4); q[j].x = d.x; q[j].y = d.y; }
+            break;
+        case 2:
+#pragma unroll
+            for (int j = 0; j < U; j++) q[j].x = ld_stream4((const char*)p + (e_first + (int64_t)j * stride) * 2);
+            break;
+        default:
+#pragma unroll
+            for (int j = 0; j < U; j++) q[j].x = ld_stream2((const char*)p + (e_first + (int64_t)j * stride));
+            break;
+    }
+}
+template <int U>
+__device__ __forceinline__ void raw_convert(int t, const uint4 (&q)[U], double (&x)[U][2]) {
+#define BDF_CONV(C0, C1) _Pragma("unroll") for (int j = 0; j < U; j++) { x[j][0] = C0; x[j][1] = C1; } break;
+    switch (t) {
+        case T_F64: BDF_CONV(__hiloint2double((int)q[j].y, (int)q[j].x), __hiloint2double((int)q[j].w, (int)q[j].z))
+        case T_I64: BDF_CONV((double)(long long)(((unsigned long long)q[j].y << 32) | q[j].x), (double)(long long)(((unsigned long long)q[j].w << 32) | q[j].z))
+        case T_U64: BDF_CONV((double)(((unsigned long long)q[j].y << 32) | q[j].x), (double)(((unsigned long long)q[j].w << 32) | q[j].z))
+        case T_F32: BDF_CONV((double)__uint_as_float(q[j].x), (double)__uint_as_float(q[j].y))
+        case T_I32: BDF_CONV((double)(int)q[j].x, (double)(int)q[j].y)
+        case T_U32: BDF_CONV((double)q[j].x, (double)q[j].y)
+        case T_I16: BDF_CONV((double)(short)(q[j].x & 0xffffu), (double)(short)(q[j].x >> 16))
+        case T_U16: BDF_CONV((double)(q[j].x & 0xffffu), (double)(q[j].x >> 16))
+        case T_I8: BDF_CONV((double)(signed char)(q[j].x & 0xffu), (double)(signed char)((q[j].x >> 8) & 0xffu))
+        default: BDF_CONV((double)(q[j].x & 0xffu), (double)((q[j].x >> 8) & 0xffu))
+    }
+#undef BDF_CONV
+}
+__device__ __forceinline__ double load1_as_f64(int t, const void* __restrict__ p, int64_t i) {
+    switch (t) {
+        case T_F64: return ((const double*)p)[i];
+        case T_I64: return (double)((const long long*)p)[i];
+        case T_U64: return (double)((const unsigned long long*)p)[i];
+        case T_F32: return (double)((const float*)p)[i];
+        case T_I32: return (double)((const int*)p)[i];
+        case T_U32: return (double)((const unsigned*)p)[i];
+        case T_I16: return (double)((const short*)p)[i];
+        case T_U16: return (double)((const unsigned short*)p)[i];
+        case T_I8: return (double)((const signed char*)p)[i];
+        default: return (double)((const unsigned char*)p)[i];
+    }
+}
+
 template <int OP, bool SCALAR>
 __global__ void __launch_bounds__(kThreads)
-k_compare(const BinDesc* __restrict__ descs, int n_chunks, double scalar, uint32_t* __restrict__ warp_counts) {
+k_compare(const BinDesc* __restrict__ descs, int n_chunks, int ta, int tb, double scalar, uint32_t* __restrict__ warp_counts) {
     constexpr int E = 2;
     constexpr int TILE = kThreads * kUnroll * E;
     const int64_t tile = blockIdx.x;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
-    const double* __restrict__ pa = (const double*)descs[c].a;
-    const double* __restrict__ pb = (const double*)descs[c].b;
+    const void* __restrict__ pa = descs[c].a;
+    const void* __restrict__ pb = descs[c].b;
     uint32_t* __restrict__ po = (uint32_t*)descs[c].out;   // boolean VALUES bitmap
     const uint32_t* __restrict__ va = descs[c].va;
     const uint32_t* __restrict__ vb = descs[c].vb;
@@ -47,30 +108,34 @@ k_compare(const BinDesc* __restrict__ descs, int n_chunks, double scalar, uint32
     const int64_t len = descs[c].len;
     const int64_t offa = descs[c].offa, offb = descs[c].offb;
     const int64_t base = (tile - descs[c].tile0) * TILE;
+    const bool zero_a = va && ta != T_F64, zero_b = !SCALAR && vb && tb != T_F64;  // cast payload of null slots
     unsigned int nvalid = 0;
     if (base + TILE <= len) {
-        Vec<double, E> a[kUnroll], b[kUnroll];
-#pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
-            const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
-            a[j].load(pa + e0);
-            if constexpr (!SCALAR) b[j].load(pb + e0);
-        }
-        MaskRaw<E, kUnroll> ra, rb;
+        double a[kUnroll][E], b[kUnroll][E];
         const int64_t e_first = base + (int64_t)threadIdx.x * E;
+        uint4 qa[kUnroll], qb[kUnroll];
+        raw_issue<kUnroll>(ta, pa, e_first, (int64_t)kThreads * E, qa);
+        if constexpr (!SCALAR) raw_issue<kUnroll>(tb, pb, e_first, (int64_t)kThreads * E, qb);
+        MaskRaw<E, kUnroll> ra, rb;
         if (va) mask_issue<E, kUnroll>(ra, va, offa + e_first, (int64_t)kThreads * E);
         if (vb) mask_issue<E, kUnroll>(rb, vb, offb + e_first, (int64_t)kThreads * E);
+        raw_convert<kUnroll>(ta, qa, a);
+        if constexpr (!SCALAR) raw_convert<kUnroll>(tb, qb, b);
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
+            const uint32_t ma = va ? mask_get<E, kUnroll>(ra, j) : 3u;
+            const uint32_t mb = vb ? mask_get<E, kUnroll>(rb, j) : 3u;
             uint32_t bits = 0;
 #pragma unroll
-            for (int e = 0; e < E; e++) bits |= (cmp_apply<OP>(a[j].e[e], SCALAR ? scalar : b[j].e[e]) ? 1u : 0u) << e;
+            for (int e = 0; e < E; e++) {
+                const double x = (zero_a && !((ma >> e) & 1u)) ? 0.0 : a[j][e];
+                const double y = SCALAR ? scalar : ((zero_b && !((mb >> e) & 1u)) ? 0.0 : b[j][e]);
+                bits |= (cmp_apply<OP>(x, y) ? 1u : 0u) << e;
+            }
             store_bits<E>(po, e0, bits, true);
             if (vo) {
-                uint32_t m = 3u;
-                if (va) m &= mask_get<E, kUnroll>(ra, j);
-                if (vb) m &= mask_get<E, kUnroll>(rb, j);
+                const uint32_t m = ma & mb;
                 store_bits<E>(vo, e0, m, true);
                 nvalid += __popc(m);
             }
@@ -80,16 +145,22 @@ k_compare(const BinDesc* __restrict__ descs, int n_chunks, double scalar, uint32
         for (int j = 0; j < kUnroll; j++) {
             const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
             const uint32_t in_range = tail_mask<E>(e0, len);
-            uint32_t bits = 0, m = in_range;
+            uint32_t ma = in_range, mb = in_range;
+            if (in_range) {
+                if (va) ma &= load_bits<E>(va, offa + e0);
+                if (vb) mb &= load_bits<E>(vb, offb + e0);
+            }
+            uint32_t bits = 0;
 #pragma unroll
             for (int e = 0; e < E; e++)
-                if ((in_range >> e) & 1u) bits |= (cmp_apply<OP>(pa[e0 + e], SCALAR ? scalar : pb[e0 + e]) ? 1u : 0u) << e;
-            if (in_range) {
-                if (va) m &= load_bits<E>(va, offa + e0);
-                if (vb) m &= load_bits<E>(vb, offb + e0);
-            }
+                if ((in_range >> e) & 1u) {
+                    const double x = (zero_a && !((ma >> e) & 1u)) ? 0.0 : load1_as_f64(ta, pa, e0 + e);
+                    const double y = SCALAR ? scalar : ((zero_b && !((mb >> e) & 1u)) ? 0.0 : load1_as_f64(tb, pb, e0 + e));
+                    bits |= (cmp_apply<OP>(x, y) ? 1u : 0u) << e;
+                }
             store_bits<E>(po, e0, bits, in_range != 0);
             if (vo) {
+                const uint32_t m = ma & mb;
                 store_bits<E>(vo, e0, m, in_range != 0);
                 nvalid += __popc(m);
             }
@@ -318,22 +389,25 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
 
 // ---- launchers -------------------------------------------------------------------------------------------------
 template <int OP>
-static cudaError_t cmp_one(const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s) {
-    if (scalar_rhs) k_compare<OP, true><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, scalar, wc);
-    else k_compare<OP, false><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, scalar, wc);
+static cudaError_t cmp_one(const BinDesc* d, int n, int64_t tiles, int ta, int tb, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s) {
+    if (scalar_rhs) k_compare<OP, true><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, ta, tb, scalar, wc);
+    else k_compare<OP, false><<<(unsigned)tiles, kThreads, 0, s>>>(d, n, ta, tb, scalar, wc);
     return cudaGetLastError();
 }
 
-cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s) {
+int compare_tile_elems() { return kThreads * kUnroll * 2; }
+
+cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, int ta, int tb, bool scalar_rhs, double scalar, uint32_t* wc,
+                           cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (op) {
-        case CMP_GT: return cmp_one<CMP_GT>(d, n, tiles, scalar_rhs, scalar, wc, s);
-        case CMP_GE: return cmp_one<CMP_GE>(d, n, tiles, scalar_rhs, scalar, wc, s);
-        case CMP_EQ: return cmp_one<CMP_EQ>(d, n, tiles, scalar_rhs, scalar, wc, s);
-        case CMP_NE: return cmp_one<CMP_NE>(d, n, tiles, scalar_rhs, scalar, wc, s);
-        case CMP_LT: return cmp_one<CMP_LT>(d, n, tiles, scalar_rhs, scalar, wc, s);
-        case CMP_LE: return cmp_one<CMP_LE>(d, n, tiles, scalar_rhs, scalar, wc, s);
+        case CMP_GT: return cmp_one<CMP_GT>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
+        case CMP_GE: return cmp_one<CMP_GE>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
+        case CMP_EQ: return cmp_one<CMP_EQ>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
+        case CMP_NE: return cmp_one<CMP_NE>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
+        case CMP_LT: return cmp_one<CMP_LT>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
+        case CMP_LE: return cmp_one<CMP_LE>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -878,7 +878,9 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
 // N2: BooleanFilter comparisons, boolean kernels, filter (k_filter.cu)
 
 namespace bdf {
-cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, bool scalar_rhs, double scalar, uint32_t* wc, cudaStream_t s);
+cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, int ta, int tb, bool scalar_rhs, double scalar, uint32_t* wc,
+                           cudaStream_t s);
+int compare_tile_elems();
 int bool_tile_elems();
 cudaError_t launch_boolean(int op, const void* d, int n, int64_t tiles, uint32_t* wc, cudaStream_t s);
 cudaError_t launch_filter_count(const void* d, int n, int64_t tiles, int tile_elems, unsigned int* tile_counts, long long* tile_offsets,
@@ -904,16 +906,13 @@ static cudaError_t finish_single_group(bdf_ctx* c, bdf_col* o) {
 static int compare_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, double scalar, bdf_col** out) {
     if (op < 0 || op > 5) return fail(BDF_INVALID, "invalid comparison op %d", op);
     if (l->dtype == kBool || (r && r->dtype == kBool)) return fail(BDF_UNSUPPORTED, "comparison of boolean columns is not part of this path");
-    bdf_col *lc = nullptr, *rc = nullptr;  // Float64 casts (owned here)
-    auto cleanup = [&]() { col_release(c, lc); col_release(c, rc); };
-    if (l->dtype != BDF_F64) { TRY(map_dev(c, true, BDF_F64, l, &lc)); l = lc; }
-    if (r && r->dtype != BDF_F64) { int st = map_dev(c, true, BDF_F64, r, &rc); if (st != BDF_OK) { cleanup(); return st; } r = rc; }
+    auto cleanup = [] {};  // (the Float64 casts of the reference are fused into the kernel's loads)
     const int64_t n = r ? std::min<int64_t>((int64_t)l->chunks.size(), (int64_t)r->chunks.size()) : (int64_t)l->chunks.size();
     for (int64_t i = 0; r && i < n; i++)
         if (l->chunks[i].len != r->chunks[i].len) { cleanup(); return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length"); }
     std::vector<ChunkPlan> plan((size_t)n);
     for (int64_t i = 0; i < n; i++) plan[i] = {l->chunks[i].len, l->chunks[i].validity != nullptr || (r && r->chunks[i].validity != nullptr)};
-    const int tile = elems_per_tile(BDF_F64);
+    const int tile = compare_tile_elems();
     bdf_col* o = nullptr;
     int st = col_alloc(c, kBool, plan, nullptr, tile, &o);
     if (st != BDF_OK) { cleanup(); return st; }
@@ -932,14 +931,15 @@ static int compare_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, d
                             a.bit_off, b ? b->bit_off : 0};
             tiles += (a.len + tile - 1) / tile;
             rows += a.len;
-            bytes += (b ? 16 : 8) * a.len + bitmap_bytes(a.len) * (1 + (a.validity ? 1 : 0) + (b && b->validity ? 1 : 0) + (oc.validity ? 1 : 0));
+            bytes += (dtype_width(l->dtype) + (b ? dtype_width(r->dtype) : 0)) * a.len +
+                     bitmap_bytes(a.len) * (1 + (a.validity ? 1 : 0) + (b && b->validity ? 1 : 0) + (oc.validity ? 1 : 0));
         }
         wait_groups(c->s_compute, l, 0, n);
         if (r) wait_groups(c->s_compute, r, 0, n);
         e = desc_upload(c, dp, hd, (size_t)n * sizeof(BinDesc));
         if (e == cudaSuccess) {
             LaunchTimer t(c, BDF_K_COMPARE, kBool, rows, bytes);
-            e = launch_compare(op, (const BinDesc*)dp, (int)n, tiles, r == nullptr, scalar, o->d_warp_counts, c->s_compute);
+            e = launch_compare(op, (const BinDesc*)dp, (int)n, tiles, l->dtype, r ? r->dtype : BDF_F64, r == nullptr, scalar, o->d_warp_counts, c->s_compute);
         }
         if (e == cudaSuccess) e = finish_single_group(c, o);
     }
