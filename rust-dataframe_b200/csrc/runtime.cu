@@ -13,7 +13,9 @@
 #include <cstring>
 #include <mutex>
 #include <new>
+#include <deque>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/b200df.h"
@@ -83,6 +85,8 @@ struct bdf_col {
     std::vector<Group> groups;
     std::vector<uint32_t> dl_counts;               // staging of d_warp_counts during a split download
     bdf_col* dl_tmp = nullptr;                     // re-aligned copy used by a split download of a sliced column
+    struct StagedCopy { void* dst; const void* src; size_t bytes; };
+    std::vector<StagedCopy> dl_staged;             // device->pageable-host copies carried out in download_finish
 };
 
 // Result of an aggregate that is still in flight (or done): a pinned slot + the event that guards it.
@@ -125,6 +129,12 @@ struct bdf_ctx {
     int fut_next = 0;                   // ring cursor over the future half of h_agg
     struct PartBuf { AggDev* p = nullptr; size_t cap = 0; cudaEvent_t done = nullptr; bool used = false; } part[3];
     int part_next = 0;                  // per-tile partials of fused aggregates: 3 persistent buffers in rotation
+    // staging for PAGEABLE host buffers: pinned slots filled/drained by a few host threads while the DMA of the
+    // previous slot is in flight (cudaMemcpyAsync straight from pageable memory is a single-threaded driver copy)
+    struct StageSlot { char* p = nullptr; cudaEvent_t ev = nullptr; bool busy = false; };
+    std::vector<StageSlot> stage;
+    int stage_next = 0;
+    int copy_threads = 4;
     cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -384,6 +394,7 @@ static int ensure_null_counts(bdf_ctx* c, bdf_col* col) {
     for (size_t i = 0; i < col->chunks.size(); i++)
         if (col->null_counts[i] < 0) unknown.push_back((int64_t)i);
     if (unknown.empty()) return BDF_OK;
+    if (col->dtype == kBool) return fail(BDF_UNSUPPORTED, "null count of an uploaded boolean column is unknown: pass null_count in the view");
     wait_groups(c->s_compute, col, 0, (int64_t)col->chunks.size());
     for (size_t k = 0; k < unknown.size(); k += kAggSlots) {
         const size_t m = std::min<size_t>(kAggSlots, unknown.size() - k);
@@ -395,6 +406,90 @@ static int ensure_null_counts(bdf_ctx* c, bdf_col* col) {
         }
     }
     return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// pageable host memory: staged copies
+
+static constexpr size_t kStageBytes = (size_t)8 << 20;
+static constexpr int kStageSlots = 6;
+static constexpr size_t kStageMin = (size_t)1 << 20;  // smaller copies go straight through the driver
+
+static bool is_pageable(const void* p) {
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, p) != cudaSuccess) { cudaGetLastError(); return true; }
+    return attr.type == cudaMemoryTypeUnregistered;
+}
+
+static int ensure_stage(bdf_ctx* c) {
+    if (!c->stage.empty()) return BDF_OK;
+    c->stage.resize(kStageSlots);
+    for (auto& sl : c->stage) {
+        CK(cudaHostAlloc((void**)&sl.p, kStageBytes, cudaHostAllocDefault));
+        CK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    }
+    const char* t = getenv("BDF_COPY_THREADS");
+    const int hw = (int)std::thread::hardware_concurrency();
+    c->copy_threads = t && atoi(t) > 0 ? atoi(t) : std::max(1, std::min(4, hw > 0 ? hw : 4));  // measured best on the B200 host (1/4/8/16 threads)
+    return BDF_OK;
+}
+
+static void parallel_memcpy(char* dst, const char* src, size_t n, int threads) {
+    const size_t part = ((n / (size_t)threads) + 4095) & ~(size_t)4095;
+    if (threads <= 1 || part == 0 || n < ((size_t)256 << 10)) { memcpy(dst, src, n); return; }
+    std::vector<std::thread> pool;
+    for (size_t off = part; off < n; off += part)
+        pool.emplace_back([=] { memcpy(dst + off, src + off, std::min(part, n - off)); });
+    memcpy(dst, src, std::min(part, n));
+    for (auto& th : pool) th.join();
+}
+
+// host -> device on the h2d stream; pageable sources are staged through pinned slots (the source has been read
+// completely when this returns).
+static cudaError_t h2d_copy(bdf_ctx* c, void* dst, const void* src, size_t bytes) {
+    if (bytes < kStageMin || !is_pageable(src)) return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, c->s_h2d);
+    if (ensure_stage(c) != BDF_OK) return cudaErrorMemoryAllocation;
+    for (size_t off = 0; off < bytes; off += kStageBytes) {
+        const size_t n = std::min(kStageBytes, bytes - off);
+        bdf_ctx::StageSlot& sl = c->stage[c->stage_next++ % kStageSlots];
+        if (sl.busy) { cudaError_t e = cudaEventSynchronize(sl.ev); if (e != cudaSuccess) return e; }
+        parallel_memcpy(sl.p, (const char*)src + off, n, c->copy_threads);
+        cudaError_t e = cudaMemcpyAsync((char*)dst + off, sl.p, n, cudaMemcpyHostToDevice, c->s_h2d);
+        if (e == cudaSuccess) e = cudaEventRecord(sl.ev, c->s_h2d);
+        if (e != cudaSuccess) return e;
+        sl.busy = true;
+    }
+    return cudaSuccess;
+}
+
+// device -> pageable host, pipelined: DMA into slot k+1.. while host threads drain slot k into the user's buffer.
+static cudaError_t d2h_staged(bdf_ctx* c, const std::vector<bdf_col::StagedCopy>& copies) {
+    if (copies.empty()) return cudaSuccess;
+    if (ensure_stage(c) != BDF_OK) return cudaErrorMemoryAllocation;
+    struct Pending { bdf_ctx::StageSlot* sl; char* dst; size_t n; };
+    std::deque<Pending> pending;
+    auto retire = [&]() -> cudaError_t {
+        Pending p = pending.front();
+        pending.pop_front();
+        cudaError_t e = cudaEventSynchronize(p.sl->ev);
+        if (e == cudaSuccess) parallel_memcpy(p.dst, p.sl->p, p.n, c->copy_threads);
+        p.sl->busy = false;
+        return e;
+    };
+    for (auto& cp : copies)
+        for (size_t off = 0; off < cp.bytes; off += kStageBytes) {
+            const size_t n = std::min(kStageBytes, cp.bytes - off);
+            if ((int)pending.size() >= kStageSlots - 1) { cudaError_t e = retire(); if (e != cudaSuccess) return e; }
+            bdf_ctx::StageSlot& sl = c->stage[c->stage_next++ % kStageSlots];
+            if (sl.busy) { cudaError_t e = cudaEventSynchronize(sl.ev); if (e != cudaSuccess) return e; }  // an earlier upload's slot
+            cudaError_t e = cudaMemcpyAsync(sl.p, (const char*)cp.src + off, n, cudaMemcpyDeviceToHost, c->s_d2h);
+            if (e == cudaSuccess) e = cudaEventRecord(sl.ev, c->s_d2h);
+            if (e != cudaSuccess) return e;
+            sl.busy = true;
+            pending.push_back(Pending{&sl, (char*)cp.dst + off, n});
+        }
+    while (!pending.empty()) { cudaError_t e = retire(); if (e != cudaSuccess) return e; }
+    return cudaSuccess;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -442,7 +537,7 @@ static int upload_many(bdf_ctx* c, const std::vector<UploadSpec>& specs, bool as
             if (v.len) {
                 const bool is_bool = specs[k].dtype == kBool;
                 const size_t vb = value_bytes(specs[k].dtype, v.len, (int)(v.offset & 7));
-                e = cudaMemcpyAsync(ch.values, (const char*)v.values + (is_bool ? (v.offset >> 3) : v.offset * w), vb, cudaMemcpyHostToDevice, c->s_h2d);
+                e = h2d_copy(c, ch.values, (const char*)v.values + (is_bool ? (v.offset >> 3) : v.offset * w), vb);
                 pending += vb;
                 if (e == cudaSuccess && v.validity)
                     e = cudaMemcpyAsync(ch.validity, v.validity + (v.offset >> 3), (size_t)((v.len + (v.offset & 7) + 7) / 8),
@@ -500,7 +595,9 @@ static int download_enqueue(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         for (int64_t i = g.begin; i < g.end; i++) {
             const DevChunk& ch = col->chunks[i];
             if (!ch.len) continue;
-            CK(cudaMemcpyAsync(out[i].values, ch.values, value_bytes(col->dtype, ch.len, 0), cudaMemcpyDeviceToHost, c->s_d2h));
+            const size_t vbytes = value_bytes(col->dtype, ch.len, 0);
+            if (vbytes >= kStageMin && is_pageable(out[i].values)) col->dl_staged.push_back({out[i].values, ch.values, vbytes});
+            else CK(cudaMemcpyAsync(out[i].values, ch.values, vbytes, cudaMemcpyDeviceToHost, c->s_d2h));
             if (ch.validity) CK(cudaMemcpyAsync(out[i].validity, ch.validity, (size_t)bitmap_bytes(ch.len), cudaMemcpyDeviceToHost, c->s_d2h));
         }
     }
@@ -520,6 +617,11 @@ static int download_finish(bdf_ctx* c, bdf_col* col, bdf_out* out) {
         return st;
     }
     const int64_t n = (int64_t)col->chunks.size();
+    if (!col->dl_staged.empty()) {  // the d2h stream already waits for the group events of this column
+        cudaError_t e = d2h_staged(c, col->dl_staged);
+        col->dl_staged.clear();
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(cuda_status(e), "staged download failed: %s", cudaGetErrorString(e)); }
+    }
     CK(cudaStreamSynchronize(c->s_d2h));
     if (col->counts_on_device && (int64_t)col->dl_counts.size() == col->tile0[n] * kWarpsPerCta) {
         fold_counts(col, col->dl_counts.data());
@@ -1092,6 +1194,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_fin) cudaStreamSynchronize(c->s_fin);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+    for (auto& sl : c->stage) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     for (auto& b : c->part) { if (b.p) cudaFree(b.p); if (b.done) cudaEventDestroy(b.done); }
     if (c->ring) cudaFreeHost(c->ring);
     if (c->dring) cudaFree(c->dring);
