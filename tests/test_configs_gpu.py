@@ -184,3 +184,56 @@ def test_config5_full_pipeline_256_batches(rdf, ctx, oracle):
         assert diff.max() <= 3 * 2.0 ** -52 + np.spacing(np.abs(want.values[m])).max(), f"cfg5 f7 chunk {i}: {diff.max()}"
     for col in (i0, i1, f0, f1, i2, f4, f7):
         col.free()
+
+
+def test_single_huge_chunk_and_many_tiny_chunks(rdf, ctx, oracle):
+    """Two extremes of the Vec<RecordBatch> shape: one 5e7-row chunk (every tile of every kernel lands in the same
+    chunk descriptor; the filter scan walks 24k tiles in one CTA) and 4000 ragged chunks of 0..3000 rows (the
+    per-CTA descriptor search, tail tiles everywhere; the reference's own benchmark is 380 x 5 rows)."""
+    # --- one huge chunk ---
+    n = 50_000_000
+    a = rdf.Column.generate(rdf.I64, [n], 3, col_id=70, null_mod=10)
+    b = rdf.Column.generate(rdf.I64, [n], 3, col_id=71)
+    c, agg = a.binary_agg(rdf.native.ADD, b)
+    oa = oracle.generate(oracle.I64, 3, 0, 0, SEED, 70, 0, n, 10)
+    ob = oracle.generate(oracle.I64, 3, 0, 0, SEED, 71, 0, n)
+    _, oc = oracle.col_binary(oracle.ADD, oracle.I64, [oa], [ob])
+    assert_same_array(c.download()[0], oc[0], what="huge chunk add")
+    for key, op in (("sum", oracle.SUM), ("min", oracle.MIN), ("max", oracle.MAX), ("count", oracle.COUNT)):
+        want = int(oracle.aggregate(op, oracle.I64, oc)[1])
+        assert int(agg[key]) == want == int(c.aggregate_all()[key]), key
+    mask = c.gt(0.0)
+    kept = c.filter(mask)
+    _, om = oracle.compare(oracle.GT, oc[0], None, scalar=0.0)
+    _, ok = oracle.filter_chunk(oc[0], om)
+    assert_same_array(kept.download()[0], ok, what="huge chunk filter")
+    for col in (a, b, c, mask, kept):
+        col.free()
+    # --- thousands of tiny ragged chunks ---
+    rng = np.random.default_rng(123)
+    lens = [int(x) for x in rng.integers(0, 3000, 4000)]
+    lens[:6] = [0, 0, 1, 2049, 0, 5]
+    x = rdf.Column.generate(rdf.F64, lens, 0, -1e3, 1e3, col_id=72, null_mod=7)
+    y = rdf.Column.generate(rdf.F64, lens, 1, col_id=73, null_mod=5)
+    q, qagg = x.binary_agg(rdf.native.DIV, y)
+    qi = q.cast(rdf.I32)
+    keep = q.filter(q.lt(0.0))
+    got_q, got_qi, got_keep = q.download(), qi.download(), keep.download()
+    row, exact, sum_abs, count = 0, np.longdouble(0), np.longdouble(0), 0
+    for i, m in enumerate(lens):
+        ox = oracle.generate(oracle.F64, 0, -1e3, 1e3, SEED, 72, row, m, 7)
+        oy = oracle.generate(oracle.F64, 1, 0, 0, SEED, 73, row, m, 5)
+        row += m
+        st, oq = oracle.col_binary(oracle.DIV, oracle.F64, [ox], [oy])
+        assert st == oracle.OK
+        assert_same_array(got_q[i], oq[0], what=f"tiny chunk {i} divide")
+        if i % 40 == 0:
+            _, oqi = oracle.col_cast(oracle.F64, oracle.I32, oq)
+            assert_same_array(got_qi[i], oqi[0], what=f"tiny chunk {i} cast")
+            _, om = oracle.compare(oracle.LT, oq[0], None, scalar=0.0)
+            _, ok = oracle.filter_chunk(oq[0], om)
+            assert_same_array(got_keep[i], ok, what=f"tiny chunk {i} filter")
+        e, sa = oracle.sum_exact(oracle.F64, oq)
+        exact += e; sum_abs += sa; count += oq[0].length - oq[0].null_count
+    assert qagg["count"] == count == q.count()
+    assert float_sum_ok(qagg["sum"], exact, sum_abs, sum(lens)) and float_sum_ok(q.sum(), exact, sum_abs, sum(lens))
