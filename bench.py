@@ -445,7 +445,21 @@ def run_cpu_baseline():
             step()
             reps += 1
         dt = time.perf_counter() - t0
-        return {"value": rows * reps / dt, "unit": "rows/s", "cores": threads, "kind": "port",
+        res_pa = None
+        try:  # secondary reference point, NOT the reference: Arrow C++ via pyarrow on the same workload
+            import pyarrow as pa
+            import pyarrow.compute as pc
+
+            a_np, b_np, _, _, _, _, _ = step._keep
+            ca = pa.chunked_array([pa.array(x.values) for x in a_np])
+            cb = pa.chunked_array([pa.array(x.values) for x in b_np])
+            pc.sum(pc.add(ca, cb))
+            t1 = time.perf_counter()
+            pc.sum(pc.add(ca, cb))
+            res_pa = {"rows_per_s": rows / (time.perf_counter() - t1), "note": "pyarrow %s pc.add + pc.sum (Arrow C++, differs from arrow-rs on f64 div-by-zero, casts, sum order)" % pa.__version__}
+        except Exception as e:  # pragma: no cover
+            res_pa = {"rows_per_s": None, "note": f"unavailable: {e}"}
+        return {"value": rows * reps / dt, "unit": "rows/s", "cores": threads, "kind": "port", "arrow_cpp_pyarrow": res_pa,
                 "sample": f"{reps} passes over the full {rows}-row workload; add on {threads} threads (one per chunk, like rayon), sum sequential on 1 thread; host has {os.cpu_count()} cpus",
                 "ms_per_step": dt / reps * 1e3}
     except Exception as e:  # pragma: no cover
