@@ -250,7 +250,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         return combine(float(s), ROWS)
 
     inflight = []
-    DEPTH = 1 if world == 1 else 2  # steps kept in flight by the host (the NCCL combine of step i runs under step i+1/i+2)
+    DEPTH = 1 if world == 1 else int(os.environ.get("BDF_BENCH_DEPTH", "3"))  # steps kept in flight by the host (the NCCL combine of step i runs under the next ones)
 
     pending_combine = []
 
