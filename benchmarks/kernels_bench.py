@@ -94,6 +94,19 @@ def main():
     report("divide f64, 10% nulls on divisor only", "cfg2-nulls", timed(ctx, lambda: a.divide(dn)), "binary")
     report("divide f64, 10% nulls on both", "cfg2-nulls", timed(ctx, lambda: bn.divide(dn)), "binary")
     report("sin f64, 10% nulls", "cfg2-nulls", timed(ctx, lambda: bn.sin()), "unary")
+    # ---- N3: the whole config-2 chain in one pass (40 B/row) vs the four materialising launches (88 B/row) ----
+    prog = [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)]
+    report("N3 fused sin(((a+b)*c)/d)", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, b, c3, d], prog)), "expr")
+    report("N3 fused ((a+b)*c)/d (arithmetic only)", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, b, c3, d], prog[:3])), "expr")
+    report("N3 fused chain, 10% nulls on b and d", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, bn, c3, dn], prog)), "expr")
+
+    def unfused():
+        e = a.add(b); f = e.multiply(c3); e.free(); g2 = f.divide(d); f.free(); h = g2.sin(); g2.free()
+        return h
+    res = timed(ctx, unfused)
+    total = sum(v[0] for v in res.values())
+    print(f"{'N3 reference: same chain, 4 launches':44s} {total:8.4f} ms  (sum of {sorted(res)})", flush=True)
+    rows_out.append({"case": "cfg2 chain unfused (4 launches)", "config": "cfg2-fused", "kernel": "binary x3 + unary", "ms": total, "rows": args.rows})
     for col in (c3, d, bn, dn):
         col.free()
     # f32 trig

@@ -164,6 +164,17 @@ int  bdf_download(bdf_ctx* ctx, const bdf_col* col, bdf_out* out /* n_chunks ent
 int  bdf_compare_dev(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, double scalar, bdf_col** out);
 int  bdf_boolean_dev(bdf_ctx* ctx, int op, const bdf_col* a, const bdf_col* b, bdf_col** out);
 int  bdf_filter_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* mask, bdf_col** out);
+/* ---- N3: consecutive Calculations fused into one pass -----------------------------------------------------------
+ * Evaluate::evaluate (src/evaluation.rs:66-96) materialises every Calculation; when the intermediates are not kept, the
+ * chain can be evaluated per element in ONE kernel: inputs are read once, only the final column is written
+ * (config 2: 40 B/row instead of 88).  The program is straight-line: slots 0..n_inputs-1 are the input columns
+ * (Float64), node k writes slot n_inputs+k and may read any earlier slot; the last node is the result.  Every node
+ * is the same operator the unfused call would run, so arithmetic chains are bit-identical; DivideByZero is raised iff
+ * a slot valid for that divide node has a zero divisor.  At most 6 inputs and 12 nodes. */
+#define BDF_EXPR_UNARY 100 /* node.op = bdf_binop for binary nodes, BDF_EXPR_UNARY + bdf_unop for unary nodes (operand a) */
+typedef struct { int32_t op, a, b; } bdf_expr_node;
+int  bdf_eval_expr_dev(bdf_ctx* ctx, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes,
+                       bdf_col** out);
 /* Split download: _begin enqueues the device->host copies (they start as soon as each chunk group is
  * ready), _end waits for them and fills len / null_count / has_validity.  Same `out` array for both. */
 int  bdf_download_begin(bdf_ctx* ctx, const bdf_col* col, bdf_out* out);
@@ -189,7 +200,7 @@ typedef struct {
     int64_t bytes;    /* algorithmic bytes of the launch (SURVEY 8(d) per-row figure x rows) */
     float   ms;       /* device time between the bracketing events */
 } bdf_launch_record;
-typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER } bdf_kernel_id;
+typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER, BDF_K_EXPR } bdf_kernel_id;
 int     bdf_profile_enable(bdf_ctx* ctx, int on);
 int     bdf_profile_read(bdf_ctx* ctx, bdf_launch_record* buf, int64_t cap, int64_t* n); /* syncs; drains */
 int64_t bdf_launch_count(bdf_ctx* ctx);           /* kernels launched since bdf_init */

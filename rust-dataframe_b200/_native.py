@@ -20,8 +20,9 @@ ADD, SUB, MUL, DIV, ATAN2, HYPOT, LOG = range(7)
 SUM, MIN, MAX, COUNT = range(4)
 OK, LENGTH_MISMATCH, DIVIDE_BY_ZERO, UNSUPPORTED, CUDA, NCCL, OOM, WOULD_PANIC, INVALID = range(9)
 ASYNC = 1
-K_BINARY, K_UNARY, K_CAST, K_REDUCE, K_GENERATE, K_AVG, K_COMPARE, K_FILTER = range(8)
-KERNEL_NAMES = ["binary", "unary", "cast", "reduce", "generate", "avg", "compare", "filter"]
+K_BINARY, K_UNARY, K_CAST, K_REDUCE, K_GENERATE, K_AVG, K_COMPARE, K_FILTER, K_EXPR = range(9)
+KERNEL_NAMES = ["binary", "unary", "cast", "reduce", "generate", "avg", "compare", "filter", "expr"]
+EXPR_UNARY = 100
 GT, GE, EQ, NE, LT, LE = range(6)
 AND, OR, NOT = range(3)
 BOOL = 10
@@ -40,6 +41,10 @@ class Out(C.Structure):
 class Agg4(C.Structure):
     _fields_ = [("sum", C.c_uint64), ("min", C.c_uint64), ("max", C.c_uint64), ("count", C.c_int64),
                 ("rows", C.c_int64), ("any_valid", C.c_int32), ("would_panic", C.c_int32)]
+
+
+class ExprNode(C.Structure):
+    _fields_ = [("op", C.c_int32), ("a", C.c_int32), ("b", C.c_int32)]
 
 
 class LaunchRecord(C.Structure):
@@ -110,6 +115,7 @@ def lib() -> C.CDLL:
         "bdf_aggregate_dev": ([vp, C.c_int, vp, vp, P(i32)], C.c_int),
         "bdf_aggregate_all_dev": ([vp, vp, P(Agg4)], C.c_int),
         "bdf_avg_dev": ([vp, vp, P(C.c_double), P(i32)], C.c_int),
+        "bdf_eval_expr_dev": ([vp, i32, P(vp), i32, P(ExprNode), P(vp)], C.c_int),
         "bdf_compare_dev": ([vp, C.c_int, vp, vp, C.c_double, P(vp)], C.c_int),
         "bdf_boolean_dev": ([vp, C.c_int, vp, vp, P(vp)], C.c_int),
         "bdf_filter_dev": ([vp, vp, vp, P(vp)], C.c_int),
@@ -145,7 +151,7 @@ EXPORTED_SYMBOLS = [
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
     "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_upload_many", "bdf_col_wait", "bdf_col_describe",
     "bdf_col_chunk_info", "bdf_binary_dev", "bdf_unary_dev", "bdf_cast_dev", "bdf_aggregate_dev",
-    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_compare_dev", "bdf_boolean_dev", "bdf_filter_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
+    "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_eval_expr_dev", "bdf_compare_dev", "bdf_boolean_dev", "bdf_filter_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
     "bdf_binary_agg_dev", "bdf_binary_agg_dev_async", "bdf_aggregate_all_dev_async", "bdf_future_wait", "bdf_col_free", "bdf_profile_enable", "bdf_profile_read",
     "bdf_launch_count", "bdf_timer_start", "bdf_timer_stop", "bdf_flush_l2", "bdf_generate",
 ]

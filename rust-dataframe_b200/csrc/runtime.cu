@@ -1171,6 +1171,107 @@ static int filter_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* mask, bd
 }
 
 // ---------------------------------------------------------------------------------------------------
+// N3: a chain of Calculations fused into one pass (k_expr.cu)
+
+namespace bdf {
+int expr_tile_elems();
+int expr_max_inputs();
+int expr_max_nodes();
+size_t expr_desc_size();
+void fill_expr_desc(void* base, int64_t i, int n_inputs, const double* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
+                    uint32_t* vout, int64_t len, int64_t tile0);
+size_t expr_prog_size();
+int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const int* b, void* prog);
+cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, cudaStream_t s);
+}  // namespace bdf
+
+static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int n_nodes, const bdf_expr_node* nodes, bdf_col** out) {
+    if (n_inputs < 1 || n_inputs > expr_max_inputs()) return fail(BDF_INVALID, "an expression takes 1..%d input columns", expr_max_inputs());
+    if (n_nodes < 1 || n_nodes > expr_max_nodes()) return fail(BDF_INVALID, "an expression has 1..%d nodes", expr_max_nodes());
+    std::vector<int> op(n_nodes), a(n_nodes), b(n_nodes);
+    bool has_div = false;
+    for (int k = 0; k < n_nodes; k++) {
+        op[k] = nodes[k].op; a[k] = nodes[k].a; b[k] = nodes[k].b;
+        const bool unary = op[k] >= BDF_EXPR_UNARY;
+        if (unary ? (op[k] - BDF_EXPR_UNARY >= BDF_NUNARY) : (op[k] < 0 || op[k] >= BDF_NBINARY)) return fail(BDF_INVALID, "node %d: invalid op %d", k, op[k]);
+        if (a[k] < 0 || a[k] >= n_inputs + k || (!unary && (b[k] < 0 || b[k] >= n_inputs + k)))
+            return fail(BDF_INVALID, "node %d refers to a slot that is not computed yet", k);
+        if (unary) b[k] = a[k];
+        has_div = has_div || op[k] == BDF_DIV;
+    }
+    alignas(8) unsigned char prog[256];
+    static_assert(sizeof(prog) >= 8 + 2 * 40, "ExprProg must fit");
+    if (expr_prog_size() > sizeof(prog)) return fail(BDF_INVALID, "internal: expression program too large");
+    switch (expr_compile(n_inputs, n_nodes, op.data(), a.data(), b.data(), prog)) {
+        case 0: break;
+        case 1: return fail(BDF_INVALID, "a node's result is never used: the materialised chain would still evaluate it, split the expression");
+        case 2: return fail(BDF_UNSUPPORTED, "the expression keeps more than two intermediates alive at once: split it");
+        default: return fail(BDF_UNSUPPORTED, "the expression is too long to fuse: split it");
+    }
+    for (int i = 0; i < n_inputs; i++)
+        if (!inputs[i]) return fail(BDF_INVALID, "null input column");
+    int64_t n = (int64_t)inputs[0]->chunks.size();
+    for (int i = 0; i < n_inputs; i++) {
+        if (inputs[i]->dtype != BDF_F64) return fail(BDF_UNSUPPORTED, "fused expressions are evaluated over Float64 columns (cast first)");
+        n = std::min<int64_t>(n, (int64_t)inputs[i]->chunks.size());
+    }
+    for (int64_t ch = 0; ch < n; ch++)
+        for (int i = 1; i < n_inputs; i++)
+            if (inputs[i]->chunks[ch].len != inputs[0]->chunks[ch].len)
+                return fail(BDF_LENGTH_MISMATCH, "Cannot perform math operation on arrays of different length");
+    std::vector<ChunkPlan> plan((size_t)n);
+    for (int64_t ch = 0; ch < n; ch++) {
+        bool hv = false;
+        for (int i = 0; i < n_inputs; i++) hv = hv || inputs[i]->chunks[ch].validity != nullptr;
+        plan[ch] = {inputs[0]->chunks[ch].len, hv};
+    }
+    const int tile = expr_tile_elems();
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, BDF_F64, plan, nullptr, tile, &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
+    void *hp = nullptr, *dp = nullptr;
+    int st = ring_alloc(c, (size_t)n * expr_desc_size(), &hp, &dp);
+    cudaError_t e = cudaSuccess;
+    if (st == BDF_OK) {
+        int64_t tiles = 0, rows = 0, bytes = 0;
+        for (int64_t ch = 0; ch < n; ch++) {
+            const double* in[8]; const uint32_t* vin[8]; int32_t off[8];
+            for (int i = 0; i < n_inputs; i++) {
+                const DevChunk& x = inputs[i]->chunks[ch];
+                in[i] = (const double*)x.values; vin[i] = x.validity; off[i] = x.bit_off;
+                if ((uintptr_t)x.values & 15) { col_release(c, o); return fail(BDF_INVALID, "internal: device chunk not 16-byte aligned"); }
+                bytes += 8 * x.len + (x.validity ? bitmap_bytes(x.len) : 0);
+            }
+            const DevChunk& oc = o->chunks[ch];
+            fill_expr_desc(hp, ch, n_inputs, in, vin, off, (double*)oc.values, oc.validity, oc.len, tiles);
+            tiles += (oc.len + tile - 1) / tile;
+            rows += oc.len;
+            bytes += 8 * oc.len + (oc.validity ? bitmap_bytes(oc.len) : 0);
+        }
+        for (int i = 0; i < n_inputs; i++) wait_groups(c->s_compute, inputs[i], 0, n);
+        e = desc_upload(c, dp, hp, (size_t)n * expr_desc_size());
+        if (e == cudaSuccess && has_div) e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
+        if (e == cudaSuccess) {
+            LaunchTimer t(c, BDF_K_EXPR, BDF_F64, rows, bytes);
+            e = launch_expr(dp, (int)n, tiles, prog, o->d_warp_counts, c->d_flag, c->s_compute);
+        }
+        if (e == cudaSuccess) e = finish_single_group(c, o);
+        if (e == cudaSuccess && has_div) {
+            e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+            if (e == cudaSuccess && *c->h_flag) { col_release(c, o); return fail(BDF_DIVIDE_BY_ZERO, "Divide by zero error"); }
+        }
+    }
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "fused expression failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // C ABI
 
 #define ENTER(ctx)                                                   \
@@ -1426,6 +1527,12 @@ int bdf_future_wait(bdf_ctx* c, bdf_future* fut, bdf_agg4* out) {
     ENTER(c);
     if (!fut) return fail(BDF_INVALID, "null future");
     return future_wait(c, fut, out);
+}
+
+int bdf_eval_expr_dev(bdf_ctx* c, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes, bdf_col** out) {
+    ENTER(c);
+    if (!inputs || !nodes || !out) return fail(BDF_INVALID, "null argument");
+    return expr_dev(c, n_inputs, inputs, n_nodes, nodes, out);
 }
 
 int bdf_compare_dev(bdf_ctx* c, int op, const bdf_col* left, const bdf_col* right, double scalar, bdf_col** out) {

@@ -435,6 +435,28 @@ class Column:
             pass
 
 
+def eval_expr(inputs: Sequence["Column"], nodes: Sequence[tuple]) -> "Column":
+    """Evaluate a chain of Calculations in ONE pass over Float64 columns.
+
+    ``nodes`` is a straight-line program: slots ``0..len(inputs)-1`` are the input columns, node ``k`` writes slot
+    ``len(inputs)+k``.  A node is ``(binop, a, b)`` with ``binop`` in native.ADD..LOG, or ``("sin", a)`` / ``(native.EXPR_UNARY + unop, a)``
+    for a unary function.  The last node is the result column; intermediates never touch HBM."""
+    ctx = inputs[0].ctx
+    arr = (N.ExprNode * len(nodes))()
+    for k, nd in enumerate(nodes):
+        if len(nd) == 2:
+            op = nd[0]
+            if isinstance(op, str):
+                op = N.EXPR_UNARY + getattr(N, op.upper())
+            arr[k].op, arr[k].a, arr[k].b = op, nd[1], nd[1]
+        else:
+            arr[k].op, arr[k].a, arr[k].b = nd
+    cols = (C.c_void_p * len(inputs))(*[c.handle for c in inputs])
+    h = C.c_void_p()
+    N.raise_for_status(N.lib().bdf_eval_expr_dev(ctx.handle, len(inputs), cols, len(nodes), arr, C.byref(h)))
+    return Column(ctx, h)
+
+
 class AggFuture:
     """An aggregate whose kernels are enqueued; result() blocks until the value is on the host."""
 
