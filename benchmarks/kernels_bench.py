@@ -98,6 +98,8 @@ def main():
     prog = [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)]
     report("N3 fused sin(((a+b)*c)/d)", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, b, c3, d], prog)), "expr")
     report("N3 fused ((a+b)*c)/d (arithmetic only)", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, b, c3, d], prog[:3])), "expr")
+    report("N3 fused chain + sum/count of h (one pass)", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr_agg([a, b, c3, d], prog)[0]), "expr")
+    report("N3 sum(sin(((a+b)*c)/d)), h never written", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr_agg([a, b, c3, d], prog, materialise=False)[1] and None), "expr")
     report("N3 fused chain, 10% nulls on b and d", "cfg2-fused", timed(ctx, lambda: rdf.eval_expr([a, bn, c3, dn], prog)), "expr")
 
     def unfused():

@@ -175,6 +175,14 @@ int  bdf_filter_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* mask, bd
 typedef struct { int32_t op, a, b; } bdf_expr_node;
 int  bdf_eval_expr_dev(bdf_ctx* ctx, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes,
                        bdf_col** out);
+/* ... with a trailing aggregate (AggregateFunctions::sum / count of the chain's last column, src/functions/aggregate.rs:22-31,
+ * 70-93) folded into the same pass, like bdf_binary_agg_dev.  `out` may be NULL: the column is then never written (the
+ * chain is only aggregated: sum(sin(((a+b)*c)/d)) reads 32 B/row and writes nothing).  Float64 result: agg->sum and
+ * agg->count are set, min/max are not (T::Native: Ord).  The _async form returns a future for bdf_future_wait. */
+int  bdf_eval_expr_agg_dev(bdf_ctx* ctx, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes,
+                           bdf_col** out, bdf_agg4* agg);
+int  bdf_eval_expr_agg_dev_async(bdf_ctx* ctx, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes,
+                                 const bdf_expr_node* nodes, bdf_col** out, bdf_future** fut);
 /* Split download: _begin enqueues the device->host copies (they start as soon as each chunk group is
  * ready), _end waits for them and fills len / null_count / has_validity.  Same `out` array for both. */
 int  bdf_download_begin(bdf_ctx* ctx, const bdf_col* col, bdf_out* out);

@@ -203,6 +203,47 @@ struct AggDev {
     unsigned long long count;     // valid slots
 };
 
+template <typename T> struct UnsignedOf { using type = T; };
+template <> struct UnsignedOf<int8_t> { using type = uint8_t; };
+template <> struct UnsignedOf<int16_t> { using type = uint16_t; };
+template <> struct UnsignedOf<int32_t> { using type = uint32_t; };
+template <> struct UnsignedOf<int64_t> { using type = uint64_t; };
+template <typename T> struct IsFloat { static constexpr bool value = false; };
+template <> struct IsFloat<float> { static constexpr bool value = true; };
+template <> struct IsFloat<double> { static constexpr bool value = true; };
+
+// ---- K5: aggregate of the OUTPUT fused into the same pass (sum/min/max/count of c while c is written) ----
+// Integers: wrapping 64-bit sum of the zero-extended values (only the low sizeof(T) bytes are meaningful),
+// min/max over order-preserving unsigned keys (value ^ sign flip).  Floats: sum in double.  One partial per
+// CTA (= per tile) in tile order; k_finish folds them in a fixed order => deterministic.
+template <typename T, bool F = IsFloat<T>::value> struct FusedAgg;
+template <typename T> struct FusedAgg<T, false> {
+    unsigned long long sum, kmin, kmax;
+    __device__ __forceinline__ void init() { sum = 0; kmin = ~0ull; kmax = 0; }
+    __device__ __forceinline__ void add(T x, bool valid, unsigned long long flip) {
+        using U = typename UnsignedOf<T>::type;
+        const unsigned long long z = (unsigned long long)(U)x;
+        if (valid) { sum += z; const unsigned long long k = z ^ flip; kmin = k < kmin ? k : kmin; kmax = k > kmax ? k : kmax; }
+    }
+    __device__ __forceinline__ void merge_shfl(int o) {
+        const unsigned long long s2 = __shfl_xor_sync(0xffffffffu, sum, o), a2 = __shfl_xor_sync(0xffffffffu, kmin, o),
+                                 b2 = __shfl_xor_sync(0xffffffffu, kmax, o);
+        sum += s2; kmin = a2 < kmin ? a2 : kmin; kmax = b2 > kmax ? b2 : kmax;
+    }
+    __device__ __forceinline__ void merge(const FusedAgg& o) { sum += o.sum; kmin = o.kmin < kmin ? o.kmin : kmin; kmax = o.kmax > kmax ? o.kmax : kmax; }
+    __device__ __forceinline__ void store(AggDev* d, unsigned long long cnt) const { d->sum_bits = sum; d->min_bits = kmin; d->max_bits = kmax; d->count = cnt; }
+};
+template <typename T> struct FusedAgg<T, true> {
+    double sum;
+    __device__ __forceinline__ void init() { sum = 0.0; }
+    __device__ __forceinline__ void add(T x, bool valid, unsigned long long) { sum = __dadd_rn(sum, valid ? (double)x : 0.0); }
+    __device__ __forceinline__ void merge_shfl(int o) { sum = __dadd_rn(sum, __shfl_xor_sync(0xffffffffu, sum, o)); }
+    __device__ __forceinline__ void merge(const FusedAgg& o) { sum = __dadd_rn(sum, o.sum); }
+    __device__ __forceinline__ void store(AggDev* d, unsigned long long cnt) const {
+        d->sum_bits = (unsigned long long)__double_as_longlong(sum); d->min_bits = ~0ull; d->max_bits = 0; d->count = cnt;
+    }
+};
+
 // ---- launchers (defined in k_*.cu) ---------------------------------------------------------------
 int elems_per_tile(int dtype);                 // tile size in elements for arrays of dtype
 int elems_per_tile_binary(int op, int dtype);

@@ -138,9 +138,12 @@ __device__ __forceinline__ void expr_dispatch(int op, Vec<double, 2> (&out)[U], 
     }
 }
 
-template <int U, int MINB>
+// AGG: also fold sum/count of the RESULT column into one partial per tile (k_finish folds them, like K5); the result
+// column itself is optional then (d.out == nullptr: aggregate only, nothing is written but the partials).
+template <int U, int MINB, bool AGG>
 __global__ void __launch_bounds__(kThreads, MINB)
-k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, uint32_t* __restrict__ warp_counts, int* __restrict__ flags) {
+k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, uint32_t* __restrict__ warp_counts, int* __restrict__ flags,
+       AggDev* __restrict__ tile_partials) {
     constexpr int E = 2;
     constexpr int TILE = kThreads * U * E;
     constexpr uint32_t ALL = (1u << (U * E)) - 1u;
@@ -250,6 +253,8 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
     }
 
     unsigned int nvalid = 0;
+    FusedAgg<double> agg;
+    if constexpr (AGG) agg.init();
 #pragma unroll
     for (int j = 0; j < U; j++) {
         const int64_t e0 = e_first + (int64_t)j * kThreads * E;
@@ -257,20 +262,38 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
         const uint32_t okbits = (am >> (j * E)) & in_range;
         Vec<double, E> r;
 #pragma unroll
-        for (int e = 0; e < E; e++) r.e[e] = ((okbits >> e) & 1u) ? acc[j].e[e] : 0.0;
-        if (full) r.store(po + e0);
-        else {
+        for (int e = 0; e < E; e++) {
+            r.e[e] = ((okbits >> e) & 1u) ? acc[j].e[e] : 0.0;
+            if constexpr (AGG) agg.add(r.e[e], (okbits >> e) & 1u, 0ull);
+        }
+        if (po) {
+            if (full) r.store(po + e0);
+            else {
 #pragma unroll
-            for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) po[e0 + e] = r.e[e];
+                for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) po[e0 + e] = r.e[e];
+            }
         }
-        if (vo) {
-            store_bits<E>(vo, e0, okbits, in_range != 0);
-            nvalid += __popc(okbits);
-        }
+        if (vo) store_bits<E>(vo, e0, okbits, in_range != 0);
+        if (vo || AGG) nvalid += __popc(okbits);
     }
-    if (vo) {
+    if (vo || AGG) {
         const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
-        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+        if ((threadIdx.x & 31) == 0 && vo) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+        if constexpr (AGG) {   // same fixed fold as K5: xor-shuffle tree per warp, warp 0 folds the 8 warp results in order
+            __shared__ unsigned int s_cnt[kWarpsPerCta];
+            __shared__ FusedAgg<double> s_agg[kWarpsPerCta];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) agg.merge_shfl(o);
+            if ((threadIdx.x & 31) == 0) { s_cnt[threadIdx.x >> 5] = wvalid; s_agg[threadIdx.x >> 5] = agg; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                FusedAgg<double> t = s_agg[0];
+                unsigned long long total = s_cnt[0];
+#pragma unroll
+                for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_agg[w]); total += s_cnt[w]; }
+                t.store(&tile_partials[blockIdx.x], total);
+            }
+        }
     }
     if (divzero) atomicOr(flags, 1);
 }
@@ -359,19 +382,25 @@ int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const i
 
 size_t expr_smem_bytes(const ExprProg& p, int unroll) { return (size_t)p.n_slots * kThreads * ((size_t)unroll * 16 + 4); }
 
-template <int U, int MINB>
-static cudaError_t launch_expr_u(const ExprDesc* dd, int n_chunks, int64_t tiles, const ExprProg& pp, uint32_t* warp_counts, int* flags, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(k_expr<U, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int U, int MINB, bool AGG>
+static cudaError_t launch_expr_u(const ExprDesc* dd, int n_chunks, int64_t tiles, const ExprProg& pp, uint32_t* warp_counts, int* flags,
+                                 AggDev* tile_partials, cudaStream_t s) {
+    static const cudaError_t attr = cudaFuncSetAttribute(k_expr<U, MINB, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)((kExprMaxInputs + kExprMaxTemps) * kThreads * (U * 16 + 4)));
     if (attr != cudaSuccess) return attr;
-    k_expr<U, MINB><<<(unsigned)tiles, kThreads, expr_smem_bytes(pp, U), s>>>(dd, n_chunks, pp, warp_counts, flags);
+    k_expr<U, MINB, AGG><<<(unsigned)tiles, kThreads, expr_smem_bytes(pp, U), s>>>(dd, n_chunks, pp, warp_counts, flags, tile_partials);
     return cudaGetLastError();
 }
 
-cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, cudaStream_t s) {
+// tile_partials != nullptr: also one AggDev per tile with sum/count of the result (fold with launch_finish(is_float = true)).
+cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags,
+                        AggDev* tile_partials, cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
-    return launch_expr_u<kExprUnroll, kExprMinCtas>((const ExprDesc*)descs, n_chunks, tiles, *(const ExprProg*)prog, warp_counts, flags, s);
+    const ExprDesc* dd = (const ExprDesc*)descs;
+    const ExprProg& pp = *(const ExprProg*)prog;
+    if (tile_partials) return launch_expr_u<kExprUnroll, kExprMinCtas, true>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
+    return launch_expr_u<kExprUnroll, kExprMinCtas, false>(dd, n_chunks, tiles, pp, warp_counts, flags, nullptr, s);
 }
 
 }  // namespace bdf

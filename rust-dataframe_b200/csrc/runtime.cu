@@ -656,6 +656,25 @@ static bool cast_is_fallible(int from, int to) {
 
 static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out);
 
+// One of three rotating per-tile partial buffers (K5 and fused expressions): grown on demand, reused once the
+// k_finish that last read it has run.
+static cudaError_t part_acquire(bdf_ctx* c, int64_t total_tiles, bdf_ctx::PartBuf** out) {
+    bdf_ctx::PartBuf* pb = &c->part[c->part_next++ % 3];
+    cudaError_t e = cudaSuccess;
+    const size_t need = std::max<size_t>(1, (size_t)total_tiles);
+    if (pb->cap < need) {  // grow (rare): nothing may still be using the old buffer
+        cudaStreamSynchronize(c->s_fin); cudaStreamSynchronize(c->s_compute);
+        if (pb->p) cudaFree(pb->p);
+        pb->p = nullptr; pb->cap = 0;
+        e = cudaMalloc((void**)&pb->p, need * sizeof(AggDev));
+        if (e == cudaSuccess) pb->cap = need;
+    }
+    if (e == cudaSuccess && !pb->done) e = cudaEventCreateWithFlags(&pb->done, cudaEventDisableTiming);
+    if (e == cudaSuccess && pb->used) e = cudaStreamWaitEvent(c->s_compute, pb->done, 0);  // its previous k_finish has read it
+    *out = pb;
+    return e;
+}
+
 static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bdf_col** out, bdf_future** fut = nullptr) {
     if (op < 0 || op >= BDF_NBINARY) return fail(BDF_INVALID, "invalid binary op %d", op);
     if (l->dtype != r->dtype) return fail(BDF_INVALID, "binary op on columns of different types (%d, %d)", l->dtype, r->dtype);
@@ -689,17 +708,7 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
         for (int64_t i = 0; i < n; i++) total_tiles += (l->chunks[i].len + tile - 1) / tile;
         st = future_new(c, dtype, 1, o->total_len, &f);
         if (st == BDF_OK) {
-            pb = &c->part[c->part_next++ % 3];
-            const size_t need = std::max<size_t>(1, (size_t)total_tiles);
-            if (pb->cap < need) {  // grow (rare): nothing may still be using the old buffer
-                cudaStreamSynchronize(c->s_fin); cudaStreamSynchronize(c->s_compute);
-                if (pb->p) cudaFree(pb->p);
-                pb->p = nullptr; pb->cap = 0;
-                e = cudaMalloc((void**)&pb->p, need * sizeof(AggDev));
-                if (e == cudaSuccess) pb->cap = need;
-            }
-            if (e == cudaSuccess && !pb->done) e = cudaEventCreateWithFlags(&pb->done, cudaEventDisableTiming);
-            if (e == cudaSuccess && pb->used) e = cudaStreamWaitEvent(c->s_compute, pb->done, 0);  // its previous k_finish has read it
+            e = part_acquire(c, total_tiles, &pb);
             partials = pb->p;
         }
     }
@@ -1182,10 +1191,13 @@ void fill_expr_desc(void* base, int64_t i, int n_inputs, const double* const* in
                     uint32_t* vout, int64_t len, int64_t tile0);
 size_t expr_prog_size();
 int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const int* b, void* prog);
-cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, cudaStream_t s);
+cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, AggDev* tile_partials,
+                        cudaStream_t s);
 }  // namespace bdf
 
-static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int n_nodes, const bdf_expr_node* nodes, bdf_col** out) {
+// out == nullptr (only with fut): aggregate only, the result column is never written.
+static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int n_nodes, const bdf_expr_node* nodes, bdf_col** out,
+                    bdf_future** fut = nullptr) {
     if (n_inputs < 1 || n_inputs > expr_max_inputs()) return fail(BDF_INVALID, "an expression takes 1..%d input columns", expr_max_inputs());
     if (n_nodes < 1 || n_nodes > expr_max_nodes()) return fail(BDF_INVALID, "an expression has 1..%d nodes", expr_max_nodes());
     std::vector<int> op(n_nodes), a(n_nodes), b(n_nodes);
@@ -1227,47 +1239,77 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
     }
     const int tile = expr_tile_elems();
     bdf_col* o = nullptr;
-    TRY(col_alloc(c, BDF_F64, plan, nullptr, tile, &o));
-    o->counts_on_device = o->d_warp_counts != nullptr;
+    if (out) {
+        TRY(col_alloc(c, BDF_F64, plan, nullptr, tile, &o));
+        o->counts_on_device = o->d_warp_counts != nullptr;
+    }
+    int64_t total_tiles = 0, total_rows = 0;
+    for (int64_t ch = 0; ch < n; ch++) { total_tiles += (plan[ch].len + tile - 1) / tile; total_rows += plan[ch].len; }
     void *hp = nullptr, *dp = nullptr;
     int st = ring_alloc(c, (size_t)n * expr_desc_size(), &hp, &dp);
     cudaError_t e = cudaSuccess;
-    if (st == BDF_OK) {
-        int64_t tiles = 0, rows = 0, bytes = 0;
+    bdf_future* f = nullptr;
+    bdf_ctx::PartBuf* pb = nullptr;
+    if (fut && st == BDF_OK) {
+        st = future_new(c, BDF_F64, 1, total_rows, &f);
+        if (st == BDF_OK) e = part_acquire(c, total_tiles, &pb);
+    }
+    cudaEvent_t ev_done = nullptr;   // the launch's completion on the compute stream, for the finish stream
+    if (st == BDF_OK && e == cudaSuccess) {
+        int64_t tiles = 0, bytes = 0;
         for (int64_t ch = 0; ch < n; ch++) {
             const double* in[8]; const uint32_t* vin[8]; int32_t off[8];
+            const int64_t len = plan[ch].len;
             for (int i = 0; i < n_inputs; i++) {
                 const DevChunk& x = inputs[i]->chunks[ch];
                 in[i] = (const double*)x.values; vin[i] = x.validity; off[i] = x.bit_off;
-                if ((uintptr_t)x.values & 15) { col_release(c, o); return fail(BDF_INVALID, "internal: device chunk not 16-byte aligned"); }
+                if ((uintptr_t)x.values & 15) e = cudaErrorMisalignedAddress;
                 bytes += 8 * x.len + (x.validity ? bitmap_bytes(x.len) : 0);
             }
-            const DevChunk& oc = o->chunks[ch];
-            fill_expr_desc(hp, ch, n_inputs, in, vin, off, (double*)oc.values, oc.validity, oc.len, tiles);
-            tiles += (oc.len + tile - 1) / tile;
-            rows += oc.len;
-            bytes += 8 * oc.len + (oc.validity ? bitmap_bytes(oc.len) : 0);
+            double* po = o ? (double*)o->chunks[ch].values : nullptr;
+            uint32_t* vo = o ? o->chunks[ch].validity : nullptr;
+            fill_expr_desc(hp, ch, n_inputs, in, vin, off, po, vo, len, tiles);
+            tiles += (len + tile - 1) / tile;
+            if (o) bytes += 8 * len + (vo ? bitmap_bytes(len) : 0);
         }
         for (int i = 0; i < n_inputs; i++) wait_groups(c->s_compute, inputs[i], 0, n);
-        e = desc_upload(c, dp, hp, (size_t)n * expr_desc_size());
+        if (e == cudaSuccess) e = desc_upload(c, dp, hp, (size_t)n * expr_desc_size());
         if (e == cudaSuccess && has_div) e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
         if (e == cudaSuccess) {
-            LaunchTimer t(c, BDF_K_EXPR, BDF_F64, rows, bytes);
-            e = launch_expr(dp, (int)n, tiles, prog, o->d_warp_counts, c->d_flag, c->s_compute);
+            LaunchTimer t(c, BDF_K_EXPR, BDF_F64, total_rows, bytes);
+            e = launch_expr(dp, (int)n, total_tiles, prog, o ? o->d_warp_counts : nullptr, c->d_flag, pb ? pb->p : nullptr, c->s_compute);
         }
-        if (e == cudaSuccess) e = finish_single_group(c, o);
+        if (e == cudaSuccess && o) e = finish_single_group(c, o);
+        if (e == cudaSuccess && f) {
+            // fold the per-tile partials on the finish stream, like K5
+            c->launches++;
+            e = ev_get(c, &ev_done);
+            if (e == cudaSuccess) e = cudaEventRecord(ev_done, c->s_compute);
+            if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_fin, ev_done, 0);
+            if (e == cudaSuccess) e = launch_finish(true, pb->p, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->h_agg_dev + f->slot, c->s_fin);
+            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
+            if (e == cudaSuccess) e = cudaEventRecord(pb->done, c->s_fin);
+            pb->used = true;
+            if (ev_done) ev_put(c, ev_done);
+        }
         if (e == cudaSuccess && has_div) {
             e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
-            if (e == cudaSuccess && *c->h_flag) { col_release(c, o); return fail(BDF_DIVIDE_BY_ZERO, "Divide by zero error"); }
+            if (e == cudaSuccess && *c->h_flag) {
+                if (o) col_release(c, o);
+                if (f) { ev_put(c, f->ev); delete f; }
+                return fail(BDF_DIVIDE_BY_ZERO, "Divide by zero error");
+            }
         }
     }
     if (st != BDF_OK || e != cudaSuccess) {
         cudaGetLastError();
-        col_release(c, o);
+        if (o) col_release(c, o);
+        if (f) { ev_put(c, f->ev); delete f; }
         return st != BDF_OK ? st : fail(cuda_status(e), "fused expression failed: %s", cudaGetErrorString(e));
     }
-    *out = o;
+    if (out) *out = o;
+    if (fut) *fut = f;
     return BDF_OK;
 }
 
@@ -1514,6 +1556,22 @@ int bdf_binary_agg_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, b
     if (!l || !r || !out || !agg) return fail(BDF_INVALID, "null argument");
     bdf_future* f = nullptr;
     TRY(binary_dev(c, op, l, r, out, &f));
+    return future_wait(c, f, agg);
+}
+
+int bdf_eval_expr_agg_dev_async(bdf_ctx* c, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes,
+                                bdf_col** out, bdf_future** fut) {
+    ENTER(c);
+    if (!inputs || !nodes || !fut) return fail(BDF_INVALID, "null argument");
+    return expr_dev(c, n_inputs, inputs, n_nodes, nodes, out, fut);
+}
+
+int bdf_eval_expr_agg_dev(bdf_ctx* c, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes, bdf_col** out,
+                          bdf_agg4* agg) {
+    ENTER(c);
+    if (!inputs || !nodes || !agg) return fail(BDF_INVALID, "null argument");
+    bdf_future* f = nullptr;
+    TRY(expr_dev(c, n_inputs, inputs, n_nodes, nodes, out, &f));
     return future_wait(c, f, agg);
 }
 

@@ -18,7 +18,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _native as N
-from .arrays import NP_DTYPES, PrimitiveArray, is_float, width_of
+from .arrays import F64, NP_DTYPES, PrimitiveArray, is_float, width_of
 
 Chunks = Sequence[PrimitiveArray]
 
@@ -435,13 +435,7 @@ class Column:
             pass
 
 
-def eval_expr(inputs: Sequence["Column"], nodes: Sequence[tuple]) -> "Column":
-    """Evaluate a chain of Calculations in ONE pass over Float64 columns (SURVEY 8(f) N3).
-
-    ``nodes`` is a straight-line program: slots ``0..len(inputs)-1`` are the input columns, node ``k`` writes slot
-    ``len(inputs)+k``.  A node is ``(binop, a, b)`` with ``binop`` in native.ADD..LOG, or ``("sin", a)`` / ``(native.EXPR_UNARY + unop, a)``
-    for a unary function.  The last node is the result column; intermediates never touch HBM."""
-    ctx = inputs[0].ctx
+def _expr_nodes(nodes: Sequence[tuple]):
     arr = (N.ExprNode * len(nodes))()
     for k, nd in enumerate(nodes):
         if len(nd) == 2:
@@ -451,10 +445,38 @@ def eval_expr(inputs: Sequence["Column"], nodes: Sequence[tuple]) -> "Column":
             arr[k].op, arr[k].a, arr[k].b = op, nd[1], nd[1]
         else:
             arr[k].op, arr[k].a, arr[k].b = nd
+    return arr
+
+
+def eval_expr(inputs: Sequence["Column"], nodes: Sequence[tuple]) -> "Column":
+    """Evaluate a chain of Calculations in ONE pass over Float64 columns (SURVEY 8(f) N3).
+
+    ``nodes`` is a straight-line program: slots ``0..len(inputs)-1`` are the input columns, node ``k`` writes slot
+    ``len(inputs)+k``.  A node is ``(binop, a, b)`` with ``binop`` in native.ADD..LOG, or ``("sin", a)`` / ``(native.EXPR_UNARY + unop, a)``
+    for a unary function.  The last node is the result column; intermediates never touch HBM."""
+    ctx = inputs[0].ctx
     cols = (C.c_void_p * len(inputs))(*[c.handle for c in inputs])
     h = C.c_void_p()
-    N.raise_for_status(N.lib().bdf_eval_expr_dev(ctx.handle, len(inputs), cols, len(nodes), arr, C.byref(h)))
+    N.raise_for_status(N.lib().bdf_eval_expr_dev(ctx.handle, len(inputs), cols, len(nodes), _expr_nodes(nodes), C.byref(h)))
     return Column(ctx, h)
+
+
+def eval_expr_agg(inputs: Sequence["Column"], nodes: Sequence[tuple], materialise: bool = True, asynchronous: bool = False):
+    """eval_expr with sum/count of the result folded into the same pass.  Returns ``(Column or None, aggregate)`` where the
+    aggregate is a dict (or an AggFuture when ``asynchronous``); ``materialise=False`` never writes the result column."""
+    ctx = inputs[0].ctx
+    cols = (C.c_void_p * len(inputs))(*[c.handle for c in inputs])
+    h = C.c_void_p()
+    hp = C.byref(h) if materialise else None
+    if asynchronous:
+        f = C.c_void_p()
+        N.raise_for_status(N.lib().bdf_eval_expr_agg_dev_async(ctx.handle, len(inputs), cols, len(nodes), _expr_nodes(nodes), hp, C.byref(f)))
+        agg = AggFuture(ctx, f, F64)
+    else:
+        a = N.Agg4()
+        N.raise_for_status(N.lib().bdf_eval_expr_agg_dev(ctx.handle, len(inputs), cols, len(nodes), _expr_nodes(nodes), hp, C.byref(a)))
+        agg = _agg4_to_dict(F64, a)
+    return (Column(ctx, h) if materialise else None), agg
 
 
 class AggFuture:

@@ -163,6 +163,42 @@ def test_argument_validation(rdf, ctx):
     assert np.array_equal(out.value_slice(), (2 * np.arange(10.0)) ** 2)
 
 
+def test_trailing_aggregate_matches_two_pass(rdf, ctx, oracle):
+    """sum/count of the chain's last column folded into the same pass: equal to aggregating the materialised column
+    (same per-tile fold order is not required -- the tolerance is the float-sum bound of the aggregate tests), the
+    column bit-identical to eval_expr's, deterministic run to run, and the column is optional."""
+    rng = np.random.default_rng(21)
+    N = rdf.native
+    lens = [0, 5, 2047, 2048, 2049, 300_001]
+    host = [make_col(rdf, rng, lens, nf, sliced=True, lo=lo) for nf, lo in ((0, -100.0), (0.2, -100.0), (0.1, 1.0))]
+    cols = [rdf.Column.upload(h) for h in host]
+    prog = [(N.ADD, 0, 1), (N.DIV, 3, 2), ("cos", 4)]
+    plain = rdf.eval_expr(cols, prog)
+    col, agg = rdf.eval_expr_agg(cols, prog)
+    none, agg2 = rdf.eval_expr_agg(cols, prog, materialise=False)
+    _, fut = rdf.eval_expr_agg(cols, prog, materialise=False, asynchronous=True)
+    assert none is None
+    want_chunks = plain.download()
+    for g, w in zip(col.download(), want_chunks):
+        assert np.array_equal(g.valid_mask(), w.valid_mask())
+        assert np.array_equal(g.value_slice().view(np.uint64), w.value_slice().view(np.uint64))
+    valid = np.concatenate([w.value_slice()[w.valid_mask()] for w in want_chunks])
+    exact = np.sum(valid.astype(np.longdouble))
+    bound = 16 * np.log2(valid.size) * 2.0 ** -53 * np.sum(np.abs(valid).astype(np.longdouble))
+    assert agg["count"] == valid.size == plain.count() and agg["rows"] == sum(lens)
+    assert abs(np.longdouble(agg["sum"]) - exact) <= bound
+    assert agg["min"] is None and agg["max"] is None
+    assert agg2 == agg and fut.result() == agg                     # same tiles, same fold: bit-identical sums
+    assert abs(agg["sum"] - plain.sum()) <= 2 * float(bound)
+    # DivideByZero wins over the aggregate; an all-null result has count 0 and sum 0
+    z = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.zeros(n)) for n in lens])
+    with pytest.raises(rdf.DivideByZero):
+        rdf.eval_expr_agg([cols[0], z], [(N.DIV, 0, 1)], materialise=False)
+    nulls = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.ones(n), np.zeros(n, bool)) for n in lens])
+    _, a0 = rdf.eval_expr_agg([cols[0], nulls], [(N.MUL, 0, 1)], materialise=False)
+    assert a0["count"] == 0 and a0["sum"] == 0.0
+
+
 def test_config2_chain_fused_1e8(rdf, ctx, oracle):
     """BASELINE config 2 at full size in ONE pass: h = sin(((a+b)*c)/d), 10% nulls on b and d."""
     CH, NCH = 4_000_000, 25
@@ -172,7 +208,9 @@ def test_config2_chain_fused_1e8(rdf, ctx, oracle):
     b = C.generate(rdf.F64, lens, 0, -1e3, 1e3, col_id=21, null_mod=10)
     c = C.generate(rdf.F64, lens, 0, -1e3, 1e3, col_id=22)
     d = C.generate(rdf.F64, lens, 1, col_id=23, null_mod=10)
-    h = rdf.eval_expr([a, b, c, d], [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)])
+    prog = [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)]
+    h, agg = rdf.eval_expr_agg([a, b, c, d], prog)
+    _, agg_only = rdf.eval_expr_agg([a, b, c, d], prog, materialise=False)
     got = h.download()
     hcount = h.count()
 
@@ -185,8 +223,12 @@ def test_config2_chain_fused_1e8(rdf, ctx, oracle):
 
     with ThreadPoolExecutor(16) as ex:
         refs = list(ex.map(ref, range(NCH)))
-    count = 0
+    count, exact, sum_abs = 0, np.longdouble(0), np.longdouble(0)
     for i, w in enumerate(refs):
         assert_same_array(got[i], w, what=f"fused cfg2 chunk {i}", exact=False, max_ulp=3, check_payload=False)
         count += w.length - w.null_count
-    assert hcount == count
+        e, sa = oracle.sum_exact(oracle.F64, [w])
+        exact += e; sum_abs += sa
+    assert hcount == count == agg["count"] and agg_only == agg
+    # sum(h): 3 ulp of |sin| <= 1 per element on top of the float-sum bound
+    assert abs(np.longdouble(agg["sum"]) - exact) <= 16 * np.log2(1e8) * 2.0 ** -53 * sum_abs + 3 * 2.0 ** -53 * count
