@@ -199,6 +199,30 @@ int  bdf_aggregate_all_dev_async(bdf_ctx* ctx, const bdf_col* in, bdf_future** f
 int  bdf_future_wait(bdf_ctx* ctx, bdf_future* fut, bdf_agg4* out);
 void bdf_col_free(bdf_ctx* ctx, bdf_col* col);
 
+/* ---- N4: Arrow IPC files either side of the path ---------------------------------------------------------------
+ * DataFrame::from_arrow (src/dataframe.rs:391-407: arrow::ipc::reader::FileReader, every RecordBatch -> one chunk per
+ * column) and DataFrame::to_arrow (:515-525: arrow::ipc::writer::FileWriter).  The file is mapped and its footer, schema
+ * and RecordBatch metadata are decoded by the library itself (Arrow IPC file format, metadata V4/V5, uncompressed,
+ * little endian); body buffers are used in place.  Columns of the ten numeric types and Boolean can be read; any other
+ * column (strings, lists, structs, dictionaries, temporal types ...) is skipped and reported with dtype -1.
+ *   bdf_ipc_open / _close / _describe / _column / _batch_rows / _view need no context (and no GPU);
+ *   bdf_ipc_view      a zero-copy bdf_view of one column of one RecordBatch, pointing into the mapping;
+ *   bdf_ipc_read      the chosen columns straight to the device, one chunk per RecordBatch (flags: BDF_ASYNC; keep the
+ *                     file open until bdf_col_wait / bdf_synchronize then);
+ *   bdf_ipc_write_host  write host arrays ([column][batch] views, any offset) as an IPC file (V5, 64-byte aligned bodies);
+ *   bdf_ipc_write     device columns (equal chunk structure: chunk b of every column = RecordBatch b) -> IPC file. */
+typedef struct bdf_ipc bdf_ipc;
+int  bdf_ipc_open(const char* path, bdf_ipc** out);
+void bdf_ipc_close(bdf_ipc* file);
+int  bdf_ipc_describe(const bdf_ipc* file, int32_t* n_columns, int64_t* n_batches, int64_t* n_rows);
+int  bdf_ipc_column(const bdf_ipc* file, int32_t col, const char** name, int32_t* dtype, int32_t* nullable);
+int  bdf_ipc_batch_rows(const bdf_ipc* file, int64_t batch, int64_t* rows);
+int  bdf_ipc_view(const bdf_ipc* file, int64_t batch, int32_t col, bdf_view* out);
+int  bdf_ipc_read(bdf_ctx* ctx, const bdf_ipc* file, int32_t n_cols, const int32_t* cols, int flags, bdf_col** out /* n_cols */);
+int  bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches,
+                        const bdf_view* const* cols /* [n_cols][n_batches] */);
+int  bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* const* names, const bdf_col* const* cols);
+
 /* ---- measurement support ------------------------------------------------------------------------ */
 /* Per-launch CUDA-event timing on the library's compute stream (the stream the kernels run on). */
 typedef struct {

@@ -1,0 +1,662 @@
+// ipc.cu -- SURVEY 8(f) N4: Arrow IPC *files* either side of the path (host code only; no kernels here).
+//
+// DataFrame::from_arrow (src/dataframe.rs:391-407) reads every RecordBatch of an IPC file through
+// arrow::ipc::reader::FileReader into host arrays, and to_arrow (:515-525) writes them back with FileWriter.  The body
+// buffers of an IPC file ARE the device layout of this library (values buffer + LSB-first validity bitmap per
+// primitive column per batch), so the file is mapped, its footer/schema/RecordBatch metadata (flatbuffers, parsed by
+// hand below: there is no flatbuffers or arrow dependency) is decoded into (offset, length) pairs, and bdf_ipc_read
+// hands views INTO THE MAPPING to bdf_upload_many: page cache -> pinned staging -> HBM, one chunk per RecordBatch, no
+// intermediate host arrays.  Columns whose type is outside the path (strings, lists, dictionaries, dates ...) are
+// skipped by their buffer count and reported with dtype -1.
+//
+// Format restated from the Arrow columnar specification (format/File.fbs, Schema.fbs, Message.fbs; metadata V4 and V5,
+// with or without the 0xFFFFFFFF continuation marker).  Checked against pyarrow in tests/test_ipc.py (both directions).
+// Everything here goes through the public C ABI of the library (bdf_upload_many, bdf_download ...).
+#include "../../include/b200df.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cerrno>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace bdf { int set_error(int status, const char* msg); }
+
+namespace {
+
+int ipc_fail(int status, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    return bdf::set_error(status, buf);
+}
+
+// ---- flatbuffers, read side (bounds-checked; every accessor returns false on a malformed buffer) ----------------
+struct FbBuf {
+    const uint8_t* p;
+    size_t n;
+    template <typename T> bool rd(size_t at, T* v) const {
+        if (at > n || n - at < sizeof(T)) return false;
+        memcpy(v, p + at, sizeof(T));
+        return true;
+    }
+};
+struct FbTable {
+    const FbBuf* b = nullptr;
+    size_t pos = 0, vt = 0;
+    uint16_t vt_len = 0;
+    bool init(const FbBuf* buf, size_t table_pos) {
+        b = buf; pos = table_pos;
+        int32_t so;
+        if (!b->rd(pos, &so)) return false;
+        const int64_t v = (int64_t)pos - so;
+        if (v < 0 || (size_t)v + 4 > b->n) return false;
+        vt = (size_t)v;
+        return b->rd(vt, &vt_len) && vt_len >= 4 && vt + vt_len <= b->n;
+    }
+    size_t field(int id) const {   // absolute position of the field's inline data, 0 if absent
+        const size_t e = 4 + 2 * (size_t)id;
+        uint16_t off = 0;
+        if (e + 2 > vt_len || !b->rd(vt + e, &off) || off == 0) return 0;
+        return pos + off;
+    }
+    template <typename T> T scalar(int id, T dflt) const {
+        const size_t f = field(id);
+        T v = dflt;
+        if (f && !b->rd(f, &v)) v = dflt;
+        return v;
+    }
+    size_t ref(int id) const {     // target of an offset field (table, string or vector), 0 if absent/bad
+        const size_t f = field(id);
+        uint32_t o;
+        if (!f || !b->rd(f, &o) || o == 0 || f + o >= b->n) return 0;
+        return f + o;
+    }
+    bool table(int id, FbTable* t) const { const size_t r = ref(id); return r && t->init(b, r); }
+    bool vec(int id, size_t* first, uint32_t* count, size_t elem) const {   // absent vector = empty
+        *first = 0; *count = 0;
+        const size_t r = ref(id);
+        if (!r) return field(id) == 0;
+        if (!b->rd(r, count)) return false;
+        *first = r + 4;
+        return (uint64_t)*count * elem <= b->n - *first;
+    }
+    bool str(int id, std::string* s) const {
+        size_t first; uint32_t cnt;
+        if (!vec(id, &first, &cnt, 1)) return false;
+        s->assign((const char*)b->p + first, cnt);
+        return true;
+    }
+};
+
+// Schema.fbs Type union tags
+enum { T_NONE = 0, T_Null, T_Int, T_FloatingPoint, T_Binary, T_Utf8, T_Bool, T_Decimal, T_Date, T_Time, T_Timestamp, T_Interval, T_List,
+       T_Struct, T_Union, T_FixedSizeBinary, T_FixedSizeList, T_Map, T_Duration, T_LargeBinary, T_LargeUtf8, T_LargeList };
+
+struct IpcField {
+    std::string name;
+    int dtype = -1;       // bdf_dtype, BDF_BOOL, or -1: a type outside the path
+    bool nullable = false;
+    int n_nodes = 0, n_buffers = 0;   // what the field (with its children) occupies in every RecordBatch
+};
+
+// Field table -> IpcField; recursion only to count the nodes/buffers of nested children.
+bool parse_field(const FbTable& f, IpcField* out, int depth, std::string* why) {
+    if (depth > 32) { *why = "schema nested too deeply"; return false; }
+    if (!f.str(0, &out->name)) { *why = "bad field name"; return false; }
+    out->nullable = f.scalar<uint8_t>(1, 0) != 0;
+    const int tt = f.scalar<uint8_t>(2, 0);
+    const bool dict = f.field(4) != 0;
+    out->n_nodes = 1;
+    out->dtype = -1;
+    if (dict) { out->n_buffers = 2; return true; }   // stored as its index column; the dictionary lives in its own batches
+    FbTable ty;
+    const bool has_ty = f.table(3, &ty);
+    int own = 0;
+    bool nested = false;
+    switch (tt) {
+        case T_Null: own = 0; break;
+        case T_Int: {
+            own = 2;
+            if (has_ty) {
+                const int bw = ty.scalar<int32_t>(0, 0);
+                const bool sg = ty.scalar<uint8_t>(1, 0) != 0;
+                const int k = bw == 8 ? 0 : bw == 16 ? 1 : bw == 32 ? 2 : bw == 64 ? 3 : -1;
+                if (k >= 0) out->dtype = sg ? (BDF_I8 + k) : (BDF_U8 + k);
+            }
+            break;
+        }
+        case T_FloatingPoint: {
+            own = 2;
+            const int prec = has_ty ? ty.scalar<int16_t>(0, 0) : 0;   // HALF, SINGLE, DOUBLE
+            if (prec == 1) out->dtype = BDF_F32;
+            if (prec == 2) out->dtype = BDF_F64;
+            break;
+        }
+        case T_Bool: own = 2; out->dtype = BDF_BOOL; break;
+        case T_Decimal: case T_Date: case T_Time: case T_Timestamp: case T_Interval: case T_FixedSizeBinary: case T_Duration: own = 2; break;
+        case T_Binary: case T_Utf8: case T_LargeBinary: case T_LargeUtf8: own = 3; break;
+        case T_List: case T_LargeList: case T_Map: own = 2; nested = true; break;
+        case T_Struct: case T_FixedSizeList: own = 1; nested = true; break;
+        default: *why = "column '" + out->name + "' has a type this reader cannot skip (union / view / run-end encoded)"; return false;
+    }
+    out->n_buffers = own;
+    if (nested) {
+        size_t first; uint32_t cnt;
+        if (!f.vec(5, &first, &cnt, 4)) { *why = "bad children vector"; return false; }
+        for (uint32_t i = 0; i < cnt; i++) {
+            uint32_t o;
+            FbTable ch;
+            if (!f.b->rd(first + 4 * i, &o) || !ch.init(f.b, first + 4 * i + o)) { *why = "bad child field"; return false; }
+            IpcField c;
+            if (!parse_field(ch, &c, depth + 1, why)) return false;
+            out->n_nodes += c.n_nodes;
+            out->n_buffers += c.n_buffers;
+        }
+    }
+    return true;
+}
+
+struct IpcBuf { int64_t off = 0, len = 0; };
+struct IpcColChunk { int64_t len = 0, null_count = 0; IpcBuf validity, values; };
+struct IpcBatch {
+    int64_t rows = 0;
+    size_t body = 0;          // file offset of the body
+    int64_t body_len = 0;
+    std::vector<IpcColChunk> cols;   // top-level columns; entries of skipped columns stay zero
+};
+
+int dtype_bytes(int dtype, int64_t len, int64_t* out) {
+    static const int w[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+    if (dtype == BDF_BOOL) { *out = (len + 7) / 8; return 0; }
+    if (dtype < 0 || dtype > 9) return -1;
+    *out = len * w[dtype];
+    return 0;
+}
+
+}  // namespace
+
+struct bdf_ipc {
+    int fd = -1;
+    const uint8_t* map = nullptr;
+    size_t size = 0;
+    std::vector<IpcField> fields;
+    std::vector<IpcBatch> batches;
+    int64_t rows = 0;
+};
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+void bdf_ipc_close(bdf_ipc* f) {
+    if (!f) return;
+    if (f->map) munmap((void*)f->map, f->size);
+    if (f->fd >= 0) close(f->fd);
+    delete f;
+}
+
+int bdf_ipc_open(const char* path, bdf_ipc** out) {
+    if (!path || !out) return ipc_fail(BDF_INVALID, "null argument");
+    *out = nullptr;
+    bdf_ipc* f = new (std::nothrow) bdf_ipc();
+    if (!f) return ipc_fail(BDF_OOM, "host allocation failed");
+    struct Guard { bdf_ipc* f; ~Guard() { if (f) bdf_ipc_close(f); } } guard{f};
+    f->fd = open(path, O_RDONLY | O_CLOEXEC);
+    if (f->fd < 0) return ipc_fail(BDF_INVALID, "cannot open %s: %s", path, strerror(errno));
+    struct stat st;
+    if (fstat(f->fd, &st) != 0) return ipc_fail(BDF_INVALID, "cannot stat %s: %s", path, strerror(errno));
+    f->size = (size_t)st.st_size;
+    if (f->size < 8 + 4 + 6) return ipc_fail(BDF_INVALID, "%s is too short to be an Arrow IPC file", path);
+    void* m = mmap(nullptr, f->size, PROT_READ, MAP_PRIVATE, f->fd, 0);
+    if (m == MAP_FAILED) return ipc_fail(BDF_INVALID, "cannot map %s: %s", path, strerror(errno));
+    f->map = (const uint8_t*)m;
+    madvise(m, f->size, MADV_SEQUENTIAL);
+    if (memcmp(f->map, "ARROW1", 6) != 0 || memcmp(f->map + f->size - 6, "ARROW1", 6) != 0)
+        return ipc_fail(BDF_INVALID, "%s is not an Arrow IPC file (magic ARROW1 missing; the stream format has no footer)", path);
+    int32_t flen;
+    memcpy(&flen, f->map + f->size - 10, 4);
+    if (flen <= 0 || (size_t)flen > f->size - 18) return ipc_fail(BDF_INVALID, "bad footer length %d", flen);
+    const FbBuf fb{f->map + f->size - 10 - (size_t)flen, (size_t)flen};
+    uint32_t root;
+    FbTable footer, schema;
+    if (!fb.rd(0, &root) || !footer.init(&fb, root)) return ipc_fail(BDF_INVALID, "malformed footer");
+    if (!footer.table(1, &schema)) return ipc_fail(BDF_INVALID, "footer without schema");
+    if (schema.scalar<int16_t>(0, 0) != 0) return ipc_fail(BDF_UNSUPPORTED, "big-endian IPC file");
+    size_t first; uint32_t cnt;
+    if (!schema.vec(1, &first, &cnt, 4)) return ipc_fail(BDF_INVALID, "malformed schema");
+    int nodes_per_batch = 0, buffers_per_batch = 0;
+    for (uint32_t i = 0; i < cnt; i++) {
+        uint32_t o;
+        FbTable ft;
+        if (!fb.rd(first + 4 * i, &o) || !ft.init(&fb, first + 4 * i + o)) return ipc_fail(BDF_INVALID, "malformed field %u", i);
+        IpcField fld;
+        std::string why;
+        if (!parse_field(ft, &fld, 0, &why)) return ipc_fail(BDF_UNSUPPORTED, "%s", why.c_str());
+        nodes_per_batch += fld.n_nodes;
+        buffers_per_batch += fld.n_buffers;
+        f->fields.push_back(std::move(fld));
+    }
+    // record batch blocks: struct Block { offset: long; metaDataLength: int; bodyLength: long } (24 bytes)
+    size_t bfirst; uint32_t bcnt;
+    if (!footer.vec(3, &bfirst, &bcnt, 24)) return ipc_fail(BDF_INVALID, "malformed record batch index");
+    for (uint32_t k = 0; k < bcnt; k++) {
+        int64_t off, body_len; int32_t meta_len;
+        fb.rd(bfirst + 24 * (size_t)k, &off); fb.rd(bfirst + 24 * (size_t)k + 8, &meta_len); fb.rd(bfirst + 24 * (size_t)k + 16, &body_len);
+        if (off < 8 || meta_len < 8 || body_len < 0 || (uint64_t)off + (uint64_t)meta_len + (uint64_t)body_len > f->size)
+            return ipc_fail(BDF_INVALID, "record batch %u lies outside the file", k);
+        // encapsulated message: [0xFFFFFFFF] <int32 metadata size> <flatbuffer> <padding> <body>
+        size_t p = (size_t)off;
+        int32_t word;
+        memcpy(&word, f->map + p, 4);
+        if (word == -1) { p += 4; memcpy(&word, f->map + p, 4); }
+        p += 4;
+        if (word <= 0 || p + (size_t)word > (size_t)off + (size_t)meta_len) return ipc_fail(BDF_INVALID, "record batch %u: bad metadata size", k);
+        const FbBuf mb{f->map + p, (size_t)word};
+        FbTable msg, rb;
+        if (!mb.rd(0, &root) || !msg.init(&mb, root)) return ipc_fail(BDF_INVALID, "record batch %u: malformed message", k);
+        if (msg.scalar<uint8_t>(1, 0) != 3 || !msg.table(2, &rb)) return ipc_fail(BDF_INVALID, "block %u is not a RecordBatch message", k);
+        if (rb.field(3)) return ipc_fail(BDF_UNSUPPORTED, "compressed IPC bodies are not supported (write the file uncompressed)");
+        IpcBatch b;
+        b.rows = rb.scalar<int64_t>(0, 0);
+        b.body = (size_t)off + (size_t)meta_len;
+        b.body_len = body_len;
+        size_t nfirst, bufirst; uint32_t ncnt, bucnt;
+        if (!rb.vec(1, &nfirst, &ncnt, 16) || !rb.vec(2, &bufirst, &bucnt, 16)) return ipc_fail(BDF_INVALID, "record batch %u: malformed nodes/buffers", k);
+        if ((int)ncnt != nodes_per_batch || (int)bucnt != buffers_per_batch)
+            return ipc_fail(BDF_INVALID, "record batch %u: %u nodes / %u buffers, the schema needs %d / %d", k, ncnt, bucnt, nodes_per_batch, buffers_per_batch);
+        b.cols.resize(f->fields.size());
+        size_t ni = 0, bi = 0;
+        for (size_t c = 0; c < f->fields.size(); c++) {
+            const IpcField& fld = f->fields[c];
+            if (fld.dtype >= 0) {
+                IpcColChunk& cc = b.cols[c];
+                mb.rd(nfirst + 16 * ni, &cc.len); mb.rd(nfirst + 16 * ni + 8, &cc.null_count);
+                mb.rd(bufirst + 16 * bi, &cc.validity.off); mb.rd(bufirst + 16 * bi + 8, &cc.validity.len);
+                mb.rd(bufirst + 16 * (bi + 1), &cc.values.off); mb.rd(bufirst + 16 * (bi + 1) + 8, &cc.values.len);
+                int64_t need = 0;
+                dtype_bytes(fld.dtype, cc.len, &need);
+                const bool has_v = cc.null_count > 0;
+                if (cc.len != b.rows || cc.null_count < 0 || cc.null_count > cc.len || cc.values.off < 0 || cc.values.len < need ||
+                    cc.values.off + cc.values.len > body_len || (has_v && (cc.validity.off < 0 || cc.validity.len < (cc.len + 7) / 8 ||
+                    cc.validity.off + cc.validity.len > body_len)))
+                    return ipc_fail(BDF_INVALID, "record batch %u, column '%s': buffers do not fit the batch", k, fld.name.c_str());
+            }
+            ni += fld.n_nodes;
+            bi += fld.n_buffers;
+        }
+        f->rows += b.rows;
+        f->batches.push_back(std::move(b));
+    }
+    guard.f = nullptr;
+    *out = f;
+    return BDF_OK;
+}
+
+int bdf_ipc_describe(const bdf_ipc* f, int32_t* n_columns, int64_t* n_batches, int64_t* n_rows) {
+    if (!f) return ipc_fail(BDF_INVALID, "null argument");
+    if (n_columns) *n_columns = (int32_t)f->fields.size();
+    if (n_batches) *n_batches = (int64_t)f->batches.size();
+    if (n_rows) *n_rows = f->rows;
+    return BDF_OK;
+}
+
+int bdf_ipc_column(const bdf_ipc* f, int32_t col, const char** name, int32_t* dtype, int32_t* nullable) {
+    if (!f || col < 0 || (size_t)col >= f->fields.size()) return ipc_fail(BDF_INVALID, "column index out of range");
+    if (name) *name = f->fields[col].name.c_str();
+    if (dtype) *dtype = f->fields[col].dtype;
+    if (nullable) *nullable = f->fields[col].nullable;
+    return BDF_OK;
+}
+
+int bdf_ipc_batch_rows(const bdf_ipc* f, int64_t batch, int64_t* rows) {
+    if (!f || !rows || batch < 0 || (size_t)batch >= f->batches.size()) return ipc_fail(BDF_INVALID, "batch index out of range");
+    *rows = f->batches[batch].rows;
+    return BDF_OK;
+}
+
+int bdf_ipc_view(const bdf_ipc* f, int64_t batch, int32_t col, bdf_view* out) {
+    if (!f || !out || batch < 0 || (size_t)batch >= f->batches.size() || col < 0 || (size_t)col >= f->fields.size())
+        return ipc_fail(BDF_INVALID, "batch/column index out of range");
+    if (f->fields[col].dtype < 0) return ipc_fail(BDF_UNSUPPORTED, "column '%s' has a type outside the numeric path", f->fields[col].name.c_str());
+    const IpcBatch& b = f->batches[batch];
+    const IpcColChunk& c = b.cols[col];
+    out->values = f->map + b.body + c.values.off;
+    out->validity = c.null_count > 0 ? f->map + b.body + c.validity.off : nullptr;
+    out->len = c.len;
+    out->offset = 0;
+    out->null_count = c.null_count;
+    return BDF_OK;
+}
+
+int bdf_ipc_read(bdf_ctx* ctx, const bdf_ipc* f, int32_t n_cols, const int32_t* cols, int flags, bdf_col** out) {
+    if (!ctx || !f || !cols || !out || n_cols <= 0) return ipc_fail(BDF_INVALID, "null argument");
+    const int64_t nb = (int64_t)f->batches.size();
+    std::vector<std::vector<bdf_view>> views((size_t)n_cols);
+    std::vector<const bdf_view*> vp((size_t)n_cols);
+    std::vector<int32_t> dtypes((size_t)n_cols);
+    std::vector<int64_t> nch((size_t)n_cols, nb);
+    for (int32_t i = 0; i < n_cols; i++) {
+        if (cols[i] < 0 || (size_t)cols[i] >= f->fields.size()) return ipc_fail(BDF_INVALID, "column index out of range");
+        dtypes[i] = f->fields[cols[i]].dtype;
+        views[i].resize((size_t)std::max<int64_t>(nb, 1));
+        for (int64_t b = 0; b < nb; b++) {
+            const int st = bdf_ipc_view(f, b, cols[i], &views[i][b]);
+            if (st != BDF_OK) return st;
+        }
+        vp[i] = views[i].data();
+    }
+    return bdf_upload_many(ctx, n_cols, dtypes.data(), nch.data(), vp.data(), flags, out);
+}
+
+}  // extern "C"
+#pragma GCC visibility pop
+
+// ---- write side ------------------------------------------------------------------------------------------------
+namespace {
+
+// Minimal flatbuffers writer, front to back: a table is laid out before the objects it refers to, reference fields
+// are patched once the target exists (uoffsets point forward, the vtable sits right before its table).
+struct FbOut {
+    std::vector<uint8_t> b;
+    template <typename T> void put(T v) { const uint8_t* p = (const uint8_t*)&v; b.insert(b.end(), p, p + sizeof v); }
+    template <typename T> void set(size_t at, T v) { memcpy(&b[at], &v, sizeof v); }
+    void pad_to(size_t a) { while (b.size() % a) b.push_back(0); }
+    void link(size_t ref_pos, size_t target) { set<uint32_t>(ref_pos, (uint32_t)(target - ref_pos)); }
+};
+struct FbF { int id; int size; uint64_t bits; };   // size 0 = reference (4 bytes, patched later)
+
+// Returns the table position; ref_pos receives the absolute position of every reference field, in `fields` order.
+size_t fb_table(FbOut& o, const std::vector<FbF>& fields, std::vector<size_t>* ref_pos) {
+    int max_id = -1;
+    for (const FbF& f : fields) max_id = f.id > max_id ? f.id : max_id;
+    const size_t vt_len = 4 + 2 * (size_t)(max_id + 1);
+    std::vector<uint16_t> offs((size_t)(max_id + 1), 0);
+    size_t off = 4;
+    std::vector<size_t> at(fields.size());
+    for (size_t i = 0; i < fields.size(); i++) {
+        const size_t sz = fields[i].size ? (size_t)fields[i].size : 4;
+        off = (off + sz - 1) / sz * sz;
+        at[i] = off; offs[fields[i].id] = (uint16_t)off;
+        off += sz;
+    }
+    const size_t tsize = (off + 3) / 4 * 4;
+    o.pad_to(2);
+    while ((o.b.size() + vt_len) % 8) o.b.push_back(0);
+    const size_t vt = o.b.size();
+    o.put<uint16_t>((uint16_t)vt_len); o.put<uint16_t>((uint16_t)tsize);
+    for (uint16_t x : offs) o.put<uint16_t>(x);
+    const size_t t = o.b.size();
+    o.b.resize(t + tsize, 0);
+    o.set<int32_t>(t, (int32_t)(t - vt));
+    if (ref_pos) ref_pos->clear();
+    for (size_t i = 0; i < fields.size(); i++) {
+        if (fields[i].size == 0) { if (ref_pos) ref_pos->push_back(t + at[i]); }
+        else memcpy(&o.b[t + at[i]], &fields[i].bits, (size_t)fields[i].size);
+    }
+    return t;
+}
+size_t fb_string(FbOut& o, const std::string& s) {
+    o.pad_to(4);
+    const size_t p = o.b.size();
+    o.put<uint32_t>((uint32_t)s.size());
+    o.b.insert(o.b.end(), s.begin(), s.end());
+    o.b.push_back(0);
+    return p;
+}
+size_t fb_struct_vec(FbOut& o, const void* data, uint32_t count, size_t elem) {   // 8-byte aligned elements
+    o.pad_to(4);
+    while ((o.b.size() + 4) % 8) o.b.push_back(0);
+    const size_t p = o.b.size();
+    o.put<uint32_t>(count);
+    const uint8_t* d = (const uint8_t*)data;
+    o.b.insert(o.b.end(), d, d + (size_t)count * elem);
+    return p;
+}
+
+// Schema table (fields of primitive / boolean type) at the current end of `o`; returns its position.
+size_t fb_schema(FbOut& o, int n_cols, const char* const* names, const int32_t* dtypes) {
+    std::vector<size_t> refs;
+    const size_t schema = fb_table(o, {{1, 0, 0}}, &refs);
+    o.pad_to(4);
+    const size_t vec = o.b.size();
+    o.link(refs[0], vec);
+    o.put<uint32_t>((uint32_t)n_cols);
+    const size_t slots = o.b.size();
+    o.b.resize(slots + 4 * (size_t)n_cols, 0);
+    for (int c = 0; c < n_cols; c++) {
+        const int dt = dtypes[c];
+        const uint8_t tt = dt == BDF_BOOL ? T_Bool : (dt == BDF_F32 || dt == BDF_F64) ? T_FloatingPoint : T_Int;
+        std::vector<size_t> fr;
+        // Field: name(0) nullable(1) type_type(2) type(3) children(5)
+        const size_t field = fb_table(o, {{0, 0, 0}, {1, 1, 1}, {2, 1, tt}, {3, 0, 0}, {5, 0, 0}}, &fr);
+        o.link(slots + 4 * (size_t)c, field);
+        o.link(fr[0], fb_string(o, names[c]));
+        size_t ty;
+        if (tt == T_Bool) ty = fb_table(o, {}, nullptr);
+        else if (tt == T_FloatingPoint) ty = fb_table(o, {{0, 2, (uint64_t)(dt == BDF_F32 ? 1 : 2)}}, nullptr);
+        else {
+            static const int bw[8] = {8, 16, 32, 64, 8, 16, 32, 64};
+            ty = fb_table(o, {{0, 4, (uint64_t)bw[dt]}, {1, 1, (uint64_t)(dt <= BDF_I64 ? 1 : 0)}}, nullptr);
+        }
+        o.link(fr[1], ty);
+        o.pad_to(4);
+        o.link(fr[2], o.b.size());
+        o.put<uint32_t>(0);   // children: empty vector
+    }
+    return schema;
+}
+
+struct Block { int64_t offset; int32_t meta_len; int32_t pad; int64_t body_len; };
+
+bool write_all(int fd, const void* p, size_t n) {
+    const uint8_t* b = (const uint8_t*)p;
+    while (n) {
+        const ssize_t w = write(fd, b, n > (1u << 30) ? (1u << 30) : n);
+        if (w < 0) { if (errno == EINTR) continue; return false; }
+        b += w; n -= (size_t)w;
+    }
+    return true;
+}
+
+// Encapsulated message: continuation marker, metadata size, flatbuffer, zero padding so that the body starts on a
+// 64-byte file offset.  Returns the Block's metaDataLength.
+bool write_message(int fd, int64_t* pos, const FbOut& fb, int32_t* meta_len) {
+    const int64_t after = (*pos + 8 + (int64_t)fb.b.size() + 63) / 64 * 64;
+    const int32_t mlen = (int32_t)(after - *pos - 8);
+    const int32_t marker = -1;
+    std::vector<uint8_t> pad((size_t)mlen - fb.b.size(), 0);
+    if (!write_all(fd, &marker, 4) || !write_all(fd, &mlen, 4) || !write_all(fd, fb.b.data(), fb.b.size()) || !write_all(fd, pad.data(), pad.size()))
+        return false;
+    *meta_len = mlen + 8;
+    *pos = after;
+    return true;
+}
+
+// Bits [bit0, bit0+n) of src, re-based to bit 0 of dst (dst zero padded to whole bytes).
+void copy_bits(const uint8_t* src, int64_t bit0, int64_t n, uint8_t* dst) {
+    const int64_t nbytes = (n + 7) / 8;
+    if (nbytes == 0) return;
+    const int sh = (int)(bit0 & 7);
+    const uint8_t* s = src + (bit0 >> 3);
+    if (sh == 0) memcpy(dst, s, (size_t)nbytes);
+    else {
+        const int64_t last_src = (bit0 + n - 1) >> 3;   // index of the last source byte that holds a wanted bit
+        for (int64_t i = 0; i < nbytes; i++) {
+            const uint8_t lo = s[i];
+            const uint8_t hi = ((bit0 >> 3) + i + 1 <= last_src) ? s[i + 1] : 0;
+            dst[i] = (uint8_t)((lo >> sh) | (hi << (8 - sh)));
+        }
+    }
+    if (n & 7) dst[nbytes - 1] &= (uint8_t)((1u << (n & 7)) - 1u);
+}
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches,
+                       const bdf_view* const* cols) {
+    if (!path || !names || !dtypes || n_cols <= 0 || n_batches < 0 || (n_batches && !cols)) return ipc_fail(BDF_INVALID, "null argument");
+    for (int c = 0; c < n_cols; c++) {
+        if (!names[c] || !((dtypes[c] >= 0 && dtypes[c] <= 9) || dtypes[c] == BDF_BOOL)) return ipc_fail(BDF_INVALID, "column %d: bad name or dtype", c);
+        for (int64_t b = 0; b < n_batches; b++)
+            if (cols[c][b].len != cols[0][b].len || cols[c][b].len < 0 || cols[c][b].offset < 0)
+                return ipc_fail(BDF_LENGTH_MISMATCH, "batch %lld: column '%s' has %lld rows, column '%s' has %lld", (long long)b, names[c],
+                                (long long)cols[c][b].len, names[0], (long long)cols[0][b].len);
+    }
+    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+    if (fd < 0) return ipc_fail(BDF_INVALID, "cannot create %s: %s", path, strerror(errno));
+    bool ok = true;
+    int64_t pos = 0;
+    static const uint8_t zeros[64] = {0};
+    ok = write_all(fd, "ARROW1\0\0", 8);
+    pos = 8;
+    {   // schema message
+        FbOut fb;
+        fb.put<uint32_t>(0);
+        std::vector<size_t> refs;
+        const size_t msg = fb_table(fb, {{0, 2, 4 /* MetadataVersion::V5 */}, {1, 1, 1 /* Schema */}, {2, 0, 0}, {3, 8, 0}}, &refs);
+        fb.link(0, msg);
+        fb.link(refs[0], fb_schema(fb, n_cols, names, dtypes));
+        fb.pad_to(8);
+        int32_t ml;
+        ok = ok && write_message(fd, &pos, fb, &ml);
+    }
+    std::vector<Block> blocks;
+    std::vector<uint8_t> tmp;
+    for (int64_t b = 0; b < n_batches && ok; b++) {
+        const int64_t rows = cols[0][b].len;
+        struct Node { int64_t len, nulls; };
+        struct Buf { int64_t off, len; };
+        std::vector<Node> nodes((size_t)n_cols);
+        std::vector<Buf> bufs(2 * (size_t)n_cols);
+        int64_t body = 0;
+        for (int c = 0; c < n_cols; c++) {
+            const bdf_view& v = cols[c][b];
+            int64_t nulls = v.validity ? v.null_count : 0;
+            if (v.validity && nulls < 0) {
+                nulls = 0;
+                for (int64_t i = 0; i < rows; i++) nulls += !((v.validity[(v.offset + i) >> 3] >> ((v.offset + i) & 7)) & 1);
+            }
+            nodes[c] = {rows, nulls};
+            const int64_t vbytes = nulls > 0 ? (rows + 7) / 8 : 0;
+            int64_t dbytes = 0;
+            dtype_bytes(dtypes[c], rows, &dbytes);
+            bufs[2 * c] = {body, vbytes};
+            body += (vbytes + 63) / 64 * 64;
+            bufs[2 * c + 1] = {body, dbytes};
+            body += (dbytes + 63) / 64 * 64;
+        }
+        FbOut fb;
+        fb.put<uint32_t>(0);
+        std::vector<size_t> mr, rr;
+        const size_t msg = fb_table(fb, {{0, 2, 4}, {1, 1, 3 /* RecordBatch */}, {2, 0, 0}, {3, 8, (uint64_t)body}}, &mr);
+        fb.link(0, msg);
+        const size_t rb = fb_table(fb, {{0, 8, (uint64_t)rows}, {1, 0, 0}, {2, 0, 0}}, &rr);
+        fb.link(mr[0], rb);
+        fb.link(rr[0], fb_struct_vec(fb, nodes.data(), (uint32_t)n_cols, 16));
+        fb.link(rr[1], fb_struct_vec(fb, bufs.data(), 2 * (uint32_t)n_cols, 16));
+        fb.pad_to(8);
+        Block blk{pos, 0, 0, body};
+        ok = ok && write_message(fd, &pos, fb, &blk.meta_len);
+        for (int c = 0; c < n_cols && ok; c++) {
+            const bdf_view& v = cols[c][b];
+            const int64_t vbytes = bufs[2 * c].len, dbytes = bufs[2 * c + 1].len;
+            if (vbytes) {
+                tmp.assign((size_t)vbytes, 0);
+                copy_bits(v.validity, v.offset, rows, tmp.data());
+                ok = ok && write_all(fd, tmp.data(), (size_t)vbytes) && write_all(fd, zeros, (size_t)((64 - vbytes % 64) % 64));
+            }
+            if (dbytes) {
+                if (dtypes[c] == BDF_BOOL) {
+                    tmp.assign((size_t)dbytes, 0);
+                    copy_bits((const uint8_t*)v.values, v.offset, rows, tmp.data());
+                    ok = ok && write_all(fd, tmp.data(), (size_t)dbytes);
+                } else {
+                    ok = ok && write_all(fd, (const uint8_t*)v.values + v.offset * (dbytes / rows), (size_t)dbytes);
+                }
+                ok = ok && write_all(fd, zeros, (size_t)((64 - dbytes % 64) % 64));
+            }
+        }
+        pos += body;
+        blocks.push_back(blk);
+    }
+    if (ok) {   // end-of-stream marker, footer, footer size, magic
+        const int32_t eos[2] = {-1, 0};
+        ok = write_all(fd, eos, 8);
+        FbOut fb;
+        fb.put<uint32_t>(0);
+        std::vector<size_t> fr;
+        // Footer: version(0) schema(1) dictionaries(2) recordBatches(3)
+        const size_t footer = fb_table(fb, {{0, 2, 4}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}}, &fr);
+        fb.link(0, footer);
+        fb.link(fr[0], fb_schema(fb, n_cols, names, dtypes));
+        fb.link(fr[1], fb_struct_vec(fb, nullptr, 0, 24));
+        fb.link(fr[2], fb_struct_vec(fb, blocks.data(), (uint32_t)blocks.size(), 24));
+        fb.pad_to(8);
+        const int32_t flen = (int32_t)fb.b.size();
+        ok = ok && write_all(fd, fb.b.data(), fb.b.size()) && write_all(fd, &flen, 4) && write_all(fd, "ARROW1", 6);
+    }
+    const int err = errno;
+    if (close(fd) != 0) ok = false;
+    if (!ok) return ipc_fail(BDF_INVALID, "writing %s failed: %s", path, strerror(err ? err : errno));
+    return BDF_OK;
+}
+
+int bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* const* names, const bdf_col* const* cols) {
+    if (!ctx || !path || !names || !cols || n_cols <= 0) return ipc_fail(BDF_INVALID, "null argument");
+    std::vector<int32_t> dtypes((size_t)n_cols);
+    std::vector<std::vector<bdf_out>> outs((size_t)n_cols);
+    std::vector<std::vector<bdf_view>> views((size_t)n_cols);
+    std::vector<const bdf_view*> vp((size_t)n_cols);
+    std::vector<void*> allocs;
+    int64_t n_batches = -1;
+    int st = BDF_OK;
+    for (int c = 0; c < n_cols && st == BDF_OK; c++) {
+        int64_t nch = 0, total = 0;
+        if (!cols[c]) { st = ipc_fail(BDF_INVALID, "null column"); break; }
+        st = bdf_col_describe(cols[c], &dtypes[c], &nch, &total);
+        if (st != BDF_OK) break;
+        if (n_batches < 0) n_batches = nch;
+        if (nch != n_batches) { st = ipc_fail(BDF_LENGTH_MISMATCH, "columns have different numbers of chunks (%lld, %lld)", (long long)nch, (long long)n_batches); break; }
+        outs[c].resize((size_t)std::max<int64_t>(nch, 1));
+        views[c].resize((size_t)std::max<int64_t>(nch, 1));
+        for (int64_t b = 0; b < nch && st == BDF_OK; b++) {
+            int64_t len = 0, nulls = 0; int32_t hv = 0;
+            st = bdf_col_chunk_info(ctx, cols[c], b, &len, &nulls, &hv);
+            if (st != BDF_OK) break;
+            int64_t dbytes = 0;
+            dtype_bytes(dtypes[c], len, &dbytes);
+            void *pv = nullptr, *pm = nullptr;
+            st = bdf_host_alloc(ctx, (size_t)dbytes + 64, &pv);   // pinned: the device->host copies run at PCIe speed
+            if (st == BDF_OK) { allocs.push_back(pv); st = bdf_host_alloc(ctx, (size_t)(len + 7) / 8 + 64, &pm); }
+            if (st == BDF_OK) allocs.push_back(pm);
+            outs[c][b] = bdf_out{pv, (uint8_t*)pm, len, 0, 0};
+        }
+        vp[c] = views[c].data();
+    }
+    for (int c = 0; c < n_cols && st == BDF_OK; c++) st = bdf_download_begin(ctx, cols[c], outs[c].data());
+    for (int c = 0; c < n_cols && st == BDF_OK; c++) {
+        st = bdf_download_end(ctx, cols[c], outs[c].data());
+        for (int64_t b = 0; b < n_batches && st == BDF_OK; b++) {
+            const bdf_out& o = outs[c][b];
+            views[c][b] = bdf_view{o.values, o.has_validity ? o.validity : nullptr, o.len, 0, o.has_validity ? o.null_count : 0};
+        }
+    }
+    if (st == BDF_OK) st = bdf_ipc_write_host(path, n_cols, names, dtypes.data(), n_batches, vp.data());
+    for (void* p : allocs) bdf_host_free(ctx, p);
+    return st;
+}
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -38,6 +38,13 @@ static int fail(int status, const char* fmt, ...) {
     return status;
 }
 
+namespace bdf {
+int set_error(int status, const char* msg) {   // for the host-only translation units of the library (ipc.cu)
+    g_err = msg;
+    return status;
+}
+}  // namespace bdf
+
 static int cuda_status(cudaError_t e) { return e == cudaErrorMemoryAllocation ? BDF_OOM : BDF_CUDA; }
 
 #define CK(call)                                                                                       \

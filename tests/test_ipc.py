@@ -1,0 +1,288 @@
+"""N4: Arrow IPC files either side of the path (DataFrame::from_arrow / to_arrow,
+src/dataframe.rs:391-407, 515-525).  The library decodes and encodes the format itself; the checker is pyarrow
+(an independent Arrow implementation): files written by pyarrow must read back identically through bdf_ipc_*,
+files written by bdf_ipc_write* must pass pyarrow's flatbuffers verifier and read back identically.
+The parser/writer tests need no GPU; the device round trips are marked gpu."""
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.ipc
+import pytest
+
+NUMERIC = [("i8", pa.int8()), ("i16", pa.int16()), ("i32", pa.int32()), ("i64", pa.int64()), ("u8", pa.uint8()), ("u16", pa.uint16()),
+           ("u32", pa.uint32()), ("u64", pa.uint64()), ("f32", pa.float32()), ("f64", pa.float64())]
+
+
+def random_array(rng, typ, n, null_frac):
+    if pa.types.is_boolean(typ):
+        v = rng.random(n) > 0.5
+    elif pa.types.is_floating(typ):
+        v = rng.normal(0, 1e3, n).astype(typ.to_pandas_dtype())
+    else:
+        info = np.iinfo(typ.to_pandas_dtype())
+        v = rng.integers(info.min, info.max, n, dtype=typ.to_pandas_dtype(), endpoint=True)
+    mask = rng.random(n) < null_frac if null_frac else None
+    return pa.array(v, type=typ, mask=mask)
+
+
+def mixed_batches(rng, lens, null_frac=0.2):
+    """Numeric + boolean columns interleaved with every kind of column the reader has to step over."""
+    fields, batches = None, []
+    for n in lens:
+        cols, names = [], []
+
+        def add(name, arr):
+            names.append(name); cols.append(arr)
+        add("s", pa.array([None if i % 7 == 0 else f"row{i}" for i in range(n)], pa.string()))
+        for name, typ in NUMERIC[:5]:
+            add(name, random_array(rng, typ, n, null_frac))
+        add("lst", pa.array([[i, i + 1] if i % 3 else None for i in range(n)], pa.list_(pa.int32())))
+        add("st", pa.array([{"x": i, "y": [float(i)]} for i in range(n)], pa.struct([("x", pa.int64()), ("y", pa.list_(pa.float64()))])))
+        for name, typ in NUMERIC[5:]:
+            add(name, random_array(rng, typ, n, 0.0 if name == "u32" else null_frac))
+        add("dict", pa.DictionaryArray.from_arrays(pa.array([None if i % 4 == 2 else i % 2 for i in range(n)], pa.int8()), pa.array(["a", "b"])))
+        add("b", random_array(rng, pa.bool_(), n, null_frac))
+        add("d32", pa.array(np.arange(n, dtype=np.int32), pa.date32()))
+        add("ts", pa.array(np.arange(n, dtype=np.int64), pa.timestamp("us")))
+        add("fsl", pa.array([[1.0, 2.0, 3.0]] * n, pa.list_(pa.float32(), 3)))
+        add("ls", pa.array([f"{i}" for i in range(n)], pa.large_string()))
+        add("nul", pa.nulls(n))
+        add("dec", pa.array([None if i % 5 == 0 else i for i in range(n)], pa.decimal128(12, 2)))
+        add("b2", random_array(rng, pa.bool_(), n, 0.0))
+        add("mp", pa.array([[("k", i)] for i in range(n)], pa.map_(pa.string(), pa.int32())))
+        add("tail", random_array(rng, pa.float64(), n, null_frac))
+        b = pa.record_batch(cols, names=names)
+        fields = fields or b.schema
+        batches.append(b)
+    return fields, batches
+
+
+def write_file(path, schema, batches, options=None):
+    with pa.ipc.new_file(path, schema, options=options) as w:
+        for b in batches:
+            w.write_batch(b)
+
+
+def check_view_against_pyarrow(arr, parr, what):
+    """arr: PrimitiveArray/BooleanArray view from the library; parr: the pyarrow array of the same batch/column."""
+    assert arr.length == len(parr), what
+    want_valid = np.array(parr.is_valid().to_pylist(), dtype=bool) if len(parr) else np.zeros(0, bool)
+    assert np.array_equal(arr.valid_mask(), want_valid), f"{what}: validity"
+    if arr.validity is None or arr.null_count >= 0:   # -1 = "unknown" on a host-made slice
+        assert (arr.null_count if arr.validity is not None else 0) == parr.null_count, f"{what}: null_count"
+    if pa.types.is_boolean(parr.type):
+        got = arr.value_bits()[want_valid]
+        want = np.array(parr.drop_null().to_pylist(), dtype=bool)
+    else:
+        got = arr.value_slice()[want_valid]
+        want = parr.drop_null().to_numpy(zero_copy_only=False)
+        assert got.dtype == want.dtype, what
+        got, want = got.view(f"u{got.dtype.itemsize}"), want.view(f"u{want.dtype.itemsize}")
+    assert np.array_equal(got, want), f"{what}: values"
+
+
+@pytest.mark.parametrize("variant", ["v5", "v4", "v4-legacy"])
+def test_reader_matches_pyarrow(rdf, tmp_path, variant):
+    rng = np.random.default_rng(7)
+    schema, batches = mixed_batches(rng, [0, 1, 7, 64, 1000, 4097])
+    opts = {"v5": None, "v4": pa.ipc.IpcWriteOptions(metadata_version=pa.ipc.MetadataVersion.V4),
+            "v4-legacy": pa.ipc.IpcWriteOptions(metadata_version=pa.ipc.MetadataVersion.V4, use_legacy_format=True)}[variant]
+    path = str(tmp_path / "mixed.arrow")
+    write_file(path, schema, batches, opts)
+    with rdf.IpcFile(path) as f:
+        assert f.num_columns == len(schema) and f.num_batches == len(batches) and f.num_rows == sum(b.num_rows for b in batches)
+        want_dtype = {name: getattr(rdf, name.upper()) for name, _ in NUMERIC}
+        want_dtype.update({"b": 10, "b2": 10, "tail": rdf.F64})
+        for (name, dtype, nullable), fld in zip(f.schema, schema):
+            assert name == fld.name and nullable == fld.nullable
+            assert dtype == want_dtype.get(name, -1), name
+        for bi, b in enumerate(batches):
+            assert f.batch_rows(bi) == b.num_rows
+            for name in want_dtype:
+                check_view_against_pyarrow(f.view(bi, name), b.column(name), f"{variant} batch {bi} column {name}")
+        with pytest.raises(rdf.UnsupportedType):
+            f.view(0, "s")
+        with pytest.raises(rdf.ArrowError):
+            f.view(len(batches), "i8")
+        with pytest.raises(KeyError):
+            f.view(0, "nope")
+
+
+def test_reader_rejects_what_it_cannot_decode(rdf, tmp_path):
+    rng = np.random.default_rng(1)
+    t = pa.record_batch([random_array(rng, pa.float64(), 100, 0.1)], names=["x"])
+    p = str(tmp_path / "z.arrow")
+    try:
+        write_file(p, t.schema, [t], pa.ipc.IpcWriteOptions(compression="lz4"))
+        with pytest.raises(rdf.UnsupportedType):
+            rdf.IpcFile(p)
+    except (pa.ArrowNotImplementedError, pa.ArrowInvalid):
+        pass   # this pyarrow build has no lz4: nothing to reject
+    p = str(tmp_path / "stream.arrows")
+    with pa.ipc.new_stream(p, t.schema) as w:
+        w.write_batch(t)
+    with pytest.raises(rdf.ArrowError):
+        rdf.IpcFile(p)
+    good = str(tmp_path / "good.arrow")
+    write_file(good, t.schema, [t])
+    raw = open(good, "rb").read()
+    for cut, name in ((len(raw) - 3, "cut-magic"), (12, "tiny")):
+        q = str(tmp_path / name)
+        open(q, "wb").write(raw[:cut])
+        with pytest.raises(rdf.ArrowError):
+            rdf.IpcFile(q)
+    bad = bytearray(raw)
+    bad[-10:-6] = (2 ** 31 - 1).to_bytes(4, "little")   # absurd footer length
+    q = str(tmp_path / "badfooter")
+    open(q, "wb").write(bytes(bad))
+    with pytest.raises(rdf.ArrowError):
+        rdf.IpcFile(q)
+    with pytest.raises(rdf.ArrowError):
+        rdf.IpcFile(str(tmp_path / "does-not-exist"))
+    u = pa.record_batch([pa.UnionArray.from_sparse(pa.array([0, 1], pa.int8()), [pa.array([1, 2]), pa.array(["a", "b"])])], names=["u"])
+    q = str(tmp_path / "union.arrow")
+    write_file(q, u.schema, [u])
+    with pytest.raises(rdf.UnsupportedType):
+        rdf.IpcFile(q)
+    empty = str(tmp_path / "empty.arrow")
+    write_file(empty, t.schema, [])
+    with rdf.IpcFile(empty) as f:
+        assert f.num_batches == 0 and f.num_rows == 0 and f.schema == [("x", rdf.F64, True)]
+
+
+def host_columns(rdf, rng, lens, sliced):
+    cols = {}
+    for k, (name, _) in enumerate(NUMERIC):
+        npdt = rdf.NP_DTYPES[getattr(rdf, name.upper())]
+        chunks = []
+        for j, n in enumerate(lens):
+            pad = (3 + 5 * j + k) % 19 if sliced else 0
+            v = (rng.normal(0, 100, n + pad + 2) if np.dtype(npdt).kind == "f" else rng.integers(0, 100, n + pad + 2)).astype(npdt)
+            mask = (rng.random(n + pad + 2) > 0.25) if (k + j) % 3 else None
+            a = rdf.PrimitiveArray.from_numpy(v, mask)
+            a.null_count = -1 if mask is not None else 0
+            chunks.append(a.slice(pad, n))
+        cols[name] = chunks
+    bools = []
+    for j, n in enumerate(lens):
+        pad = (2 + 3 * j) % 11 if sliced else 0
+        bools.append(rdf.BooleanArray.from_numpy(rng.random(n + pad) > 0.4, (rng.random(n + pad) > 0.2) if j % 2 else None).slice(pad, n))
+    cols["flag"] = bools
+    return cols
+
+
+def check_file_against_host(rdf, path, cols, lens):
+    with pa.ipc.open_file(path) as r:   # runs pyarrow's metadata verifier
+        assert r.num_record_batches == len(lens)
+        assert r.schema.names == list(cols)
+        for bi in range(len(lens)):
+            b = r.get_batch(bi)
+            b.validate(full=True)
+            assert b.num_rows == lens[bi]
+            for name, chunks in cols.items():
+                check_view_against_pyarrow(chunks[bi], b.column(name), f"written batch {bi} column {name}")
+    with rdf.IpcFile(path) as f:        # and the library reads its own files
+        assert f.num_batches == len(lens) and [s[0] for s in f.schema] == list(cols)
+        for bi in range(len(lens)):
+            for name, chunks in cols.items():
+                got, want = f.view(bi, name), chunks[bi]
+                assert np.array_equal(got.valid_mask(), want.valid_mask())
+                if name == "flag":
+                    assert np.array_equal(got.value_bits()[want.valid_mask()], want.value_bits()[want.valid_mask()])
+                else:
+                    assert np.array_equal(got.value_slice()[want.valid_mask()], want.value_slice()[want.valid_mask()])
+
+
+@pytest.mark.parametrize("sliced", [False, True])
+def test_writer_is_read_by_pyarrow(rdf, tmp_path, sliced):
+    rng = np.random.default_rng(3 + sliced)
+    lens = [5, 0, 64, 1001, 4096]
+    cols = host_columns(rdf, rng, lens, sliced)
+    path = str(tmp_path / "out.arrow")
+    rdf.write_ipc_host(path, cols)
+    check_file_against_host(rdf, path, cols, lens)
+    # the body of every buffer starts on a 64-byte file offset (what the device upload likes)
+    with rdf.IpcFile(path) as f:
+        base = np.frombuffer(open(path, "rb").read(16), np.uint8)  # noqa: F841 (keeps the file in the page cache)
+        v = f.view(3, "f64")
+        assert v.values.ctypes.data % 64 == 0
+    rdf.write_ipc_host(path, {"only": []})   # zero batches: schema + footer only
+    with pa.ipc.open_file(path) as r:
+        assert r.num_record_batches == 0 and r.schema.names == ["only"]
+    with pytest.raises(rdf.ComputeError):
+        rdf.write_ipc_host(path, {"a": cols["i8"], "b": [c.slice(0, max(c.length - 1, 0)) for c in cols["i16"]]})
+    with pytest.raises(rdf.ArrowError):
+        rdf.write_ipc_host(str(tmp_path / "no" / "such" / "dir.arrow"), {"a": cols["i8"]})
+
+
+# ---- device round trips -----------------------------------------------------------------------------------------
+
+@pytest.mark.gpu
+def test_file_to_device_and_back(rdf, ctx, oracle, tmp_path):
+    """from_arrow -> compute on the device -> to_arrow, checked by pyarrow on both ends."""
+    rng = np.random.default_rng(12)
+    lens = [0, 1, 2047, 2049, 70_001, 300_000]
+    schema, batches = mixed_batches(rng, lens, null_frac=0.15)
+    src = str(tmp_path / "in.arrow")
+    write_file(src, schema, batches)
+    with rdf.IpcFile(src) as f:
+        cols = f.read()                                    # every numeric/boolean column
+        assert set(cols) == {n for n, _ in NUMERIC} | {"b", "b2", "tail"}
+        for name, col in cols.items():                     # device copy == file contents
+            for bi, g in enumerate(col.download()):
+                check_view_against_pyarrow(g, batches[bi].column(name), f"device copy batch {bi} column {name}")
+        a, t = cols["f64"], cols["tail"]
+        s = a.add(t)
+        kept = s.filter(cols["b"])
+        h = rdf.eval_expr([a, t], [(rdf.native.MUL, 0, 1), ("sin", 2)])
+        with pytest.raises(rdf.UnsupportedType):
+            f.read(["s"])
+        lazy = f.read(["i32", "u8"], asynchronous=True)
+        assert lazy["i32"].count() == sum(len(b.column("i32")) - b.column("i32").null_count for b in batches)
+    out = str(tmp_path / "out.arrow")
+    rdf.write_ipc(out, {"f64": a, "tail": t, "sum": s, "h": h, "b": cols["b"], "i8": cols["i8"]})
+    with pa.ipc.open_file(out) as r:
+        assert r.num_record_batches == len(lens)
+        for bi in range(len(lens)):
+            b = r.get_batch(bi)
+            b.validate(full=True)
+            src_b = batches[bi]
+            for name in ("f64", "tail", "b", "i8"):
+                assert b.column(name).equals(src_b.column(name)), f"batch {bi} column {name} changed on the round trip"
+            want = pa.compute.add(src_b.column("f64"), src_b.column("tail"))
+            assert b.column("sum").equals(want), f"batch {bi}: device a+b differs from pyarrow's"
+            got_h, ref_h = b.column("h"), pa.compute.sin(pa.compute.multiply(src_b.column("f64"), src_b.column("tail")))
+            assert got_h.is_valid().equals(ref_h.is_valid())
+            gv, rv = got_h.drop_null().to_numpy(zero_copy_only=False), ref_h.drop_null().to_numpy(zero_copy_only=False)
+            assert np.allclose(gv, rv, rtol=0, atol=4 * 2.0 ** -53)
+    # filter output has data-dependent chunk lengths: written as its own file
+    out2 = str(tmp_path / "kept.arrow")
+    rdf.write_ipc(out2, {"kept": kept})
+    with pa.ipc.open_file(out2) as r:
+        for bi in range(len(lens)):
+            sb = batches[bi]
+            want = pa.compute.add(sb.column("f64"), sb.column("tail")).filter(sb.column("b"), null_selection_behavior="drop")
+            assert r.get_batch(bi).column("kept").equals(want)
+    with pytest.raises(rdf.ComputeError):
+        rdf.write_ipc(out2, {"a": a, "kept": kept})      # chunk lengths differ: not a set of RecordBatches
+
+
+@pytest.mark.gpu
+def test_large_file_read_1e7(rdf, ctx, tmp_path):
+    """2 x Float64 x 1e7 rows in 10 batches: file -> device add + fused sum equals numpy on the file's data."""
+    rng = np.random.default_rng(2)
+    n, nb = 1_000_000, 10
+    batches = [pa.record_batch([pa.array(rng.normal(0, 10, n)), pa.array(rng.normal(0, 10, n), mask=rng.random(n) < 0.1)], names=["a", "b"])
+               for _ in range(nb)]
+    path = str(tmp_path / "big.arrow")
+    write_file(path, batches[0].schema, batches)
+    with rdf.IpcFile(path) as f:
+        cols = f.read(["a", "b"])
+    c, agg = cols["a"].binary_agg(rdf.native.ADD, cols["b"])
+    want = [pa.compute.add(b.column("a"), b.column("b")) for b in batches]
+    assert agg["count"] == sum(len(w) - w.null_count for w in want)
+    tot = sum(float(np.sum(w.drop_null().to_numpy(zero_copy_only=False).astype(np.longdouble))) for w in want)
+    assert abs(agg["sum"] - tot) <= 1e-6
+    for bi, g in enumerate(c.download()):
+        check_view_against_pyarrow(g, want[bi], f"a+b batch {bi}")
