@@ -457,30 +457,6 @@ size_t fb_schema(FbOut& o, int n_cols, const char* const* names, const int32_t* 
 
 struct Block { int64_t offset; int32_t meta_len; int32_t pad; int64_t body_len; };
 
-bool write_all(int fd, const void* p, size_t n) {
-    const uint8_t* b = (const uint8_t*)p;
-    while (n) {
-        const ssize_t w = write(fd, b, n > (1u << 30) ? (1u << 30) : n);
-        if (w < 0) { if (errno == EINTR) continue; return false; }
-        b += w; n -= (size_t)w;
-    }
-    return true;
-}
-
-// Encapsulated message: continuation marker, metadata size, flatbuffer, zero padding so that the body starts on a
-// 64-byte file offset.  Returns the Block's metaDataLength.
-bool write_message(int fd, int64_t* pos, const FbOut& fb, int32_t* meta_len) {
-    const int64_t after = (*pos + 8 + (int64_t)fb.b.size() + 63) / 64 * 64;
-    const int32_t mlen = (int32_t)(after - *pos - 8);
-    const int32_t marker = -1;
-    std::vector<uint8_t> pad((size_t)mlen - fb.b.size(), 0);
-    if (!write_all(fd, &marker, 4) || !write_all(fd, &mlen, 4) || !write_all(fd, fb.b.data(), fb.b.size()) || !write_all(fd, pad.data(), pad.size()))
-        return false;
-    *meta_len = mlen + 8;
-    *pos = after;
-    return true;
-}
-
 // Bits [bit0, bit0+n) of src, re-based to bit 0 of dst (dst zero padded to whole bytes).
 void copy_bits(const uint8_t* src, int64_t bit0, int64_t n, uint8_t* dst) {
     const int64_t nbytes = (n + 7) / 8;
@@ -499,27 +475,41 @@ void copy_bits(const uint8_t* src, int64_t bit0, int64_t n, uint8_t* dst) {
     if (n & 7) dst[nbytes - 1] &= (uint8_t)((1u << (n & 7)) - 1u);
 }
 
-}  // namespace
+// What one column contributes to one RecordBatch, and where its buffers land in the file.
+struct ChunkSpec {
+    int64_t rows = 0, nulls = 0;
+    bool has_validity = false;            // a validity buffer is written (always when nulls > 0)
+    int64_t validity_pos = 0, values_pos = 0;   // absolute file offsets (filled by plan_file)
+    int64_t validity_len = 0, values_len = 0;
+};
 
-#pragma GCC visibility push(default)
-extern "C" {
+// The whole file is laid out before a byte of data moves: metadata is small and known up front, so the file can be
+// sized, mapped, and the body buffers produced IN PLACE (memcpy from host views, or device->host copies that land
+// directly in the page cache).  Bodies start on 64-byte file offsets; padding stays zero (ftruncate).
+struct FilePlan {
+    struct Piece { int64_t pos; std::vector<uint8_t> bytes; };
+    std::vector<Piece> meta;   // magic, framed messages, EOS, footer, trailer
+    int64_t size = 0;
+};
 
-int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches,
-                       const bdf_view* const* cols) {
-    if (!path || !names || !dtypes || n_cols <= 0 || n_batches < 0 || (n_batches && !cols)) return ipc_fail(BDF_INVALID, "null argument");
-    for (int c = 0; c < n_cols; c++) {
-        if (!names[c] || !((dtypes[c] >= 0 && dtypes[c] <= 9) || dtypes[c] == BDF_BOOL)) return ipc_fail(BDF_INVALID, "column %d: bad name or dtype", c);
-        for (int64_t b = 0; b < n_batches; b++)
-            if (cols[c][b].len != cols[0][b].len || cols[c][b].len < 0 || cols[c][b].offset < 0)
-                return ipc_fail(BDF_LENGTH_MISMATCH, "batch %lld: column '%s' has %lld rows, column '%s' has %lld", (long long)b, names[c],
-                                (long long)cols[c][b].len, names[0], (long long)cols[0][b].len);
-    }
-    const int fd = open(path, O_WRONLY | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
-    if (fd < 0) return ipc_fail(BDF_INVALID, "cannot create %s: %s", path, strerror(errno));
-    bool ok = true;
+void frame_message(FilePlan* plan, int64_t* pos, const FbOut& fb, int32_t* meta_len) {
+    // continuation marker, metadata size, flatbuffer, zero padding up to the next 64-byte file offset
+    const int64_t after = (*pos + 8 + (int64_t)fb.b.size() + 63) / 64 * 64;
+    const int32_t mlen = (int32_t)(after - *pos - 8);
+    FilePlan::Piece pc{*pos, {}};
+    const int32_t marker = -1;
+    pc.bytes.insert(pc.bytes.end(), (const uint8_t*)&marker, (const uint8_t*)&marker + 4);
+    pc.bytes.insert(pc.bytes.end(), (const uint8_t*)&mlen, (const uint8_t*)&mlen + 4);
+    pc.bytes.insert(pc.bytes.end(), fb.b.begin(), fb.b.end());
+    plan->meta.push_back(std::move(pc));
+    *meta_len = mlen + 8;
+    *pos = after;
+}
+
+void plan_file(int n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches, std::vector<std::vector<ChunkSpec>>& spec,
+               FilePlan* plan) {
     int64_t pos = 0;
-    static const uint8_t zeros[64] = {0};
-    ok = write_all(fd, "ARROW1\0\0", 8);
+    plan->meta.push_back({0, {'A', 'R', 'R', 'O', 'W', '1', 0, 0}});
     pos = 8;
     {   // schema message
         FbOut fb;
@@ -530,32 +520,27 @@ int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* name
         fb.link(refs[0], fb_schema(fb, n_cols, names, dtypes));
         fb.pad_to(8);
         int32_t ml;
-        ok = ok && write_message(fd, &pos, fb, &ml);
+        frame_message(plan, &pos, fb, &ml);
     }
     std::vector<Block> blocks;
-    std::vector<uint8_t> tmp;
-    for (int64_t b = 0; b < n_batches && ok; b++) {
-        const int64_t rows = cols[0][b].len;
+    for (int64_t b = 0; b < n_batches; b++) {
+        const int64_t rows = spec[0][b].rows;
         struct Node { int64_t len, nulls; };
         struct Buf { int64_t off, len; };
         std::vector<Node> nodes((size_t)n_cols);
         std::vector<Buf> bufs(2 * (size_t)n_cols);
         int64_t body = 0;
         for (int c = 0; c < n_cols; c++) {
-            const bdf_view& v = cols[c][b];
-            int64_t nulls = v.validity ? v.null_count : 0;
-            if (v.validity && nulls < 0) {
-                nulls = 0;
-                for (int64_t i = 0; i < rows; i++) nulls += !((v.validity[(v.offset + i) >> 3] >> ((v.offset + i) & 7)) & 1);
-            }
-            nodes[c] = {rows, nulls};
-            const int64_t vbytes = nulls > 0 ? (rows + 7) / 8 : 0;
-            int64_t dbytes = 0;
-            dtype_bytes(dtypes[c], rows, &dbytes);
-            bufs[2 * c] = {body, vbytes};
-            body += (vbytes + 63) / 64 * 64;
-            bufs[2 * c + 1] = {body, dbytes};
-            body += (dbytes + 63) / 64 * 64;
+            ChunkSpec& cs = spec[c][b];
+            nodes[c] = {rows, cs.nulls};
+            cs.validity_len = cs.has_validity ? (rows + 7) / 8 : 0;
+            dtype_bytes(dtypes[c], rows, &cs.values_len);
+            bufs[2 * c] = {body, cs.validity_len};
+            cs.validity_pos = body;                      // relative for now
+            body += (cs.validity_len + 63) / 64 * 64;
+            bufs[2 * c + 1] = {body, cs.values_len};
+            cs.values_pos = body;
+            body += (cs.values_len + 63) / 64 * 64;
         }
         FbOut fb;
         fb.put<uint32_t>(0);
@@ -568,94 +553,147 @@ int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* name
         fb.link(rr[1], fb_struct_vec(fb, bufs.data(), 2 * (uint32_t)n_cols, 16));
         fb.pad_to(8);
         Block blk{pos, 0, 0, body};
-        ok = ok && write_message(fd, &pos, fb, &blk.meta_len);
-        for (int c = 0; c < n_cols && ok; c++) {
-            const bdf_view& v = cols[c][b];
-            const int64_t vbytes = bufs[2 * c].len, dbytes = bufs[2 * c + 1].len;
-            if (vbytes) {
-                tmp.assign((size_t)vbytes, 0);
-                copy_bits(v.validity, v.offset, rows, tmp.data());
-                ok = ok && write_all(fd, tmp.data(), (size_t)vbytes) && write_all(fd, zeros, (size_t)((64 - vbytes % 64) % 64));
-            }
-            if (dbytes) {
-                if (dtypes[c] == BDF_BOOL) {
-                    tmp.assign((size_t)dbytes, 0);
-                    copy_bits((const uint8_t*)v.values, v.offset, rows, tmp.data());
-                    ok = ok && write_all(fd, tmp.data(), (size_t)dbytes);
-                } else {
-                    ok = ok && write_all(fd, (const uint8_t*)v.values + v.offset * (dbytes / rows), (size_t)dbytes);
-                }
-                ok = ok && write_all(fd, zeros, (size_t)((64 - dbytes % 64) % 64));
-            }
-        }
+        frame_message(plan, &pos, fb, &blk.meta_len);
+        for (int c = 0; c < n_cols; c++) { spec[c][b].validity_pos += pos; spec[c][b].values_pos += pos; }
         pos += body;
         blocks.push_back(blk);
     }
-    if (ok) {   // end-of-stream marker, footer, footer size, magic
-        const int32_t eos[2] = {-1, 0};
-        ok = write_all(fd, eos, 8);
-        FbOut fb;
-        fb.put<uint32_t>(0);
-        std::vector<size_t> fr;
-        // Footer: version(0) schema(1) dictionaries(2) recordBatches(3)
-        const size_t footer = fb_table(fb, {{0, 2, 4}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}}, &fr);
-        fb.link(0, footer);
-        fb.link(fr[0], fb_schema(fb, n_cols, names, dtypes));
-        fb.link(fr[1], fb_struct_vec(fb, nullptr, 0, 24));
-        fb.link(fr[2], fb_struct_vec(fb, blocks.data(), (uint32_t)blocks.size(), 24));
-        fb.pad_to(8);
-        const int32_t flen = (int32_t)fb.b.size();
-        ok = ok && write_all(fd, fb.b.data(), fb.b.size()) && write_all(fd, &flen, 4) && write_all(fd, "ARROW1", 6);
+    // end-of-stream marker, footer, footer size, magic
+    FbOut fb;
+    fb.put<uint32_t>(0);
+    std::vector<size_t> fr;
+    const size_t footer = fb_table(fb, {{0, 2, 4}, {1, 0, 0}, {2, 0, 0}, {3, 0, 0}}, &fr);   // version, schema, dictionaries, recordBatches
+    fb.link(0, footer);
+    fb.link(fr[0], fb_schema(fb, n_cols, names, dtypes));
+    fb.link(fr[1], fb_struct_vec(fb, nullptr, 0, 24));
+    fb.link(fr[2], fb_struct_vec(fb, blocks.data(), (uint32_t)blocks.size(), 24));
+    fb.pad_to(8);
+    FilePlan::Piece tail{pos, {}};
+    const int32_t eos[2] = {-1, 0};
+    const int32_t flen = (int32_t)fb.b.size();
+    tail.bytes.insert(tail.bytes.end(), (const uint8_t*)eos, (const uint8_t*)eos + 8);
+    tail.bytes.insert(tail.bytes.end(), fb.b.begin(), fb.b.end());
+    tail.bytes.insert(tail.bytes.end(), (const uint8_t*)&flen, (const uint8_t*)&flen + 4);
+    tail.bytes.insert(tail.bytes.end(), {'A', 'R', 'R', 'O', 'W', '1'});
+    plan->size = pos + (int64_t)tail.bytes.size();
+    plan->meta.push_back(std::move(tail));
+}
+
+// A new file of the planned size, mapped read/write, metadata already in place.
+struct OutFile {
+    int fd = -1;
+    uint8_t* map = nullptr;
+    size_t size = 0;
+    int open_planned(const char* path, const FilePlan& plan) {
+        fd = open(path, O_RDWR | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+        if (fd < 0) return ipc_fail(BDF_INVALID, "cannot create %s: %s", path, strerror(errno));
+        size = (size_t)plan.size;
+        if (ftruncate(fd, (off_t)size) != 0) return ipc_fail(BDF_INVALID, "cannot size %s to %zu bytes: %s", path, size, strerror(errno));
+        void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+        if (m == MAP_FAILED) return ipc_fail(BDF_INVALID, "cannot map %s: %s", path, strerror(errno));
+        map = (uint8_t*)m;
+        for (const FilePlan::Piece& pc : plan.meta) memcpy(map + pc.pos, pc.bytes.data(), pc.bytes.size());
+        return BDF_OK;
     }
-    const int err = errno;
-    if (close(fd) != 0) ok = false;
-    if (!ok) return ipc_fail(BDF_INVALID, "writing %s failed: %s", path, strerror(err ? err : errno));
-    return BDF_OK;
+    int finish(const char* path) {
+        int st = BDF_OK;
+        if (map && munmap(map, size) != 0) st = ipc_fail(BDF_INVALID, "unmapping %s failed: %s", path, strerror(errno));
+        map = nullptr;
+        if (fd >= 0 && close(fd) != 0 && st == BDF_OK) st = ipc_fail(BDF_INVALID, "closing %s failed: %s", path, strerror(errno));
+        fd = -1;
+        return st;
+    }
+    ~OutFile() { if (map) munmap(map, size); if (fd >= 0) close(fd); }
+};
+
+}  // namespace
+
+#pragma GCC visibility push(default)
+extern "C" {
+
+int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches,
+                       const bdf_view* const* cols) {
+    if (!path || !names || !dtypes || n_cols <= 0 || n_batches < 0 || (n_batches && !cols)) return ipc_fail(BDF_INVALID, "null argument");
+    std::vector<std::vector<ChunkSpec>> spec((size_t)n_cols, std::vector<ChunkSpec>((size_t)n_batches));
+    for (int c = 0; c < n_cols; c++) {
+        if (!names[c] || !((dtypes[c] >= 0 && dtypes[c] <= 9) || dtypes[c] == BDF_BOOL)) return ipc_fail(BDF_INVALID, "column %d: bad name or dtype", c);
+        for (int64_t b = 0; b < n_batches; b++) {
+            const bdf_view& v = cols[c][b];
+            if (v.len != cols[0][b].len || v.len < 0 || v.offset < 0)
+                return ipc_fail(BDF_LENGTH_MISMATCH, "batch %lld: column '%s' has %lld rows, column '%s' has %lld", (long long)b, names[c],
+                                (long long)v.len, names[0], (long long)cols[0][b].len);
+            int64_t nulls = v.validity ? v.null_count : 0;
+            if (v.validity && nulls < 0) {
+                nulls = 0;
+                for (int64_t i = 0; i < v.len; i++) nulls += !((v.validity[(v.offset + i) >> 3] >> ((v.offset + i) & 7)) & 1);
+            }
+            spec[c][b].rows = v.len; spec[c][b].nulls = nulls; spec[c][b].has_validity = nulls > 0;
+        }
+    }
+    FilePlan plan;
+    plan_file(n_cols, names, dtypes, n_batches, spec, &plan);
+    OutFile of;
+    const int st = of.open_planned(path, plan);
+    if (st != BDF_OK) return st;
+    static const int w[10] = {1, 2, 4, 8, 1, 2, 4, 8, 4, 8};
+    for (int c = 0; c < n_cols; c++)
+        for (int64_t b = 0; b < n_batches; b++) {
+            const bdf_view& v = cols[c][b];
+            const ChunkSpec& cs = spec[c][b];
+            if (cs.validity_len) copy_bits(v.validity, v.offset, cs.rows, of.map + cs.validity_pos);
+            if (!cs.values_len) continue;
+            if (dtypes[c] == BDF_BOOL) copy_bits((const uint8_t*)v.values, v.offset, cs.rows, of.map + cs.values_pos);
+            else memcpy(of.map + cs.values_pos, (const uint8_t*)v.values + v.offset * w[dtypes[c]], (size_t)cs.values_len);
+        }
+    return of.finish(path);
 }
 
 int bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* const* names, const bdf_col* const* cols) {
     if (!ctx || !path || !names || !cols || n_cols <= 0) return ipc_fail(BDF_INVALID, "null argument");
     std::vector<int32_t> dtypes((size_t)n_cols);
-    std::vector<std::vector<bdf_out>> outs((size_t)n_cols);
-    std::vector<std::vector<bdf_view>> views((size_t)n_cols);
-    std::vector<const bdf_view*> vp((size_t)n_cols);
-    std::vector<void*> allocs;
+    std::vector<std::vector<ChunkSpec>> spec((size_t)n_cols);
     int64_t n_batches = -1;
-    int st = BDF_OK;
-    for (int c = 0; c < n_cols && st == BDF_OK; c++) {
+    for (int c = 0; c < n_cols; c++) {
         int64_t nch = 0, total = 0;
-        if (!cols[c]) { st = ipc_fail(BDF_INVALID, "null column"); break; }
-        st = bdf_col_describe(cols[c], &dtypes[c], &nch, &total);
-        if (st != BDF_OK) break;
+        if (!cols[c] || !names[c]) return ipc_fail(BDF_INVALID, "null column or name");
+        int st = bdf_col_describe(cols[c], &dtypes[c], &nch, &total);
+        if (st != BDF_OK) return st;
         if (n_batches < 0) n_batches = nch;
-        if (nch != n_batches) { st = ipc_fail(BDF_LENGTH_MISMATCH, "columns have different numbers of chunks (%lld, %lld)", (long long)nch, (long long)n_batches); break; }
-        outs[c].resize((size_t)std::max<int64_t>(nch, 1));
-        views[c].resize((size_t)std::max<int64_t>(nch, 1));
-        for (int64_t b = 0; b < nch && st == BDF_OK; b++) {
+        if (nch != n_batches) return ipc_fail(BDF_LENGTH_MISMATCH, "columns have different numbers of chunks (%lld, %lld)", (long long)nch, (long long)n_batches);
+        spec[c].resize((size_t)nch);
+        for (int64_t b = 0; b < nch; b++) {
             int64_t len = 0, nulls = 0; int32_t hv = 0;
             st = bdf_col_chunk_info(ctx, cols[c], b, &len, &nulls, &hv);
-            if (st != BDF_OK) break;
-            int64_t dbytes = 0;
-            dtype_bytes(dtypes[c], len, &dbytes);
-            void *pv = nullptr, *pm = nullptr;
-            st = bdf_host_alloc(ctx, (size_t)dbytes + 64, &pv);   // pinned: the device->host copies run at PCIe speed
-            if (st == BDF_OK) { allocs.push_back(pv); st = bdf_host_alloc(ctx, (size_t)(len + 7) / 8 + 64, &pm); }
-            if (st == BDF_OK) allocs.push_back(pm);
-            outs[c][b] = bdf_out{pv, (uint8_t*)pm, len, 0, 0};
-        }
-        vp[c] = views[c].data();
-    }
-    for (int c = 0; c < n_cols && st == BDF_OK; c++) st = bdf_download_begin(ctx, cols[c], outs[c].data());
-    for (int c = 0; c < n_cols && st == BDF_OK; c++) {
-        st = bdf_download_end(ctx, cols[c], outs[c].data());
-        for (int64_t b = 0; b < n_batches && st == BDF_OK; b++) {
-            const bdf_out& o = outs[c][b];
-            views[c][b] = bdf_view{o.values, o.has_validity ? o.validity : nullptr, o.len, 0, o.has_validity ? o.null_count : 0};
+            if (st != BDF_OK) return st;
+            if (len != spec[0][b].rows && c > 0)
+                return ipc_fail(BDF_LENGTH_MISMATCH, "chunk %lld: column '%s' has %lld rows, column '%s' has %lld", (long long)b, names[c], (long long)len,
+                                names[0], (long long)spec[0][b].rows);
+            spec[c][b].rows = len; spec[c][b].nulls = hv ? nulls : 0; spec[c][b].has_validity = hv != 0;
         }
     }
-    if (st == BDF_OK) st = bdf_ipc_write_host(path, n_cols, names, dtypes.data(), n_batches, vp.data());
-    for (void* p : allocs) bdf_host_free(ctx, p);
-    return st;
+    FilePlan plan;
+    plan_file(n_cols, names, dtypes.data(), n_batches, spec, &plan);
+    OutFile of;
+    int st = of.open_planned(path, plan);
+    if (st != BDF_OK) return st;
+    // device -> host copies land in the mapping: every column's chunks go to their final place in the file
+    std::vector<std::vector<bdf_out>> outs((size_t)n_cols);
+    for (int c = 0; c < n_cols; c++) {
+        outs[c].resize((size_t)std::max<int64_t>(n_batches, 1));
+        for (int64_t b = 0; b < n_batches; b++) {
+            const ChunkSpec& cs = spec[c][b];
+            outs[c][b] = bdf_out{of.map + cs.values_pos, cs.has_validity ? of.map + cs.validity_pos : nullptr, cs.rows, 0, 0};
+        }
+    }
+    int begun = 0;
+    for (; begun < n_cols && st == BDF_OK; begun++) st = bdf_download_begin(ctx, cols[begun], outs[begun].data());
+    if (st != BDF_OK) begun--;   // the failing column never started
+    for (int c = 0; c < begun; c++) {
+        const int s2 = bdf_download_end(ctx, cols[c], outs[c].data());
+        if (st == BDF_OK) st = s2;
+    }
+    const int s3 = of.finish(path);
+    return st != BDF_OK ? st : s3;
 }
 
 }  // extern "C"
