@@ -11,6 +11,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <memory>
 #include <mutex>
 #include <new>
 #include <deque>
@@ -110,6 +112,62 @@ struct ProfEntry {
     cudaEvent_t e0, e1;
 };
 
+// Persistent host threads for the staged copies of PAGEABLE buffers (Arrow MutableBuffers, a mapped IPC file): a copy
+// is cut into 512 KiB jobs that the workers and the calling thread pull until it is done.  (Spawning threads per 8 MiB
+// slot, the first version, stopped scaling at 4 threads because the spawn/join cost was comparable to the copy.)
+class CopyPool {
+  public:
+    explicit CopyPool(int workers) {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { work(); });
+    }
+    ~CopyPool() {
+        { std::lock_guard<std::mutex> g(m_); stop_ = true; }
+        cv_work_.notify_all();
+        for (auto& t : th_) t.join();
+    }
+    int workers() const { return (int)th_.size(); }
+    void copy(char* dst, const char* src, size_t n) {
+        constexpr size_t kJob = (size_t)512 << 10;
+        if (th_.empty() || n < 2 * kJob) { memcpy(dst, src, n); return; }
+        std::unique_lock<std::mutex> lk(m_);
+        dst_ = dst; src_ = src; n_ = n; next_ = 0; jobs_ = (n + kJob - 1) / kJob; done_ = 0;
+        lk.unlock();
+        cv_work_.notify_all();
+        lk.lock();
+        while (next_ < jobs_) {   // the caller works too
+            const size_t j = next_++;
+            lk.unlock();
+            memcpy(dst + j * kJob, src + j * kJob, std::min(kJob, n - j * kJob));
+            lk.lock();
+            done_++;
+        }
+        cv_done_.wait(lk, [this] { return done_ == jobs_; });
+        jobs_ = 0; next_ = 0; done_ = 0;
+    }
+
+  private:
+    void work() {
+        constexpr size_t kJob = (size_t)512 << 10;
+        std::unique_lock<std::mutex> lk(m_);
+        for (;;) {
+            cv_work_.wait(lk, [this] { return stop_ || next_ < jobs_; });
+            if (stop_) return;
+            const size_t j = next_++;
+            char* d = dst_; const char* s = src_; const size_t n = n_;
+            lk.unlock();
+            memcpy(d + j * kJob, s + j * kJob, std::min(kJob, n - j * kJob));
+            lk.lock();
+            if (++done_ == jobs_) cv_done_.notify_all();
+        }
+    }
+    std::mutex m_;
+    std::condition_variable cv_work_, cv_done_;
+    std::vector<std::thread> th_;
+    char* dst_ = nullptr; const char* src_ = nullptr;
+    size_t n_ = 0, next_ = 0, jobs_ = 0, done_ = 0;
+    bool stop_ = false;
+};
+
 struct bdf_ctx {
     int device = 0;
     int sm_count = 0, cc_major = 0, cc_minor = 0;
@@ -141,7 +199,8 @@ struct bdf_ctx {
     struct StageSlot { char* p = nullptr; cudaEvent_t ev = nullptr; bool busy = false; };
     std::vector<StageSlot> stage;
     int stage_next = 0;
-    int copy_threads = 4;
+    int copy_threads = 8;
+    std::unique_ptr<CopyPool> pool;
     cudaEvent_t ev_tmp = nullptr, ev_t0 = nullptr, ev_t1 = nullptr;
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
@@ -437,18 +496,9 @@ static int ensure_stage(bdf_ctx* c) {
     }
     const char* t = getenv("BDF_COPY_THREADS");
     const int hw = (int)std::thread::hardware_concurrency();
-    c->copy_threads = t && atoi(t) > 0 ? atoi(t) : std::max(1, std::min(4, hw > 0 ? hw : 4));  // measured best on the B200 host (1/4/8/16 threads)
+    c->copy_threads = t && atoi(t) > 0 ? atoi(t) : std::max(1, std::min(8, hw > 0 ? hw : 8));
+    c->pool.reset(new CopyPool(c->copy_threads - 1));   // the calling thread is the last worker
     return BDF_OK;
-}
-
-static void parallel_memcpy(char* dst, const char* src, size_t n, int threads) {
-    const size_t part = ((n / (size_t)threads) + 4095) & ~(size_t)4095;
-    if (threads <= 1 || part == 0 || n < ((size_t)256 << 10)) { memcpy(dst, src, n); return; }
-    std::vector<std::thread> pool;
-    for (size_t off = part; off < n; off += part)
-        pool.emplace_back([=] { memcpy(dst + off, src + off, std::min(part, n - off)); });
-    memcpy(dst, src, std::min(part, n));
-    for (auto& th : pool) th.join();
 }
 
 // host -> device on the h2d stream; pageable sources are staged through pinned slots (the source has been read
@@ -460,7 +510,7 @@ static cudaError_t h2d_copy(bdf_ctx* c, void* dst, const void* src, size_t bytes
         const size_t n = std::min(kStageBytes, bytes - off);
         bdf_ctx::StageSlot& sl = c->stage[c->stage_next++ % kStageSlots];
         if (sl.busy) { cudaError_t e = cudaEventSynchronize(sl.ev); if (e != cudaSuccess) return e; }
-        parallel_memcpy(sl.p, (const char*)src + off, n, c->copy_threads);
+        c->pool->copy(sl.p, (const char*)src + off, n);
         cudaError_t e = cudaMemcpyAsync((char*)dst + off, sl.p, n, cudaMemcpyHostToDevice, c->s_h2d);
         if (e == cudaSuccess) e = cudaEventRecord(sl.ev, c->s_h2d);
         if (e != cudaSuccess) return e;
@@ -479,7 +529,7 @@ static cudaError_t d2h_staged(bdf_ctx* c, const std::vector<bdf_col::StagedCopy>
         Pending p = pending.front();
         pending.pop_front();
         cudaError_t e = cudaEventSynchronize(p.sl->ev);
-        if (e == cudaSuccess) parallel_memcpy(p.dst, p.sl->p, p.n, c->copy_threads);
+        if (e == cudaSuccess) c->pool->copy(p.dst, p.sl->p, p.n);
         p.sl->busy = false;
         return e;
     };
@@ -1344,6 +1394,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_fin) cudaStreamSynchronize(c->s_fin);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
+    c->pool.reset();
     for (auto& sl : c->stage) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
     for (auto& b : c->part) { if (b.p) cudaFree(b.p); if (b.done) cudaEventDestroy(b.done); }
     if (c->ring) cudaFreeHost(c->ring);
