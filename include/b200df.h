@@ -219,6 +219,9 @@ int  bdf_ipc_column(const bdf_ipc* file, int32_t col, const char** name, int32_t
 int  bdf_ipc_batch_rows(const bdf_ipc* file, int64_t batch, int64_t* rows);
 int  bdf_ipc_view(const bdf_ipc* file, int64_t batch, int32_t col, bdf_view* out);
 int  bdf_ipc_read(bdf_ctx* ctx, const bdf_ipc* file, int32_t n_cols, const int32_t* cols, int flags, bdf_col** out /* n_cols */);
+/* A subset of the RecordBatches, in the given order (multi-GPU: rank r of N reads batches r, r+N, ... -- SURVEY 8(e)). */
+int  bdf_ipc_read_batches(bdf_ctx* ctx, const bdf_ipc* file, int32_t n_cols, const int32_t* cols, int64_t n_batches,
+                          const int64_t* batches, int flags, bdf_col** out /* n_cols */);
 int  bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* names, const int32_t* dtypes, int64_t n_batches,
                         const bdf_view* const* cols /* [n_cols][n_batches] */);
 int  bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* const* names, const bdf_col* const* cols);

@@ -25,6 +25,13 @@ pub struct BdfOut {
 }
 
 pub enum BdfCtx {}
+pub enum BdfCol {}   // a column resident in HBM (one chunk per RecordBatch)
+pub enum BdfIpc {}   // a mapped Arrow IPC file
+
+#[repr(C)]
+pub struct BdfExprNode { pub op: i32, pub a: i32, pub b: i32 }   // op: bdf_binop, or BDF_EXPR_UNARY + bdf_unop
+pub const BDF_EXPR_UNARY: i32 = 100;
+pub const BDF_ASYNC: c_int = 1;
 
 pub const BDF_OK: c_int = 0;
 pub const BDF_LENGTH_MISMATCH: c_int = 1;
@@ -43,6 +50,25 @@ extern "C" {
     pub fn bdf_aggregate(ctx: *mut BdfCtx, op: c_int, dtype: c_int, n: i64, input: *const BdfView, out_scalar: *mut c_void,
                          is_some: *mut i32) -> c_int;
     pub fn bdf_avg(ctx: *mut BdfCtx, dtype: c_int, n: i64, input: *const BdfView, out: *mut f64, is_some: *mut i32) -> c_int;
+    // device-resident columns (the lazy evaluator keeps a frame's numeric columns in HBM between Calculations)
+    pub fn bdf_upload_many(ctx: *mut BdfCtx, n_cols: i64, dtypes: *const i32, n_chunks: *const i64, input: *const *const BdfView, flags: c_int,
+                           out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_binary_dev(ctx: *mut BdfCtx, op: c_int, left: *const BdfCol, right: *const BdfCol, out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_unary_dev(ctx: *mut BdfCtx, op: c_int, input: *const BdfCol, out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_cast_dev(ctx: *mut BdfCtx, to: c_int, input: *const BdfCol, out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_eval_expr_dev(ctx: *mut BdfCtx, n_inputs: i32, inputs: *const *const BdfCol, n_nodes: i32, nodes: *const BdfExprNode,
+                             out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_download(ctx: *mut BdfCtx, col: *const BdfCol, out: *mut BdfOut) -> c_int;
+    pub fn bdf_col_free(ctx: *mut BdfCtx, col: *mut BdfCol);
+    // Arrow IPC files (DataFrame::from_arrow / to_arrow)
+    pub fn bdf_ipc_open(path: *const c_char, out: *mut *mut BdfIpc) -> c_int;
+    pub fn bdf_ipc_close(file: *mut BdfIpc);
+    pub fn bdf_ipc_describe(file: *const BdfIpc, n_columns: *mut i32, n_batches: *mut i64, n_rows: *mut i64) -> c_int;
+    pub fn bdf_ipc_column(file: *const BdfIpc, col: i32, name: *mut *const c_char, dtype: *mut i32, nullable: *mut i32) -> c_int;
+    pub fn bdf_ipc_read(ctx: *mut BdfCtx, file: *const BdfIpc, n_cols: i32, cols: *const i32, flags: c_int, out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_ipc_read_batches(ctx: *mut BdfCtx, file: *const BdfIpc, n_cols: i32, cols: *const i32, n_batches: i64, batches: *const i64,
+                                flags: c_int, out: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_ipc_write(ctx: *mut BdfCtx, path: *const c_char, n_cols: i32, names: *const *const c_char, cols: *const *const BdfCol) -> c_int;
 }
 
 /// Process-wide context: one GPU per process, LOCAL_RANK selects the device under a multi-process launcher.

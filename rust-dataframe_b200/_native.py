@@ -142,6 +142,7 @@ def lib() -> C.CDLL:
         "bdf_ipc_batch_rows": ([vp, i64, P(i64)], C.c_int),
         "bdf_ipc_view": ([vp, i64, i32, P(View)], C.c_int),
         "bdf_ipc_read": ([vp, vp, i32, P(i32), C.c_int, P(vp)], C.c_int),
+        "bdf_ipc_read_batches": ([vp, vp, i32, P(i32), i64, P(i64), C.c_int, P(vp)], C.c_int),
         "bdf_ipc_write_host": ([C.c_char_p, i32, P(C.c_char_p), P(i32), i64, P(P(View))], C.c_int),
         "bdf_ipc_write": ([vp, C.c_char_p, i32, P(C.c_char_p), P(vp)], C.c_int),
         "bdf_generate": ([vp, C.c_int, C.c_int, C.c_double, C.c_double, u64, u64, i64, P(i64), i64, C.c_uint32, P(vp)],
@@ -165,7 +166,7 @@ EXPORTED_SYMBOLS = [
     "bdf_aggregate_all_dev", "bdf_avg_dev", "bdf_eval_expr_dev", "bdf_eval_expr_agg_dev", "bdf_eval_expr_agg_dev_async", "bdf_compare_dev", "bdf_boolean_dev", "bdf_filter_dev", "bdf_download", "bdf_download_begin", "bdf_download_end",
     "bdf_binary_agg_dev", "bdf_binary_agg_dev_async", "bdf_aggregate_all_dev_async", "bdf_future_wait", "bdf_col_free", "bdf_profile_enable", "bdf_profile_read",
     "bdf_launch_count", "bdf_timer_start", "bdf_timer_stop", "bdf_flush_l2", "bdf_generate",
-    "bdf_ipc_open", "bdf_ipc_close", "bdf_ipc_describe", "bdf_ipc_column", "bdf_ipc_batch_rows", "bdf_ipc_view", "bdf_ipc_read",
+    "bdf_ipc_open", "bdf_ipc_close", "bdf_ipc_describe", "bdf_ipc_column", "bdf_ipc_batch_rows", "bdf_ipc_view", "bdf_ipc_read", "bdf_ipc_read_batches",
     "bdf_ipc_write_host", "bdf_ipc_write",
 ]
 

@@ -337,24 +337,31 @@ int bdf_ipc_view(const bdf_ipc* f, int64_t batch, int32_t col, bdf_view* out) {
     return BDF_OK;
 }
 
-int bdf_ipc_read(bdf_ctx* ctx, const bdf_ipc* f, int32_t n_cols, const int32_t* cols, int flags, bdf_col** out) {
-    if (!ctx || !f || !cols || !out || n_cols <= 0) return ipc_fail(BDF_INVALID, "null argument");
-    const int64_t nb = (int64_t)f->batches.size();
+int bdf_ipc_read_batches(bdf_ctx* ctx, const bdf_ipc* f, int32_t n_cols, const int32_t* cols, int64_t n_batches, const int64_t* batches, int flags,
+                         bdf_col** out) {
+    if (!ctx || !f || !cols || !out || n_cols <= 0 || n_batches < 0 || (n_batches && !batches)) return ipc_fail(BDF_INVALID, "null argument");
     std::vector<std::vector<bdf_view>> views((size_t)n_cols);
     std::vector<const bdf_view*> vp((size_t)n_cols);
     std::vector<int32_t> dtypes((size_t)n_cols);
-    std::vector<int64_t> nch((size_t)n_cols, nb);
+    std::vector<int64_t> nch((size_t)n_cols, n_batches);
     for (int32_t i = 0; i < n_cols; i++) {
         if (cols[i] < 0 || (size_t)cols[i] >= f->fields.size()) return ipc_fail(BDF_INVALID, "column index out of range");
         dtypes[i] = f->fields[cols[i]].dtype;
-        views[i].resize((size_t)std::max<int64_t>(nb, 1));
-        for (int64_t b = 0; b < nb; b++) {
-            const int st = bdf_ipc_view(f, b, cols[i], &views[i][b]);
+        views[i].resize((size_t)std::max<int64_t>(n_batches, 1));
+        for (int64_t b = 0; b < n_batches; b++) {
+            const int st = bdf_ipc_view(f, batches[b], cols[i], &views[i][b]);
             if (st != BDF_OK) return st;
         }
         vp[i] = views[i].data();
     }
     return bdf_upload_many(ctx, n_cols, dtypes.data(), nch.data(), vp.data(), flags, out);
+}
+
+int bdf_ipc_read(bdf_ctx* ctx, const bdf_ipc* f, int32_t n_cols, const int32_t* cols, int flags, bdf_col** out) {
+    if (!f) return ipc_fail(BDF_INVALID, "null argument");
+    std::vector<int64_t> all(f->batches.size());
+    for (size_t b = 0; b < all.size(); b++) all[b] = (int64_t)b;
+    return bdf_ipc_read_batches(ctx, f, n_cols, cols, (int64_t)all.size(), all.data(), flags, out);
 }
 
 }  // extern "C"

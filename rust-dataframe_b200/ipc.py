@@ -89,8 +89,10 @@ class IpcFile:
         return PrimitiveArray(dtype, vals, validity, 0, n, v.null_count, keepalive=self)
 
     # -- device --
-    def read(self, columns: Optional[Sequence[Union[int, str]]] = None, ctx: Optional[N.Context] = None, asynchronous: bool = False) -> Dict[str, "object"]:
-        """The chosen columns (default: every column of a type on the path) as device Columns, one chunk per RecordBatch."""
+    def read(self, columns: Optional[Sequence[Union[int, str]]] = None, ctx: Optional[N.Context] = None, asynchronous: bool = False,
+             batches: Optional[Sequence[int]] = None) -> Dict[str, "object"]:
+        """The chosen columns (default: every column of a type on the path) as device Columns, one chunk per RecordBatch.
+        ``batches`` restricts the read to those RecordBatches (one rank's share: ``parallel.shard_indices``)."""
         from .functions import Column
 
         ctx = ctx or N.default_context()
@@ -100,7 +102,13 @@ class IpcFile:
             idx = [self.column_index(c) for c in columns]
         arr = (C.c_int32 * len(idx))(*idx)
         outs = (C.c_void_p * len(idx))()
-        N.raise_for_status(N.lib().bdf_ipc_read(ctx.handle, self.handle, len(idx), arr, N.ASYNC if asynchronous else 0, outs))
+        flags = N.ASYNC if asynchronous else 0
+        if batches is None:
+            N.raise_for_status(N.lib().bdf_ipc_read(ctx.handle, self.handle, len(idx), arr, flags, outs))
+        else:
+            bl = list(batches)
+            barr = (C.c_int64 * max(len(bl), 1))(*bl)
+            N.raise_for_status(N.lib().bdf_ipc_read_batches(ctx.handle, self.handle, len(idx), arr, len(bl), barr, flags, outs))
         res = {}
         for i, h in zip(idx, outs):
             col = Column(ctx, C.c_void_p(h))

@@ -269,6 +269,37 @@ def test_file_to_device_and_back(rdf, ctx, oracle, tmp_path):
 
 
 @pytest.mark.gpu
+def test_sharded_read_combines_to_the_whole_file(rdf, ctx, tmp_path):
+    """Multi-GPU shape of from_arrow: rank r of N reads RecordBatches by the shard map, aggregate partials combine
+    to the single-reader result (here the N ranks are played in one process; the combine rules are the ones
+    tests/test_parallel.py checks over gloo)."""
+    from rust_dataframe_b200 import parallel
+
+    rng = np.random.default_rng(5)
+    lens = [100, 0, 4097, 30_000, 5, 77_777, 2048]
+    batches = [pa.record_batch([random_array(rng, pa.int64(), n, 0.2), random_array(rng, pa.float64(), n, 0.1)], names=["k", "x"]) for n in lens]
+    path = str(tmp_path / "sharded.arrow")
+    write_file(path, batches[0].schema, batches)
+    with rdf.IpcFile(path) as f:
+        whole = f.read(["k"])["k"].aggregate_all()
+        for world in (2, 3):
+            parts, seen = [], []
+            for rank in range(world):
+                mine = parallel.shard_indices(f.num_batches, rank, world, lens=[f.batch_rows(b) for b in range(f.num_batches)])
+                seen += mine
+                col = f.read(["k", "x"], batches=mine)["k"]
+                assert [col.chunk_info(i)["len"] for i in range(len(mine))] == [lens[b] for b in mine]
+                parts.append(col.aggregate_all() if mine else None)
+            assert sorted(seen) == list(range(len(lens)))
+            parts = [p for p in parts if p is not None and p["count"] > 0]
+            assert sum(p["count"] for p in parts) == whole["count"]
+            assert (sum(int(p["sum"]) for p in parts) + 2 ** 63) % 2 ** 64 - 2 ** 63 == whole["sum"]
+            assert min(p["min"] for p in parts) == whole["min"] and max(p["max"] for p in parts) == whole["max"]
+        with pytest.raises(rdf.ArrowError):
+            f.read(["k"], batches=[len(lens)])
+
+
+@pytest.mark.gpu
 def test_large_file_read_1e7(rdf, ctx, tmp_path):
     """2 x Float64 x 1e7 rows in 10 batches: file -> device add + fused sum equals numpy on the file's data."""
     rng = np.random.default_rng(2)
