@@ -147,6 +147,14 @@ def main():
         keys = sorted(k for k in res if k.startswith("filter"))
         report(name + ": count+scan", "N2", res, keys[0])
         report(name + ": scatter", "N2", res, keys[1])
+    # ---- DataFrame::sort: lexsort_to_indices (stable LSD radix, 32 B/row per executed pass) + take ----
+    report("sort indices f64 (8 passes)", "sort", timed(ctx, lambda: rdf.sort_indices([(a, False)]), reps=4), "sort")
+    report("sort indices i64 10% nulls, |x| < 2^40 (6+1 passes)", "sort", timed(ctx, lambda: rdf.sort_indices([(i64n, True)]), reps=4), "sort")
+    report("sort indices i32 10% nulls (4+1 passes)", "sort", timed(ctx, lambda: rdf.sort_indices([(i32n, False)]), reps=4), "sort")
+    report("sort indices i8 then f64 (two criteria)", "sort", timed(ctx, lambda: rdf.sort_indices([(i8, False), (a, True)]), reps=4), "sort")
+    sidx = rdf.sort_indices([(a, False)])
+    report("take f64 by the sort indices (random gather)", "sort", timed(ctx, lambda: b.take(sidx), reps=4), "take")
+    report("take i32 10% nulls by the sort indices", "sort", timed(ctx, lambda: i32n.take(sidx), reps=4), "take")
     if args.json:
         with open(args.json, "w") as f:
             json.dump({"rows": args.rows, "peak_GBs_measured": pk, "results": rows_out}, f, indent=1)

@@ -199,6 +199,20 @@ int  bdf_aggregate_all_dev_async(bdf_ctx* ctx, const bdf_col* in, bdf_future** f
 int  bdf_future_wait(bdf_ctx* ctx, bdf_future* fut, bdf_agg4* out);
 void bdf_col_free(bdf_ctx* ctx, bdf_col* col);
 
+/* ---- DataFrame::sort (src/dataframe.rs:194-222): lexsort_to_indices + take ------------------------------------------
+ * bdf_sort_indices_dev  arrow compute::lexsort_to_indices over the criteria columns (numeric, equal lengths, any chunking;
+ *                       row numbers count through the chunks): a STABLE sort; per criterion ascending or descending,
+ *                       nulls always last (the reference passes nulls_first: false), NaN greater than every number,
+ *                       -0.0 == 0.0.  Result: one UInt32 chunk of row numbers.  BDF_INVALID for zero criteria
+ *                       ("Sort criteria cannot be empty").
+ * bdf_take_dev          Column::take (src/table.rs:218-241) -> arrow compute::take: out[i] = values[indices[i]], one
+ *                       chunk (the reference's repartitioning loop always produces a single chunk); a null index or a
+ *                       null value gives a null slot; an index past the end is an error (BDF_INVALID).  Any numeric
+ *                       or boolean values column; indices: a UInt32 column. */
+typedef struct { const bdf_col* column; int32_t descending; } bdf_sort_key;
+int  bdf_sort_indices_dev(bdf_ctx* ctx, int32_t n_keys, const bdf_sort_key* keys, bdf_col** indices);
+int  bdf_take_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* indices, bdf_col** out);
+
 /* ---- N4: Arrow IPC files either side of the path ---------------------------------------------------------------
  * DataFrame::from_arrow (src/dataframe.rs:391-407: arrow::ipc::reader::FileReader, every RecordBatch -> one chunk per
  * column) and DataFrame::to_arrow (:515-525: arrow::ipc::writer::FileWriter).  The file is mapped and its footer, schema
@@ -235,7 +249,7 @@ typedef struct {
     int64_t bytes;    /* algorithmic bytes of the launch (SURVEY 8(d) per-row figure x rows) */
     float   ms;       /* device time between the bracketing events */
 } bdf_launch_record;
-typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER, BDF_K_EXPR } bdf_kernel_id;
+typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER, BDF_K_EXPR, BDF_K_SORT, BDF_K_TAKE } bdf_kernel_id;
 int     bdf_profile_enable(bdf_ctx* ctx, int on);
 int     bdf_profile_read(bdf_ctx* ctx, bdf_launch_record* buf, int64_t cap, int64_t* n); /* syncs; drains */
 int64_t bdf_launch_count(bdf_ctx* ctx);           /* kernels launched since bdf_init */

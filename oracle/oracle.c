@@ -673,3 +673,119 @@ void orc_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint
     }
     if (null_count) *null_count = nulls;
 }
+
+/* ---- DataFrame::sort: lexsort_to_indices + take (src/dataframe.rs:194-222, src/table.rs:218-241) ------------------ */
+typedef struct {
+    int dtype, descending;
+    const void* flat;       /* concatenated values (Column::to_array) */
+    const uint8_t* valid;   /* one byte per row */
+} sort_col;
+
+static int cmp_values(const sort_col* k, uint32_t a, uint32_t b) {
+    switch (k->dtype) {
+#define ORC_CMP_INT(ID, T) case ID: { T x = ((const T*)k->flat)[a], y = ((const T*)k->flat)[b]; return x < y ? -1 : (x > y ? 1 : 0); }
+        ORC_CMP_INT(ORC_I8, int8_t) ORC_CMP_INT(ORC_I16, int16_t) ORC_CMP_INT(ORC_I32, int32_t) ORC_CMP_INT(ORC_I64, int64_t)
+        ORC_CMP_INT(ORC_U8, uint8_t) ORC_CMP_INT(ORC_U16, uint16_t) ORC_CMP_INT(ORC_U32, uint32_t) ORC_CMP_INT(ORC_U64, uint64_t)
+#undef ORC_CMP_INT
+        case ORC_F32: {   /* cmp_nans_last */
+            float x = ((const float*)k->flat)[a], y = ((const float*)k->flat)[b];
+            if (x != x) return y != y ? 0 : 1;
+            if (y != y) return -1;
+            return x < y ? -1 : (x > y ? 1 : 0);
+        }
+        default: {
+            double x = ((const double*)k->flat)[a], y = ((const double*)k->flat)[b];
+            if (x != x) return y != y ? 0 : 1;
+            if (y != y) return -1;
+            return x < y ? -1 : (x > y ? 1 : 0);
+        }
+    }
+}
+
+/* LexicographicalComparator::compare with nulls_first == false */
+static int cmp_rows(int n_keys, const sort_col* k, uint32_t a, uint32_t b) {
+    for (int i = 0; i < n_keys; i++) {
+        const int va = k[i].valid[a], vb = k[i].valid[b];
+        if (va && vb) {
+            int c = cmp_values(&k[i], a, b);
+            if (c) return k[i].descending ? -c : c;
+        } else if (va != vb) {
+            return va ? -1 : 1;
+        }
+    }
+    return 0;
+}
+
+int orc_lexsort_indices(int n_keys, const orc_sort_key* keys, uint32_t* out) {
+    if (n_keys < 1) return ORC_UNSUPPORTED;   /* DataFrameError::ComputeError("Sort criteria cannot be empty") */
+    int64_t n = -1;
+    for (int i = 0; i < n_keys; i++) {
+        int64_t t = 0;
+        for (int64_t c = 0; c < keys[i].n_chunks; c++) t += keys[i].chunks[c].len;
+        if (n < 0) n = t;
+        if (t != n) return ORC_LENGTH_MISMATCH;
+        if (keys[i].dtype < 0 || keys[i].dtype > ORC_F64) return ORC_UNSUPPORTED;
+    }
+    sort_col* k = (sort_col*)calloc((size_t)n_keys, sizeof(sort_col));
+    for (int i = 0; i < n_keys; i++) {
+        const int w = orc_width(keys[i].dtype);
+        char* flat = (char*)malloc((size_t)(n > 0 ? n : 1) * (size_t)w);
+        uint8_t* valid = (uint8_t*)malloc((size_t)(n > 0 ? n : 1));
+        int64_t at = 0;
+        for (int64_t c = 0; c < keys[i].n_chunks; c++) {
+            const orc_view* v = &keys[i].chunks[c];
+            if (v->len) memcpy(flat + at * w, (const char*)v->values + v->offset * w, (size_t)v->len * (size_t)w);
+            for (int64_t j = 0; j < v->len; j++) valid[at + j] = v->validity ? (uint8_t)bit_get(v->validity, v->offset + j) : 1;
+            at += v->len;
+        }
+        k[i].dtype = keys[i].dtype; k[i].descending = keys[i].descending; k[i].flat = flat; k[i].valid = valid;
+    }
+    uint32_t* tmp = (uint32_t*)malloc((size_t)(n > 0 ? n : 1) * sizeof(uint32_t));
+    for (int64_t i = 0; i < n; i++) out[i] = (uint32_t)i;
+    uint32_t *src = out, *dst = tmp;
+    for (int64_t width = 1; width < n; width *= 2) {   /* bottom-up stable merge sort */
+        for (int64_t lo = 0; lo < n; lo += 2 * width) {
+            int64_t mid = lo + width < n ? lo + width : n, hi = lo + 2 * width < n ? lo + 2 * width : n;
+            int64_t a = lo, b = mid, o = lo;
+            while (a < mid && b < hi) dst[o++] = cmp_rows(n_keys, k, src[b], src[a]) < 0 ? src[b++] : src[a++];   /* ties: left first */
+            while (a < mid) dst[o++] = src[a++];
+            while (b < hi) dst[o++] = src[b++];
+        }
+        uint32_t* t = src; src = dst; dst = t;
+    }
+    if (src != out) memcpy(out, src, (size_t)n * sizeof(uint32_t));
+    free(tmp);
+    for (int i = 0; i < n_keys; i++) { free((void*)k[i].flat); free((void*)k[i].valid); }
+    free(k);
+    return ORC_OK;
+}
+
+int orc_take(int dtype, int64_t n_chunks, const orc_view* chunks, int64_t n_idx, const uint32_t* idx, const uint8_t* idx_validity, orc_out* out) {
+    const int is_bool = dtype == ORC_BOOL;
+    if (!is_bool && (dtype < 0 || dtype > ORC_F64)) return ORC_UNSUPPORTED;
+    const int w = is_bool ? 1 : orc_width(dtype);
+    int64_t total = 0;
+    int any_validity = idx_validity != NULL;
+    for (int64_t c = 0; c < n_chunks; c++) { total += chunks[c].len; any_validity |= chunks[c].validity != NULL; }
+    out->len = n_idx; out->null_count = 0; out->has_validity = any_validity;
+    if (is_bool) memset(out->values, 0, (size_t)((n_idx + 7) / 8));
+    if (any_validity) memset(out->validity, 0, (size_t)((n_idx + 7) / 8));
+    for (int64_t i = 0; i < n_idx; i++) {
+        int valid = idx_validity ? bit_get(idx_validity, i) : 1;
+        if (valid) {
+            int64_t r = idx[i];
+            if (r >= total) return ORC_PANIC;
+            int64_t c = 0;
+            while (r >= chunks[c].len) { r -= chunks[c].len; c++; }
+            const orc_view* v = &chunks[c];
+            valid = v->validity ? bit_get(v->validity, v->offset + r) : 1;
+            if (valid) {
+                if (is_bool) { if (bit_get((const uint8_t*)v->values, v->offset + r)) bit_set((uint8_t*)out->values, i); }
+                else memcpy((char*)out->values + i * w, (const char*)v->values + (v->offset + r) * w, (size_t)w);
+            }
+        }
+        if (!valid && !is_bool) memset((char*)out->values + i * w, 0, (size_t)w);
+        if (any_validity) { if (valid) bit_set(out->validity, i); else out->null_count++; }
+    }
+    return ORC_OK;
+}

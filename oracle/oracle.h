@@ -121,6 +121,24 @@ int orc_compare(int op, int ltype, const orc_view* l, int rtype, const orc_view*
 int orc_bool(int op, const orc_view* a, const orc_view* b, orc_out* out);
 int orc_filter(int dtype, const orc_view* values, const orc_view* mask, orc_out* out);
 
+/* ---- DataFrame::sort (src/dataframe.rs:194-222) = arrow compute::lexsort_to_indices + Column::take (src/table.rs:218-241) ----
+ *   orc_lexsort_indices  every criterion column is concatenated (Column::to_array), SortOptions { descending, nulls_first:
+ *                 false } -- the reference ignores SortCriteria::nulls_first (:205-208).  arrow-rs builds a
+ *                 LexicographicalComparator and runs a STABLE sort (slice::sort_by) of the row numbers with it: per criterion,
+ *                 (valid, valid) -> value order, reversed when descending; (null, valid) -> Greater; (valid, null) -> Less;
+ *                 (null, null) -> next criterion.  Floats use cmp_nans_last: NaN == NaN, NaN greater than any number,
+ *                 otherwise partial_cmp (so -0.0 == 0.0).  Restated here as a bottom-up merge sort with that comparator
+ *                 (nothing shared with the product's radix sort).
+ *   orc_take      arrow compute::take(values, indices): out[i] = values[indices[i]]; a null index or a null value gives a
+ *                 null slot; the reference's repartitioning loop (table.rs:223-236) always yields ONE chunk.  ORC_PANIC for
+ *                 an index past the end (arrow returns an error).
+ * Pinned by the reference's own test_sort vector (src/dataframe.rs:963-1002) in tests/test_oracle_golden.py; pyarrow
+ * cross-checks the NaN-free cases.  The arrow-rs source is not vendored: the comparator above is restated from recall. */
+typedef struct { int dtype; int64_t n_chunks; const orc_view* chunks; int descending; } orc_sort_key;
+int orc_lexsort_indices(int n_keys, const orc_sort_key* keys, uint32_t* out_indices);
+int orc_take(int dtype, int64_t n_chunks, const orc_view* chunks, int64_t n_idx, const uint32_t* idx, const uint8_t* idx_validity,
+             orc_out* out);
+
 /* Counter-based synthetic data; the CUDA generator in the product reproduces it bit-for-bit.
  * kind 0: real uniform [lo,hi)   1: real +-[1,2)   2: integer, full range of the type
  * kind 3: integer uniform [-2^40, 2^40) (truncated to the type)

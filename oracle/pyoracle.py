@@ -247,6 +247,54 @@ def filter_chunk(values, mask):
     return st, OracleArray(values.dtype, v[:k], b[: (k + 7) // 8] if out[0].has_validity else None, int(out[0].null_count))
 
 
+class SortKey(C.Structure):
+    _fields_ = [("dtype", C.c_int), ("n_chunks", C.c_int64), ("chunks", C.POINTER(View)), ("descending", C.c_int)]
+
+
+def lexsort_indices(keys: Sequence[tuple]):
+    """DataFrame::sort's index step.  keys: [(chunks, descending)], chunks = host arrays of one numeric column.
+    Returns (status, np.uint32 row numbers)."""
+    L = lib()
+    L.orc_lexsort_indices.argtypes = [C.c_int, C.POINTER(SortKey), C.POINTER(C.c_uint32)]
+    arr = (SortKey * max(len(keys), 1))()
+    keep = []
+    n = 0
+    for i, (chunks, desc) in enumerate(keys):
+        v = _views(chunks)
+        keep.append(v)
+        arr[i].dtype = chunks[0].dtype if chunks else F64
+        arr[i].n_chunks = len(chunks)
+        arr[i].chunks = C.cast(v, C.POINTER(View))
+        arr[i].descending = 1 if desc else 0
+        n = sum(c.length for c in chunks)
+    out = np.zeros(max(n, 1), dtype=np.uint32)
+    st = L.orc_lexsort_indices(len(keys), arr, out.ctypes.data_as(C.POINTER(C.c_uint32)))
+    return st, (out[:n] if st == OK else None)
+
+
+def take(chunks: Sequence, indices: np.ndarray, index_valid: Optional[np.ndarray] = None):
+    """Column::take: one output chunk.  indices: uint32 row numbers over the concatenated chunks; index_valid: bool mask."""
+    L = lib()
+    L.orc_take.argtypes = [C.c_int, C.c_int64, C.POINTER(View), C.c_int64, C.POINTER(C.c_uint32), C.c_void_p, C.POINTER(Out)]
+    dtype = chunks[0].dtype
+    idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    n = idx.shape[0]
+    iv = None if index_valid is None else np.packbits(np.asarray(index_valid, bool), bitorder="little")
+    is_bool = dtype == BOOL
+    v = np.zeros((n + 7) // 8, dtype=np.uint8) if is_bool else np.zeros(n, dtype=NP_DTYPES[dtype])
+    b = np.zeros((n + 7) // 8, dtype=np.uint8)
+    out = (Out * 1)()
+    out[0].values = v.ctypes.data if v.size else 0
+    out[0].validity = b.ctypes.data if b.size else 0
+    st = L.orc_take(dtype, len(chunks), _views(chunks), n, idx.ctypes.data_as(C.POINTER(C.c_uint32)) if n else None,
+                    iv.ctypes.data if iv is not None and iv.size else None, out)
+    if st != OK:
+        return st, None
+    if is_bool:
+        return st, OracleBoolArray(v, b if out[0].has_validity else None, n, int(out[0].null_count))
+    return st, OracleArray(dtype, v, b if out[0].has_validity else None, int(out[0].null_count))
+
+
 def generate(dtype: int, kind: int, lo: float, hi: float, seed: int, col: int, row0: int, length: int,
              null_mod: int = 0) -> OracleArray:
     v = np.zeros(length, dtype=NP_DTYPES[dtype])

@@ -1,0 +1,383 @@
+// k_sort.cu -- DataFrame::sort (src/dataframe.rs:194-222): lexsort_to_indices over the criteria columns, then
+// Column::take for every column (src/table.rs:218-241).  SURVEY 8(f) names sort right after the N4 row.
+//
+// arrow-rs lexsort_to_indices is a STABLE sort of row indices under a lexicographic comparator: per criterion, two
+// valid slots compare by value (reversed when `descending`), a null slot is greater than any valid slot when
+// nulls_first == false (the reference hard-codes false, :205-208) whatever `descending` says, two nulls are equal;
+// floats compare with partial_cmp with NaN greater than everything and -0.0 == 0.0.  A stable LSD radix sort
+// reproduces exactly that order: criteria are processed from the LAST to the FIRST; within a criterion the value is
+// mapped to an order-preserving unsigned key (sign flip for ints; the usual float transform with -0.0 and NaN
+// canonicalised; bitwise NOT for descending; 0 for null slots), sorted byte by byte, and a final 2-bucket pass on the
+// null flag moves the nulls behind the valid rows without disturbing either group.
+//
+// Pass structure (per 8-bit digit): k_radix_hist (per-CTA digit counts over the CTA's contiguous range of tiles) ->
+// k_radix_scan (one CTA, exclusive scan in digit-major order) -> k_radix_scatter (per tile: warp-level match_any ranks,
+// reorder through shared memory, write each digit's run contiguously).  A digit on which every key agrees is skipped:
+// k_sort_keys also accumulates the 8 x 256 global digit histogram of the keys it builds.
+// HBM traffic per executed pass: 8 (hist) + 12 + 12 B/row; Float64/Int64 criterion = 8 value passes (+1 if nullable).
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace bdf {
+
+constexpr int kSortItems = 8;                      // keys per thread in the scatter kernel
+constexpr int kSortTile = kThreads * kSortItems;   // 2048 keys per tile
+
+struct SortChunk {          // one chunk of a column in the concatenated row space
+    const void* values;
+    const uint32_t* validity;
+    int64_t start;          // first global row of the chunk
+    int32_t bit_off;        // residual bit offset of the validity bitmap
+    int32_t val_bit_off;    // boolean columns: residual bit offset of the values bitmap
+};
+
+__device__ __forceinline__ int chunk_of(const SortChunk* __restrict__ t, int n, int64_t row) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) {   // last chunk whose start <= row (empty chunks share their start with the next one)
+        const int mid = (lo + hi + 1) >> 1;
+        if (__ldg(&t[mid].start) <= row) lo = mid; else hi = mid - 1;
+    }
+    return lo;
+}
+__device__ __forceinline__ bool chunk_bit(const uint32_t* __restrict__ bits, int64_t bit) {
+    return (__ldg(bits + (bit >> 5)) >> (bit & 31)) & 1u;
+}
+
+// ---- order-preserving keys --------------------------------------------------------------------------------------
+template <typename T> struct SortKey;
+template <> struct SortKey<int8_t>   { static __device__ __forceinline__ unsigned long long of(int8_t x)   { return (uint8_t)x ^ 0x80u; } };
+template <> struct SortKey<int16_t>  { static __device__ __forceinline__ unsigned long long of(int16_t x)  { return (uint16_t)x ^ 0x8000u; } };
+template <> struct SortKey<int32_t>  { static __device__ __forceinline__ unsigned long long of(int32_t x)  { return (uint32_t)x ^ 0x80000000u; } };
+template <> struct SortKey<int64_t>  { static __device__ __forceinline__ unsigned long long of(int64_t x)  { return (unsigned long long)x ^ (1ull << 63); } };
+template <> struct SortKey<uint8_t>  { static __device__ __forceinline__ unsigned long long of(uint8_t x)  { return x; } };
+template <> struct SortKey<uint16_t> { static __device__ __forceinline__ unsigned long long of(uint16_t x) { return x; } };
+template <> struct SortKey<uint32_t> { static __device__ __forceinline__ unsigned long long of(uint32_t x) { return x; } };
+template <> struct SortKey<uint64_t> { static __device__ __forceinline__ unsigned long long of(uint64_t x) { return x; } };
+template <> struct SortKey<float> {
+    static __device__ __forceinline__ unsigned long long of(float x) {
+        if (x != x) return 0xffffffffull;            // every NaN is the same, greatest key
+        if (x == 0.0f) x = 0.0f;                     // -0.0 == 0.0
+        const uint32_t b = __float_as_uint(x);
+        return (b >> 31) ? (uint32_t)~b : (b | 0x80000000u);
+    }
+};
+template <> struct SortKey<double> {
+    static __device__ __forceinline__ unsigned long long of(double x) {
+        if (x != x) return ~0ull;
+        if (x == 0.0) x = 0.0;
+        const unsigned long long b = (unsigned long long)__double_as_longlong(x);
+        return (b >> 63) ? ~b : (b | (1ull << 63));
+    }
+};
+
+// keys[i] = key of row idx[i] (idx == nullptr: row i) of the chunked column; mode 1: the null flag instead.
+// Also accumulates hist[8][256], the digit histograms of the keys written.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_sort_keys(const SortChunk* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ idx, int64_t n, int mode, int descending,
+            unsigned long long* __restrict__ keys, unsigned int* __restrict__ hist) {
+    __shared__ unsigned int s_hist[8 * 256];
+    for (int i = threadIdx.x; i < 8 * 256; i += kThreads) s_hist[i] = 0;
+    __syncthreads();
+    constexpr unsigned long long MASK = sizeof(T) == 8 ? ~0ull : ((1ull << (8 * (sizeof(T) & 7))) - 1ull);
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const int64_t r = idx ? (int64_t)idx[i] : i;
+        const int c = n_chunks == 1 ? 0 : chunk_of(chunks, n_chunks, r);
+        const SortChunk ch = chunks[c];
+        const int64_t local = r - ch.start;
+        const bool valid = ch.validity ? chunk_bit(ch.validity, ch.bit_off + local) : true;
+        unsigned long long k;
+        if (mode) k = valid ? 0ull : 1ull;
+        else {
+            k = 0ull;
+            if (valid) {
+                k = SortKey<T>::of(((const T*)ch.values)[local]);
+                if (descending) k = ~k & MASK;
+            }
+        }
+        keys[i] = k;
+#pragma unroll
+        for (int d = 0; d < (mode ? 1 : (int)sizeof(T)); d++) atomicAdd(&s_hist[d * 256 + ((k >> (8 * d)) & 0xff)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * 256; i += kThreads)
+        if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) k_iota(uint32_t* __restrict__ out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) out[i] = (uint32_t)i;
+}
+
+// ---- one radix pass -----------------------------------------------------------------------------------------------
+// CTA b owns tiles [b * tiles_per_cta, ...): block_hist[d * G + b] = number of its keys with digit d.
+__global__ void __launch_bounds__(kThreads)
+k_radix_hist(const unsigned long long* __restrict__ keys, int64_t n, int shift, int64_t tiles_per_cta, unsigned int* __restrict__ block_hist) {
+    __shared__ unsigned int s_hist[256];
+    s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    const int64_t begin = (int64_t)blockIdx.x * tiles_per_cta * kSortTile;
+    const int64_t end = min(n, begin + tiles_per_cta * kSortTile);
+    for (int64_t i = begin + threadIdx.x; i < end; i += kThreads) atomicAdd(&s_hist[(keys[i] >> shift) & 0xff], 1u);
+    __syncthreads();
+    block_hist[(int64_t)threadIdx.x * gridDim.x + blockIdx.x] = s_hist[threadIdx.x];
+}
+
+// Exclusive scan of `count` entries in place, one CTA of 1024 threads.
+__global__ void __launch_bounds__(1024) k_radix_scan(unsigned int* __restrict__ data, int64_t count) {
+    __shared__ unsigned int s_warp[32];
+    __shared__ unsigned int s_carry;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = 0; base < count; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const unsigned int v = i < count ? data[i] : 0u;
+        unsigned int x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+            s_warp[lane] = w;   // inclusive over warps
+        }
+        __syncthreads();
+        const unsigned int carry = s_carry;
+        const unsigned int before = carry + (warp ? s_warp[warp - 1] : 0u) + x - v;
+        if (i < count) data[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+}
+
+// Stable scatter of the CTA's tiles.  Within a tile, warp w owns elements [w*256, (w+1)*256) as 8 rows of 32 lanes, so
+// (warp, row, lane) order is the input order; ranks come from match_any + per-warp digit counters.
+__global__ void __launch_bounds__(kThreads)
+k_radix_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, int64_t n, int shift, int64_t tiles_per_cta,
+                const unsigned int* __restrict__ block_offsets, unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+    __shared__ unsigned long long s_key[kSortTile];
+    __shared__ uint32_t s_idx[kSortTile];
+    __shared__ unsigned int s_cnt[kWarpsPerCta][256];
+    __shared__ unsigned int s_start[256];   // first slot of each digit's run in the sorted tile
+    __shared__ unsigned int s_gbase[256];   // global position of the next key of each digit written by this CTA
+    __shared__ unsigned int s_wsum[kWarpsPerCta];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const unsigned int lt_mask = (1u << lane) - 1u;
+    s_gbase[tid] = block_offsets[(int64_t)tid * gridDim.x + blockIdx.x];
+    const int64_t tile_begin = (int64_t)blockIdx.x * tiles_per_cta;
+    for (int64_t t = tile_begin; t < tile_begin + tiles_per_cta; t++) {
+        const int64_t base = t * kSortTile;
+        if (base >= n) break;
+        const int in_tile = (int)min((int64_t)kSortTile, n - base);
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; w++) s_cnt[w][tid] = 0;
+        __syncthreads();
+        unsigned long long key[kSortItems];
+        uint32_t id[kSortItems];
+        unsigned int rank[kSortItems];
+#pragma unroll
+        for (int it = 0; it < kSortItems; it++) {
+            const int e = warp * (kSortItems * 32) + it * 32 + lane;
+            const bool ok = e < in_tile;
+            key[it] = ok ? keys_in[base + e] : 0ull;
+            id[it] = ok ? idx_in[base + e] : 0u;
+        }
+#pragma unroll
+        for (int it = 0; it < kSortItems; it++) {
+            const int e = warp * (kSortItems * 32) + it * 32 + lane;
+            const bool ok = e < in_tile;
+            const unsigned int d = ok ? (unsigned int)((key[it] >> shift) & 0xff) : 256u;   // 256: not a key
+            const unsigned int peers = __match_any_sync(0xffffffffu, d);
+            const int leader = __ffs(peers) - 1;
+            unsigned int old = 0;
+            if (lane == leader && ok) { old = s_cnt[warp][d]; s_cnt[warp][d] = old + __popc(peers); }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[it] = old + __popc(peers & lt_mask);
+            __syncwarp();
+        }
+        __syncthreads();
+        // thread d: exclusive prefix over the warps for digit d, then exclusive scan over the digits
+        unsigned int run = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; w++) { const unsigned int c = s_cnt[w][tid]; s_cnt[w][tid] = run; run += c; }
+        unsigned int x = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+        if (lane == 31) s_wsum[warp] = x;
+        __syncthreads();
+        unsigned int wbase = 0;
+#pragma unroll
+        for (int w = 0; w < kWarpsPerCta; w++) wbase += (w < warp) ? s_wsum[w] : 0u;
+        const unsigned int dstart = wbase + x - run;
+        s_start[tid] = dstart;
+        __syncthreads();
+#pragma unroll
+        for (int it = 0; it < kSortItems; it++) {
+            const int e = warp * (kSortItems * 32) + it * 32 + lane;
+            if (e < in_tile) {
+                const unsigned int d = (unsigned int)((key[it] >> shift) & 0xff);
+                const unsigned int pos = s_start[d] + s_cnt[warp][d] + rank[it];
+                s_key[pos] = key[it];
+                s_idx[pos] = id[it];
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < kSortItems; k++) {
+            const int s = k * kThreads + tid;
+            if (s < in_tile) {
+                const unsigned long long kk = s_key[s];
+                const unsigned int d = (unsigned int)((kk >> shift) & 0xff);
+                const unsigned int g = s_gbase[d] + ((unsigned int)s - s_start[d]);
+                keys_out[g] = kk;
+                idx_out[g] = s_idx[s];
+            }
+        }
+        __syncthreads();
+        s_gbase[tid] += run;   // thread d owns digit d
+        __syncthreads();
+    }
+}
+
+// ---- take -----------------------------------------------------------------------------------------------------------
+// out[i] = values[indices[i]] over chunked values and chunked indices (concatenated row spaces); a null index or a null
+// value gives a null slot with payload 0.  One row per thread: a warp assembles one validity word with a ballot.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_take(const SortChunk* __restrict__ vals, int n_vals, const SortChunk* __restrict__ idxs, int n_idxs, int64_t n, int64_t n_rows_values, T* __restrict__ out,
+       uint32_t* __restrict__ vout, uint32_t* __restrict__ warp_counts, int* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool valid = false;
+    T v = (T)0;
+    if (i < n) {
+        const int ic = n_idxs == 1 ? 0 : chunk_of(idxs, n_idxs, i);
+        const SortChunk ich = idxs[ic];
+        const int64_t il = i - ich.start;
+        valid = ich.validity ? chunk_bit(ich.validity, ich.bit_off + il) : true;
+        if (valid) {
+            const int64_t r = (int64_t)((const uint32_t*)ich.values)[il];
+            if (r >= n_rows_values) { atomicOr(flags, 1); valid = false; }   // arrow take: index out of bounds is an error
+            else {
+                const int c = n_vals == 1 ? 0 : chunk_of(vals, n_vals, r);
+                const SortChunk ch = vals[c];
+                const int64_t local = r - ch.start;
+                valid = ch.validity ? chunk_bit(ch.validity, ch.bit_off + local) : true;
+                if (valid) v = ((const T*)ch.values)[local];
+            }
+        }
+        out[i] = v;
+    }
+    const unsigned int word = __ballot_sync(0xffffffffu, valid);
+    if ((threadIdx.x & 31) == 0) {
+        if (vout && (i < n)) vout[i >> 5] = word;
+        if (vout) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = __popc(word);
+    }
+}
+
+// Boolean values: gather bits, one output word of values and one of validity per warp.
+__global__ void __launch_bounds__(kThreads)
+k_take_bool(const SortChunk* __restrict__ vals, int n_vals, const SortChunk* __restrict__ idxs, int n_idxs, int64_t n, int64_t n_rows_values,
+            uint32_t* __restrict__ out, uint32_t* __restrict__ vout, uint32_t* __restrict__ warp_counts, int* __restrict__ flags) {
+    const int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+    bool valid = false, bit = false;
+    if (i < n) {
+        const int ic = n_idxs == 1 ? 0 : chunk_of(idxs, n_idxs, i);
+        const SortChunk ich = idxs[ic];
+        const int64_t il = i - ich.start;
+        valid = ich.validity ? chunk_bit(ich.validity, ich.bit_off + il) : true;
+        if (valid) {
+            const int64_t r = (int64_t)((const uint32_t*)ich.values)[il];
+            if (r >= n_rows_values) { atomicOr(flags, 1); valid = false; }
+            else {
+                const int c = n_vals == 1 ? 0 : chunk_of(vals, n_vals, r);
+                const SortChunk ch = vals[c];
+                const int64_t local = r - ch.start;
+                valid = ch.validity ? chunk_bit(ch.validity, ch.bit_off + local) : true;
+                bit = valid && chunk_bit((const uint32_t*)ch.values, ch.val_bit_off + local);
+            }
+        }
+    }
+    const unsigned int vword = __ballot_sync(0xffffffffu, valid), bword = __ballot_sync(0xffffffffu, bit);
+    if ((threadIdx.x & 31) == 0) {
+        if (i < n) { out[i >> 5] = bword; if (vout) vout[i >> 5] = vword; }
+        if (vout) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = __popc(vword);
+    }
+}
+
+// ---- launchers ------------------------------------------------------------------------------------------------------
+size_t sort_chunk_size() { return sizeof(SortChunk); }
+void fill_sort_chunk(void* base, int64_t i, const void* values, const uint32_t* validity, int64_t start, int32_t bit_off, int32_t val_bit_off) {
+    SortChunk* c = (SortChunk*)base + i;
+    c->values = values; c->validity = validity; c->start = start; c->bit_off = bit_off; c->val_bit_off = val_bit_off;
+}
+int sort_tile_elems() { return kSortTile; }
+int take_tile_elems() { return kThreads; }
+
+static int grid_for(int64_t n, int sm_count) {
+    const int64_t want = (n + kThreads - 1) / kThreads;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(want, (int64_t)sm_count * 8));
+}
+
+cudaError_t launch_iota(uint32_t* out, int64_t n, int sm_count, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    k_iota<<<grid_for(n, sm_count), kThreads, 0, s>>>(out, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_sort_keys(int dtype, const void* chunks, int n_chunks, const uint32_t* idx, int64_t n, int mode, int descending,
+                             unsigned long long* keys, unsigned int* hist, int sm_count, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const SortChunk* ch = (const SortChunk*)chunks;
+    const int g = grid_for(n, sm_count);
+    switch (dtype) {
+#define BDF_SORT_CASE(ID, T) case ID: k_sort_keys<T><<<g, kThreads, 0, s>>>(ch, n_chunks, idx, n, mode, descending, keys, hist); break;
+        BDF_SORT_CASE(0, int8_t) BDF_SORT_CASE(1, int16_t) BDF_SORT_CASE(2, int32_t) BDF_SORT_CASE(3, int64_t)
+        BDF_SORT_CASE(4, uint8_t) BDF_SORT_CASE(5, uint16_t) BDF_SORT_CASE(6, uint32_t) BDF_SORT_CASE(7, uint64_t)
+        BDF_SORT_CASE(8, float) BDF_SORT_CASE(9, double)
+#undef BDF_SORT_CASE
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// One stable pass on bits [shift, shift+8).  block_hist: 256 * sort_pass_ctas(n, sm_count) counters.
+int sort_pass_ctas(int64_t n, int sm_count) {
+    const int64_t tiles = (n + kSortTile - 1) / kSortTile;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 4));
+}
+cudaError_t launch_radix_pass(const unsigned long long* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
+                              unsigned long long* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t tiles = (n + kSortTile - 1) / kSortTile;
+    const int g = sort_pass_ctas(n, sm_count);
+    const int64_t per = (tiles + g - 1) / g;
+    k_radix_hist<<<g, kThreads, 0, s>>>(keys_in, n, shift, per, block_hist);
+    k_radix_scan<<<1, 1024, 0, s>>>(block_hist, (int64_t)256 * g);
+    k_radix_scatter<<<g, kThreads, 0, s>>>(keys_in, idx_in, n, shift, per, block_hist, keys_out, idx_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_take(int dtype, const void* vals, int n_vals, const void* idxs, int n_idxs, int64_t n, int64_t n_rows_values, void* out,
+                        uint32_t* vout, uint32_t* warp_counts, int* flags, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    const int64_t g = (n + kThreads - 1) / kThreads;
+    if (g > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    const SortChunk* v = (const SortChunk*)vals;
+    const SortChunk* ix = (const SortChunk*)idxs;
+    switch (dtype) {
+#define BDF_TAKE_CASE(ID, T) case ID: k_take<T><<<(unsigned)g, kThreads, 0, s>>>(v, n_vals, ix, n_idxs, n, n_rows_values, (T*)out, vout, warp_counts, flags); break;
+        BDF_TAKE_CASE(0, int8_t) BDF_TAKE_CASE(1, int16_t) BDF_TAKE_CASE(2, int32_t) BDF_TAKE_CASE(3, int64_t)
+        BDF_TAKE_CASE(4, uint8_t) BDF_TAKE_CASE(5, uint16_t) BDF_TAKE_CASE(6, uint32_t) BDF_TAKE_CASE(7, uint64_t)
+        BDF_TAKE_CASE(8, float) BDF_TAKE_CASE(9, double)
+#undef BDF_TAKE_CASE
+        case 10: k_take_bool<<<(unsigned)g, kThreads, 0, s>>>(v, n_vals, ix, n_idxs, n, n_rows_values, (uint32_t*)out, vout, warp_counts, flags); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+}  // namespace bdf

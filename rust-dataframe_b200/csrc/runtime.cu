@@ -184,6 +184,8 @@ struct bdf_ctx {
     AggDev* h_agg = nullptr;        // pinned + device-mapped: kernels write results straight into it
     AggDev* h_agg_dev = nullptr;    // device-side address of h_agg
     int* h_flag = nullptr;          // pinned
+    unsigned int* h_sort_hist = nullptr;   // pinned, 8 x 256 digit counts of the sort keys
+    int64_t last_sort_passes = 0;
     // device scratch
     AggDev* d_partials = nullptr;       // per-tile partials of k_reduce (compute stream only)
     size_t red_part_cap = 0;
@@ -1371,6 +1373,145 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// DataFrame::sort = lexsort_to_indices + take (k_sort.cu)
+
+namespace bdf {
+size_t sort_chunk_size();
+void fill_sort_chunk(void* base, int64_t i, const void* values, const uint32_t* validity, int64_t start, int32_t bit_off, int32_t val_bit_off);
+int sort_tile_elems();
+int take_tile_elems();
+int sort_pass_ctas(int64_t n, int sm_count);
+cudaError_t launch_iota(uint32_t* out, int64_t n, int sm_count, cudaStream_t s);
+cudaError_t launch_sort_keys(int dtype, const void* chunks, int n_chunks, const uint32_t* idx, int64_t n, int mode, int descending,
+                             unsigned long long* keys, unsigned int* hist, int sm_count, cudaStream_t s);
+cudaError_t launch_radix_pass(const unsigned long long* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
+                              unsigned long long* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s);
+cudaError_t launch_take(int dtype, const void* vals, int n_vals, const void* idxs, int n_idxs, int64_t n, int64_t n_rows_values, void* out,
+                        uint32_t* vout, uint32_t* warp_counts, int* flags, cudaStream_t s);
+}  // namespace bdf
+
+// The chunk table of a column in the concatenated row space (descriptor ring, uploaded on the descriptor stream).
+static int sort_table(bdf_ctx* c, const bdf_col* col, void** dev, int* n_chunks, bool* nullable) {
+    const int64_t n = (int64_t)col->chunks.size();
+    void* hp = nullptr;
+    TRY(ring_alloc(c, (size_t)std::max<int64_t>(n, 1) * sort_chunk_size(), &hp, dev));
+    int64_t start = 0;
+    bool any = false;
+    for (int64_t i = 0; i < n; i++) {
+        const DevChunk& ch = col->chunks[i];
+        fill_sort_chunk(hp, i, ch.values, ch.validity, start, ch.bit_off, ch.val_bit_off);
+        start += ch.len;
+        any = any || ch.validity != nullptr;
+    }
+    if (n == 0) fill_sort_chunk(hp, 0, nullptr, nullptr, 0, 0, 0);
+    wait_groups(c->s_compute, col, 0, n);
+    cudaError_t e = desc_upload(c, *dev, hp, (size_t)std::max<int64_t>(n, 1) * sort_chunk_size());
+    if (e != cudaSuccess) return fail(cuda_status(e), "descriptor upload failed: %s", cudaGetErrorString(e));
+    *n_chunks = (int)std::max<int64_t>(n, 1);
+    if (nullable) *nullable = any;
+    return BDF_OK;
+}
+
+static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bdf_col** out) {
+    if (n_keys < 1) return fail(BDF_INVALID, "Sort criteria cannot be empty");
+    for (int k = 0; k < n_keys; k++) {
+        if (!keys[k].column) return fail(BDF_INVALID, "null sort column");
+        const int dt = keys[k].column->dtype;
+        if (dt < 0 || dt >= BDF_NTYPES) return fail(BDF_UNSUPPORTED, "sort criteria must be numeric columns");
+        if (keys[k].column->total_len != keys[0].column->total_len) return fail(BDF_LENGTH_MISMATCH, "sort columns have different lengths");
+    }
+    const int64_t n = keys[0].column->total_len;
+    if (n > 0xffffffffLL) return fail(BDF_UNSUPPORTED, "sort indices are UInt32: at most 2^32-1 rows");
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, BDF_U32, {ChunkPlan{n, false}}, nullptr, sort_tile_elems(), &o));
+    cudaError_t e = cudaSuccess;
+    int st = BDF_OK;
+    unsigned long long* kbuf[2] = {nullptr, nullptr};
+    uint32_t* ibuf[2] = {nullptr, nullptr};
+    unsigned int *block_hist = nullptr, *ghist = nullptr;
+    if (n > 0) {
+        if (!c->h_sort_hist) e = cudaHostAlloc((void**)&c->h_sort_hist, 8 * 256 * sizeof(unsigned int), cudaHostAllocDefault);
+        for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+            e = cudaMallocAsync((void**)&kbuf[b], (size_t)n * 8, c->s_compute);
+            if (e == cudaSuccess) e = cudaMallocAsync((void**)&ibuf[b], (size_t)n * 4, c->s_compute);
+        }
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&block_hist, (size_t)256 * sort_pass_ctas(n, c->sm_count) * sizeof(unsigned int), c->s_compute);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&ghist, 8 * 256 * sizeof(unsigned int), c->s_compute);
+        int cur = 0;
+        int64_t passes = 0;
+        if (e == cudaSuccess) {
+            LaunchTimer t(c, BDF_K_SORT, keys[0].column->dtype, n, 0);
+            e = launch_iota(ibuf[0], n, c->sm_count, c->s_compute);
+            for (int k = n_keys - 1; k >= 0 && e == cudaSuccess && st == BDF_OK; k--) {
+                const bdf_col* col = keys[k].column;
+                void* table = nullptr; int nch = 0; bool nullable = false;
+                st = sort_table(c, col, &table, &nch, &nullable);
+                for (int mode = 0; mode < (nullable ? 2 : 1) && e == cudaSuccess && st == BDF_OK; mode++) {
+                    e = cudaMemsetAsync(ghist, 0, 8 * 256 * sizeof(unsigned int), c->s_compute);
+                    if (e == cudaSuccess) e = launch_sort_keys(col->dtype, table, nch, ibuf[cur], n, mode, keys[k].descending != 0, kbuf[cur], ghist, c->sm_count, c->s_compute);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_sort_hist, ghist, 8 * 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->s_compute);
+                    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+                    const int digits = mode ? 1 : dtype_width(col->dtype);
+                    for (int d = 0; d < digits && e == cudaSuccess; d++) {
+                        bool constant = false;   // every key has the same digit: the pass would be the identity
+                        for (int b = 0; b < 256; b++) constant = constant || c->h_sort_hist[d * 256 + b] == (unsigned int)n;
+                        if (constant) continue;
+                        e = launch_radix_pass(kbuf[cur], ibuf[cur], n, 8 * d, block_hist, kbuf[cur ^ 1], ibuf[cur ^ 1], c->sm_count, c->s_compute);
+                        cur ^= 1;
+                        passes++;
+                    }
+                }
+            }
+            if (e == cudaSuccess && st == BDF_OK)
+                e = cudaMemcpyAsync(o->chunks[0].values, ibuf[cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, c->s_compute);
+            c->last_sort_passes = passes;
+        }
+        if (c->profiling && !c->prof.empty() && c->prof.back().rec.kernel == BDF_K_SORT) c->prof.back().rec.bytes = 8 * n + passes * 32 * n + 4 * n;
+        for (int b = 0; b < 2; b++) { if (kbuf[b]) cudaFreeAsync(kbuf[b], c->s_compute); if (ibuf[b]) cudaFreeAsync(ibuf[b], c->s_compute); }
+        if (block_hist) cudaFreeAsync(block_hist, c->s_compute);
+        if (ghist) cudaFreeAsync(ghist, c->s_compute);
+    }
+    if (e == cudaSuccess && st == BDF_OK) e = finish_single_group(c, o);
+    if (st != BDF_OK || e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return st != BDF_OK ? st : fail(cuda_status(e), "sort failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+static int take_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* indices, bdf_col** out) {
+    if (indices->dtype != BDF_U32) return fail(BDF_UNSUPPORTED, "take indices must be a UInt32 column");
+    const int64_t n = indices->total_len;
+    void *vt = nullptr, *it = nullptr;
+    int nv = 0, ni = 0;
+    bool vnull = false, inull = false;
+    TRY(sort_table(c, values, &vt, &nv, &vnull));
+    TRY(sort_table(c, indices, &it, &ni, &inull));
+    bdf_col* o = nullptr;
+    TRY(col_alloc(c, values->dtype, {ChunkPlan{n, vnull || inull}}, nullptr, take_tile_elems(), &o));
+    o->counts_on_device = o->d_warp_counts != nullptr;
+    cudaError_t e = cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->s_compute);
+    if (e == cudaSuccess) {
+        const int w = values->dtype == kBool ? 1 : dtype_width(values->dtype);
+        LaunchTimer t(c, BDF_K_TAKE, values->dtype, n, n * (4 + 2 * (int64_t)w));
+        e = launch_take(values->dtype, vt, nv, it, ni, n, values->total_len, o->chunks[0].values, o->chunks[0].validity, o->d_warp_counts, c->d_flag, c->s_compute);
+    }
+    if (e == cudaSuccess) e = finish_single_group(c, o);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
+    if (e == cudaSuccess && *c->h_flag) { col_release(c, o); return fail(BDF_INVALID, "take: index out of bounds"); }
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        col_release(c, o);
+        return fail(cuda_status(e), "take failed: %s", cudaGetErrorString(e));
+    }
+    *out = o;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // C ABI
 
 #define ENTER(ctx)                                                   \
@@ -1402,6 +1543,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_agg) cudaFreeHost(c->h_agg);
     if (c->h_flag) cudaFreeHost(c->h_flag);
+    if (c->h_sort_hist) cudaFreeHost(c->h_sort_hist);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_stage2) cudaFree(c->d_stage2);
     if (c->d_ticket) cudaFree(c->d_ticket);
@@ -1649,6 +1791,18 @@ int bdf_eval_expr_dev(bdf_ctx* c, int32_t n_inputs, const bdf_col* const* inputs
     ENTER(c);
     if (!inputs || !nodes || !out) return fail(BDF_INVALID, "null argument");
     return expr_dev(c, n_inputs, inputs, n_nodes, nodes, out);
+}
+
+int bdf_sort_indices_dev(bdf_ctx* c, int32_t n_keys, const bdf_sort_key* keys, bdf_col** indices) {
+    ENTER(c);
+    if (!keys || !indices) return fail(BDF_INVALID, "null argument");
+    return sort_indices_dev(c, n_keys, keys, indices);
+}
+
+int bdf_take_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* indices, bdf_col** out) {
+    ENTER(c);
+    if (!values || !indices || !out) return fail(BDF_INVALID, "null argument");
+    return take_dev(c, values, indices, out);
 }
 
 int bdf_compare_dev(bdf_ctx* c, int op, const bdf_col* left, const bdf_col* right, double scalar, bdf_col** out) {

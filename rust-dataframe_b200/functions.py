@@ -316,6 +316,12 @@ class Column:
         N.raise_for_status(N.lib().bdf_binary_agg_dev_async(self.ctx.handle, op, self.handle, other.handle, C.byref(h), C.byref(f)))
         return Column(self.ctx, h), AggFuture(self.ctx, f, self.dtype)
 
+    def take(self, indices: "Column") -> "Column":
+        """Column::take (src/table.rs:218-241): values at the UInt32 row numbers, as ONE chunk; null index -> null slot."""
+        h = C.c_void_p()
+        N.raise_for_status(N.lib().bdf_take_dev(self.ctx.handle, self.handle, indices.handle, C.byref(h)))
+        return Column(self.ctx, h)
+
     def aggregate_all_async(self) -> "AggFuture":
         f = C.c_void_p()
         N.raise_for_status(N.lib().bdf_aggregate_all_dev_async(self.ctx.handle, self.handle, C.byref(f)))
@@ -433,6 +439,26 @@ class Column:
             self.free()
         except Exception:
             pass
+
+
+def sort_indices(criteria: Sequence[tuple]) -> "Column":
+    """compute::lexsort_to_indices as DataFrame::sort calls it (src/dataframe.rs:194-213).  criteria: [(Column, descending)];
+    stable, nulls last.  Returns a one-chunk UInt32 Column of row numbers."""
+    if not criteria:
+        raise N.ComputeError("Sort criteria cannot be empty")
+    ctx = criteria[0][0].ctx
+    arr = (N.SortKeyC * len(criteria))()
+    for i, (col, desc) in enumerate(criteria):
+        arr[i].column, arr[i].descending = col.handle.value if isinstance(col.handle, C.c_void_p) else col.handle, 1 if desc else 0
+    h = C.c_void_p()
+    N.raise_for_status(N.lib().bdf_sort_indices_dev(ctx.handle, len(criteria), arr, C.byref(h)))
+    return Column(ctx, h)
+
+
+def sort_columns(criteria: Sequence[tuple], columns: Sequence["Column"]) -> List["Column"]:
+    """DataFrame::sort: the index sort, then DataFrame::sort_by_indices (Column::take of every column, one chunk each)."""
+    idx = sort_indices(criteria)
+    return [c.take(idx) for c in columns]
 
 
 def _expr_nodes(nodes: Sequence[tuple]):

@@ -384,3 +384,58 @@ def test_compare_bool_filter_match_pyarrow(oracle):
     sel = a.value_bits() & a.valid_mask()
     assert fb.length == int(sel.sum()) and np.array_equal(fb.value_bits(), b.value_bits()[sel])
     assert oracle.filter_chunk(cx, Chunk(np.zeros(1, np.uint8), oracle.BOOL, None, 0, 5))[0] == oracle.LENGTH_MISMATCH
+
+
+# ---- DataFrame::sort: lexsort_to_indices + take ---------------------------------------------------------
+
+def test_sort_reference_golden(oracle):  # src/dataframe.rs:963-1002 (test_sort): a descending, b ascending, nulls last
+    a = from_list(oracle, oracle.I32, [1, 1, None, 3, 3, 4])
+    b = from_list(oracle, oracle.U8, [9, 5, 6, 7, 4, 8])
+    st, idx = oracle.lexsort_indices([([a], True), ([b], False)])
+    assert st == oracle.OK
+    _, sa = oracle.take([a], idx)
+    _, sb = oracle.take([b], idx)
+    assert to_list(sa) == [4, 3, 3, 1, 1, None]          # is_null(5), values 4,3,3,1,1
+    assert to_list(sb) == [8, 4, 7, 5, 9, 6]
+    assert oracle.lexsort_indices([])[0] != oracle.OK     # "Sort criteria cannot be empty"
+
+
+def test_sort_and_take_match_pyarrow(oracle):
+    """Stable multi-key order (nulls last whatever the direction) and take, against Arrow C++ on NaN-free data
+    (Arrow C++ keeps NaN behind the numbers in descending order too; arrow-rs reverses the comparator, NaN first)."""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+
+    rng = np.random.default_rng(33)
+    n = 5000
+    k1 = rng.integers(-3, 4, n).astype(np.int16)
+    k2 = np.round(rng.normal(0, 2, n)).astype(np.float64)
+    k2[::17] = -0.0
+    k3 = rng.integers(0, 2 ** 63, n).astype(np.uint64)
+    m1, m2 = rng.random(n) > 0.2, rng.random(n) > 0.1
+    split = [0, 1, 1, 1200, 5000]
+    def chunks(v, dt, m=None):
+        return [Chunk(v, dt, m, offset=s, length=e - s) if m is not None else Chunk(v[s:e], dt) for s, e in zip(split[:-1], split[1:])]
+    c1 = [Chunk(k1, oracle.I16, m1, offset=s, length=e - s) for s, e in zip(split[:-1], split[1:])]
+    c2 = [Chunk(k2, oracle.F64, m2, offset=s, length=e - s) for s, e in zip(split[:-1], split[1:])]
+    c3 = [Chunk(k3[s:e], oracle.U64) for s, e in zip(split[:-1], split[1:])]
+    t = pa.table({"k1": pa.array(k1, mask=~m1), "k2": pa.array(k2, mask=~m2), "k3": pa.array(k3)})
+    for desc in ((False, False, False), (True, False, True), (False, True, False), (True, True, True)):
+        st, idx = oracle.lexsort_indices([(c1, desc[0]), (c2, desc[1]), (c3, desc[2])])
+        assert st == oracle.OK
+        want = pc.sort_indices(t, sort_keys=[(f"k{i + 1}", "descending" if d else "ascending") for i, d in enumerate(desc)], null_placement="at_end")
+        assert np.array_equal(idx, want.to_numpy().astype(np.uint32)), desc
+    # ties only: a stable sort leaves the rows where they are
+    st, idx = oracle.lexsort_indices([([Chunk(np.zeros(100, np.int8), oracle.I8)], True)])
+    assert np.array_equal(idx, np.arange(100))
+    # NaN is the greatest number (cmp_nans_last), -0.0 == 0.0, nulls after NaN
+    f = Chunk(np.array([np.nan, 1.0, -np.inf, 0.0, -0.0, np.inf, 7.0, np.nan]), oracle.F64, [1, 1, 1, 1, 1, 1, 0, 1])
+    assert oracle.lexsort_indices([([f], False)])[1].tolist() == [2, 3, 4, 1, 5, 0, 7, 6]
+    assert oracle.lexsort_indices([([f], True)])[1].tolist() == [0, 7, 5, 1, 3, 4, 2, 6]
+    # take with null indices and across chunks
+    ix = rng.integers(0, n, 777).astype(np.uint32)
+    iv = rng.random(777) > 0.3
+    st, got = oracle.take(c2, ix, iv)
+    want = pc.take(t["k2"], pa.array(ix, mask=~iv))
+    assert to_list(got) == want.to_pylist()
+    assert oracle.take(c2, np.array([n], np.uint32))[0] == oracle.PANIC
