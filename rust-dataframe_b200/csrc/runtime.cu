@@ -184,7 +184,7 @@ struct bdf_ctx {
     AggDev* h_agg = nullptr;        // pinned + device-mapped: kernels write results straight into it
     AggDev* h_agg_dev = nullptr;    // device-side address of h_agg
     int* h_flag = nullptr;          // pinned
-    unsigned int* h_sort_hist = nullptr;   // pinned, 8 x 256 digit counts of the sort keys
+    unsigned long long* h_sort_agree = nullptr;   // pinned: OR and AND of the sort keys of one criterion
     int64_t last_sort_passes = 0;
     // device scratch
     AggDev* d_partials = nullptr;       // per-tile partials of k_reduce (compute stream only)
@@ -1383,7 +1383,7 @@ int take_tile_elems();
 int sort_pass_ctas(int64_t n, int sm_count);
 cudaError_t launch_iota(uint32_t* out, int64_t n, int sm_count, cudaStream_t s);
 cudaError_t launch_sort_keys(int dtype, const void* chunks, int n_chunks, const uint32_t* idx, int64_t n, int mode, int descending,
-                             unsigned long long* keys, unsigned int* hist, int sm_count, cudaStream_t s);
+                             unsigned long long* keys, unsigned long long* agree, int sm_count, cudaStream_t s);
 cudaError_t launch_radix_pass(const unsigned long long* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
                               unsigned long long* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s);
 cudaError_t launch_take(int dtype, const void* vals, int n_vals, const void* idxs, int n_idxs, int64_t n, int64_t n_rows_values, void* out,
@@ -1428,15 +1428,16 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
     int st = BDF_OK;
     unsigned long long* kbuf[2] = {nullptr, nullptr};
     uint32_t* ibuf[2] = {nullptr, nullptr};
-    unsigned int *block_hist = nullptr, *ghist = nullptr;
+    unsigned int* block_hist = nullptr;
+    unsigned long long* agree = nullptr;   // [0] OR, [1] AND of the keys of the current criterion
     if (n > 0) {
-        if (!c->h_sort_hist) e = cudaHostAlloc((void**)&c->h_sort_hist, 8 * 256 * sizeof(unsigned int), cudaHostAllocDefault);
+        if (!c->h_sort_agree) e = cudaHostAlloc((void**)&c->h_sort_agree, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
         for (int b = 0; b < 2 && e == cudaSuccess; b++) {
             e = cudaMallocAsync((void**)&kbuf[b], (size_t)n * 8, c->s_compute);
             if (e == cudaSuccess) e = cudaMallocAsync((void**)&ibuf[b], (size_t)n * 4, c->s_compute);
         }
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&block_hist, (size_t)256 * sort_pass_ctas(n, c->sm_count) * sizeof(unsigned int), c->s_compute);
-        if (e == cudaSuccess) e = cudaMallocAsync((void**)&ghist, 8 * 256 * sizeof(unsigned int), c->s_compute);
+        if (e == cudaSuccess) e = cudaMallocAsync((void**)&agree, 2 * sizeof(unsigned long long), c->s_compute);
         int cur = 0;
         int64_t passes = 0;
         if (e == cudaSuccess) {
@@ -1447,15 +1448,15 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
                 void* table = nullptr; int nch = 0; bool nullable = false;
                 st = sort_table(c, col, &table, &nch, &nullable);
                 for (int mode = 0; mode < (nullable ? 2 : 1) && e == cudaSuccess && st == BDF_OK; mode++) {
-                    e = cudaMemsetAsync(ghist, 0, 8 * 256 * sizeof(unsigned int), c->s_compute);
-                    if (e == cudaSuccess) e = launch_sort_keys(col->dtype, table, nch, ibuf[cur], n, mode, keys[k].descending != 0, kbuf[cur], ghist, c->sm_count, c->s_compute);
-                    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_sort_hist, ghist, 8 * 256 * sizeof(unsigned int), cudaMemcpyDeviceToHost, c->s_compute);
+                    e = cudaMemsetAsync(agree, 0, sizeof(unsigned long long), c->s_compute);
+                    if (e == cudaSuccess) e = cudaMemsetAsync(agree + 1, 0xff, sizeof(unsigned long long), c->s_compute);
+                    if (e == cudaSuccess) e = launch_sort_keys(col->dtype, table, nch, ibuf[cur], n, mode, keys[k].descending != 0, kbuf[cur], agree, c->sm_count, c->s_compute);
+                    if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_sort_agree, agree, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, c->s_compute);
                     if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
                     const int digits = mode ? 1 : dtype_width(col->dtype);
+                    const unsigned long long differ = e == cudaSuccess ? (c->h_sort_agree[0] ^ c->h_sort_agree[1]) : 0ull;   // bits that are not the same in all keys
                     for (int d = 0; d < digits && e == cudaSuccess; d++) {
-                        bool constant = false;   // every key has the same digit: the pass would be the identity
-                        for (int b = 0; b < 256; b++) constant = constant || c->h_sort_hist[d * 256 + b] == (unsigned int)n;
-                        if (constant) continue;
+                        if (((differ >> (8 * d)) & 0xff) == 0) continue;   // every key has the same digit: the pass would be the identity
                         e = launch_radix_pass(kbuf[cur], ibuf[cur], n, 8 * d, block_hist, kbuf[cur ^ 1], ibuf[cur ^ 1], c->sm_count, c->s_compute);
                         cur ^= 1;
                         passes++;
@@ -1469,7 +1470,7 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
         if (c->profiling && !c->prof.empty() && c->prof.back().rec.kernel == BDF_K_SORT) c->prof.back().rec.bytes = 8 * n + passes * 32 * n + 4 * n;
         for (int b = 0; b < 2; b++) { if (kbuf[b]) cudaFreeAsync(kbuf[b], c->s_compute); if (ibuf[b]) cudaFreeAsync(ibuf[b], c->s_compute); }
         if (block_hist) cudaFreeAsync(block_hist, c->s_compute);
-        if (ghist) cudaFreeAsync(ghist, c->s_compute);
+        if (agree) cudaFreeAsync(agree, c->s_compute);
     }
     if (e == cudaSuccess && st == BDF_OK) e = finish_single_group(c, o);
     if (st != BDF_OK || e != cudaSuccess) {
@@ -1543,7 +1544,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->d_stage) cudaFree(c->d_stage);
     if (c->h_agg) cudaFreeHost(c->h_agg);
     if (c->h_flag) cudaFreeHost(c->h_flag);
-    if (c->h_sort_hist) cudaFreeHost(c->h_sort_hist);
+    if (c->h_sort_agree) cudaFreeHost(c->h_sort_agree);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_stage2) cudaFree(c->d_stage2);
     if (c->d_ticket) cudaFree(c->d_ticket);
