@@ -35,6 +35,9 @@ for dtype in (rdf.I8, rdf.I16, rdf.I32, rdf.I64, rdf.U8, rdf.F32, rdf.F64):
     if dtype == rdf.F64:   # N3: fused expression with both temporaries, a shared node, a divide and a libm node
         prog = [(N.ADD, 0, 1), (N.SUB, 0, 1), (N.MUL, 2, 3), (N.MUL, 2, 2), (N.ADD, 4, 5), (N.DIV, 6, 1), ("sin", 7)]
         rdf.eval_expr([ca, cb], prog).download()
+    if dtype in (rdf.F64, rdf.I16):   # DataFrame::sort: two criteria (nullable + dense), take of a numeric and a boolean column
+        idx = rdf.sort_indices([(ca, True), (cb, False)])
+        ca.take(idx).download(); cb.gt(50.0).take(idx).download()
     if dtype not in (rdf.I64,):
         rdf.AggregateFunctions.avg([c for c in a if c.length])
 print("sanitize cases done")

@@ -31,6 +31,8 @@ pub enum BdfIpc {}   // a mapped Arrow IPC file
 #[repr(C)]
 pub struct BdfExprNode { pub op: i32, pub a: i32, pub b: i32 }   // op: bdf_binop, or BDF_EXPR_UNARY + bdf_unop
 pub const BDF_EXPR_UNARY: i32 = 100;
+#[repr(C)]
+pub struct BdfSortKey { pub column: *const BdfCol, pub descending: i32 }
 pub const BDF_ASYNC: c_int = 1;
 
 pub const BDF_OK: c_int = 0;
@@ -60,6 +62,9 @@ extern "C" {
                              out: *mut *mut BdfCol) -> c_int;
     pub fn bdf_download(ctx: *mut BdfCtx, col: *const BdfCol, out: *mut BdfOut) -> c_int;
     pub fn bdf_col_free(ctx: *mut BdfCtx, col: *mut BdfCol);
+    // DataFrame::sort
+    pub fn bdf_sort_indices_dev(ctx: *mut BdfCtx, n_keys: i32, keys: *const BdfSortKey, indices: *mut *mut BdfCol) -> c_int;
+    pub fn bdf_take_dev(ctx: *mut BdfCtx, values: *const BdfCol, indices: *const BdfCol, out: *mut *mut BdfCol) -> c_int;
     // Arrow IPC files (DataFrame::from_arrow / to_arrow)
     pub fn bdf_ipc_open(path: *const c_char, out: *mut *mut BdfIpc) -> c_int;
     pub fn bdf_ipc_close(file: *mut BdfIpc);
