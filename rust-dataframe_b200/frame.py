@@ -1,0 +1,375 @@
+"""Device-resident mirror of the reference's lazy evaluator for the transformations on the path.
+
+``Evaluate::evaluate`` (src/evaluation.rs:66-96) walks a list of Transformations and rebuilds the DataFrame after each
+one; ``Evaluate::calculate`` (:97-323) dispatches a Calculation to ScalarFunctions / cast and appends the result with
+``with_column``.  ``DeviceFrame`` does the same with columns that live in HBM (one ``Column`` per name, one chunk per
+RecordBatch), so a pipeline of Calculations, filters and a sort never crosses PCIe between steps:
+
+    frame = DeviceFrame.from_arrow("in.arrow")                        # DataFrame::from_arrow
+    frame = frame.evaluate([calculate("add", ["a", "b"], "e"), ..., select(["h"])])
+    frame.to_arrow("out.arrow")                                       # DataFrame::to_arrow
+
+``plan_fusion`` is the optimiser pass SURVEY 8(f) N3 asks for (the natural neighbour of src/optimiser.rs): a run of
+consecutive Float64 Calculations whose intermediate columns are removed by a later Select/Drop before anything else
+reads them is replaced by ONE fused step (``bdf_eval_expr_dev``); what the caller can observe does not change.
+The planner is plain host logic (tested without a GPU); everything that touches data goes through the C ABI.
+
+Kept as the reference has it: select/drop keep frame order (:258-330), with_column replaces an existing name by
+drop + append (:97-113), arithmetic Calculations exist for the 8 types of calculate's match (Int8/UInt8 panic with
+"Unsupported operation"), trig for floats only, GroupAggregate panics.  Different on purpose: ``limit`` gathers the
+first rows into one chunk (the reference slices chunks zero-copy), Join is not mirrored (src/functions/join.rs emits
+its pairs in HashMap iteration order and hashes null rows with truncated keys -- there is no single right answer
+to be identical to).
+"""
+from __future__ import annotations
+
+from collections import OrderedDict
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import _native as N
+from .arrays import F32, F64, I8, U8, PrimitiveArray, is_float
+from .functions import Column, eval_expr, sort_indices
+from .ipc import BOOL, IpcFile, write_ipc
+
+ARITH = {"add": N.ADD, "subtract": N.SUB, "multiply": N.MUL, "divide": N.DIV}
+TRIG = {"sine": "sin", "cosine": "cos", "tangent": "tan"}
+CMP = {"gt": N.GT, "ge": N.GE, "eq": N.EQ, "ne": N.NE, "lt": N.LT, "le": N.LE}
+FLIP = {"gt": "lt", "ge": "le", "lt": "gt", "le": "ge", "eq": "eq", "ne": "ne"}
+
+
+@dataclass
+class Calculation:
+    """expression.rs:410-416: inputs by name, one output column, a Function."""
+    function: str                      # add | subtract | multiply | divide | sine | cosine | tangent | cast | rename
+    inputs: List[str]
+    output: str
+    dtype: Optional[int] = None        # output type (cast: the target; others: the inputs' type)
+
+
+@dataclass
+class Fused:
+    """A run of Calculations the planner merged: slots 0..len(inputs)-1 are input columns, node k is slot len(inputs)+k."""
+    inputs: List[str]
+    nodes: List[tuple]
+    output: str
+    replaced: List[Calculation] = field(default_factory=list)
+
+
+def calculate(function: str, inputs: Sequence[str], output: str, dtype: Optional[int] = None):
+    return ("calculate", Calculation(function, list(inputs), output, dtype))
+
+
+def select(names: Sequence[str]):
+    return ("select", list(names))
+
+
+def drop(names: Sequence[str]):
+    return ("drop", list(names))
+
+
+def filter_(condition):
+    return ("filter", condition)
+
+
+def limit(n: int):
+    return ("limit", int(n))
+
+
+def sort(criteria: Sequence[Tuple[str, bool]]):
+    """criteria: [(column, descending)] -- SortCriteria::nulls_first is ignored by the reference (dataframe.rs:205-208)."""
+    return ("sort", [(c, bool(d)) for c, d in criteria])
+
+
+# ---- BooleanFilter (expression.rs:752-763) as nested tuples: ("col", name) | ("scalar", v) | ("not", x) | ("and", a, b) | ("gt", a, b) ...
+def col(name: str):
+    return ("col", name)
+
+
+def lit(v: float):
+    return ("scalar", float(v))
+
+
+def _filter_columns(cond) -> set:
+    if cond[0] == "col":
+        return {cond[1]}
+    if cond[0] == "scalar":
+        return set()
+    out = set()
+    for x in cond[1:]:
+        out |= _filter_columns(x)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# the optimiser pass: which Calculations can be evaluated in one fused step
+
+def _columns_read(t) -> set:
+    kind, arg = t
+    if kind == "calculate":
+        return set(arg.inputs)
+    if kind == "fused":
+        return set(arg.inputs)
+    if kind == "filter":
+        return _filter_columns(arg)
+    if kind == "sort":
+        return {c for c, _ in arg}
+    return set()
+
+
+def _needed_after(transformations: Sequence[tuple], final_columns: Sequence[str]) -> List[set]:
+    """needed[i] = names whose VALUES can still be observed after step i (read by a later step or present at the end)."""
+    needed = [set() for _ in transformations]
+    live = set(final_columns)
+    for i in range(len(transformations) - 1, -1, -1):
+        needed[i] = set(live)
+        kind, arg = transformations[i]
+        if kind == "select":
+            live = set(live) if "*" in arg else {n for n in live if n in arg}
+        elif kind == "drop":
+            live = set(live)            # a dropped name is not in `live` here unless a later step re-creates it
+        elif kind == "calculate":
+            if arg.function == "rename":
+                live = (live - {arg.output}) | {arg.inputs[0]}
+            else:
+                live = (live - {arg.output}) | set(arg.inputs)   # a Calculation is kept even when its output is dead:
+        else:                                                   # its DivideByZero panic is observable
+            live = live | _columns_read(transformations[i])
+    return needed
+
+
+def _schema_walk(schema: "OrderedDict[str, int]", transformations: Sequence[tuple]) -> List["OrderedDict[str, int]"]:
+    """Schema BEFORE each step (and after the last one as the final element)."""
+    out = []
+    cur = OrderedDict(schema)
+    for kind, arg in transformations:
+        out.append(OrderedDict(cur))
+        if kind == "select":
+            cur = OrderedDict((n, t) for n, t in cur.items() if "*" in arg or n in arg)
+        elif kind == "drop":
+            cur = OrderedDict((n, t) for n, t in cur.items() if n not in arg)
+        elif kind == "calculate":
+            if arg.function == "rename":
+                cur = OrderedDict(((arg.output if n == arg.inputs[0] else n), t) for n, t in cur.items())
+            else:
+                t = arg.dtype if arg.function == "cast" else cur.get(arg.inputs[0], F64)
+                cur.pop(arg.output, None)
+                cur[arg.output] = t
+    out.append(cur)
+    return out
+
+
+def _fusable(calc: Calculation, schema) -> bool:
+    if calc.function not in ARITH and calc.function not in TRIG:
+        return False
+    return all(schema.get(n) == F64 for n in calc.inputs)
+
+
+def plan_fusion(schema: "OrderedDict[str, int]", transformations: Sequence[tuple], max_inputs: int = 6, max_nodes: int = 12) -> List[tuple]:
+    """Rewrite ``transformations``: runs of fusable Calculations whose intermediates nobody can observe become one
+    ("fused", Fused) step.  The result evaluates to the same frame (same columns, same order, same values)."""
+    steps = list(transformations)
+    schemas = _schema_walk(schema, steps)
+    needed = _needed_after(steps, list(schemas[-1].keys()))
+    out: List[tuple] = []
+    i = 0
+    while i < len(steps):
+        kind, arg = steps[i]
+        if kind != "calculate" or not _fusable(arg, schemas[i]):
+            out.append(steps[i]); i += 1
+            continue
+        j = i
+        while j + 1 < len(steps) and steps[j + 1][0] == "calculate" and _fusable(steps[j + 1][1], schemas[j + 1]):
+            j += 1
+        fused = None
+        while j > i and fused is None:
+            fused = _try_fuse([s[1] for s in steps[i:j + 1]], needed[j], max_inputs, max_nodes)
+            if fused is None:
+                j -= 1
+        if fused is None:
+            out.append(steps[i]); i += 1
+        else:
+            out.append(("fused", fused)); i = j + 1
+    return out
+
+
+def _try_fuse(run: List[Calculation], needed_after_run: set, max_inputs: int, max_nodes: int) -> Optional[Fused]:
+    if len(run) > max_nodes:
+        return None
+    outputs = [c.output for c in run]
+    final = run[-1].output
+    if len(set(outputs)) != len(outputs):
+        return None                                   # a name produced twice inside the run: keep it simple, do not fuse
+    inputs: List[str] = []
+    produced: Dict[str, int] = {}
+    nodes: List[tuple] = []
+    used = set()
+    for k, c in enumerate(run):
+        ops = []
+        for name in c.inputs:
+            if name in produced:
+                ops.append(("node", produced[name])); used.add(name)
+            else:
+                if name not in inputs:
+                    inputs.append(name)
+                ops.append(("in", inputs.index(name)))
+        nodes.append((c.function, ops))
+        produced[c.output] = k
+    if len(inputs) > max_inputs:
+        return None
+    for name in outputs[:-1]:
+        if name in needed_after_run or name not in used or name in inputs:
+            return None                               # observable later, dead inside the run, or shadows an input
+    if final in inputs:
+        return None
+    ni = len(inputs)
+    slot = lambda o: o[1] if o[0] == "in" else ni + o[1]
+    prog = []
+    for fn, ops in nodes:
+        if fn in ARITH:
+            prog.append((ARITH[fn], slot(ops[0]), slot(ops[1])))
+        else:
+            prog.append((TRIG[fn], slot(ops[0])))
+    return Fused(inputs, prog, final, list(run))
+
+
+# ---------------------------------------------------------------------------------------------------------
+
+class DeviceFrame:
+    """Ordered name -> Column; every column has the same chunk lengths (the frame's RecordBatches)."""
+
+    def __init__(self, columns: "OrderedDict[str, Column]"):
+        self.columns: "OrderedDict[str, Column]" = OrderedDict(columns)
+
+    # -- construction / export --
+    @classmethod
+    def from_arrow(cls, path: str, columns: Optional[Sequence[str]] = None, ctx: Optional[N.Context] = None) -> "DeviceFrame":
+        with IpcFile(path) as f:
+            names = [n for n, dt, _ in f.schema if dt >= 0 and (columns is None or n in columns)]
+            cols = f.read(names, ctx=ctx)
+        return cls(OrderedDict((n, cols[n]) for n in names))
+
+    @classmethod
+    def from_host(cls, columns: Dict[str, list], ctx: Optional[N.Context] = None) -> "DeviceFrame":
+        names = list(columns)
+        cols = Column.upload_many([columns[n] for n in names], ctx=ctx)
+        return cls(OrderedDict(zip(names, cols)))
+
+    def to_arrow(self, path: str) -> None:
+        write_ipc(path, dict(self.columns))
+
+    def to_host(self) -> Dict[str, list]:
+        return {n: c.download() for n, c in self.columns.items()}
+
+    @property
+    def schema(self) -> "OrderedDict[str, int]":
+        return OrderedDict((n, c.dtype) for n, c in self.columns.items())
+
+    def column(self, name: str) -> Column:
+        if name not in self.columns:
+            raise N.ReferencePanic(f"column {name!r} not found (column_by_name panics)")
+        return self.columns[name]
+
+    # -- DataFrame methods --
+    def with_column(self, name: str, column: Column) -> "DeviceFrame":
+        cols = OrderedDict((n, c) for n, c in self.columns.items() if n != name)
+        cols[name] = column
+        return DeviceFrame(cols)
+
+    def select(self, names: Sequence[str]) -> "DeviceFrame":
+        return DeviceFrame(OrderedDict((n, c) for n, c in self.columns.items() if "*" in names or n in names))
+
+    def drop(self, names: Sequence[str]) -> "DeviceFrame":
+        return DeviceFrame(OrderedDict((n, c) for n, c in self.columns.items() if n not in names))
+
+    def filter(self, cond) -> "DeviceFrame":
+        mask = self._boolean(cond)
+        return DeviceFrame(OrderedDict((n, c.filter(mask)) for n, c in self.columns.items()))
+
+    def sort(self, criteria: Sequence[Tuple[str, bool]]) -> "DeviceFrame":
+        if not criteria:
+            raise N.ComputeError("Sort criteria cannot be empty")
+        idx = sort_indices([(self.column(c), d) for c, d in criteria])
+        return DeviceFrame(OrderedDict((n, c.take(idx)) for n, c in self.columns.items()))
+
+    def limit(self, count: int) -> "DeviceFrame":
+        if not self.columns:
+            return self
+        first = next(iter(self.columns.values()))
+        n = min(int(count), len(first))
+        idx = Column.upload([PrimitiveArray.from_numpy(np.arange(n, dtype=np.uint32))], ctx=first.ctx)
+        return DeviceFrame(OrderedDict((name, c.take(idx)) for name, c in self.columns.items()))
+
+    def _boolean(self, cond) -> Column:
+        kind = cond[0]
+        if kind == "col":
+            c = self.column(cond[1])
+            if c.dtype != BOOL:
+                raise N.UnsupportedType("a BooleanFilter input column must be Boolean unless it is compared")
+            return c
+        if kind == "not":
+            return self._boolean(cond[1]).logical_not()
+        if kind in ("and", "or"):
+            a, b = self._boolean(cond[1]), self._boolean(cond[2])
+            return a.logical_and(b) if kind == "and" else a.logical_or(b)
+        if kind in CMP:
+            l, r = cond[1], cond[2]
+            if l[0] == "scalar" and r[0] == "col":
+                kind, l, r = FLIP[kind], r, l
+            if l[0] != "col":
+                raise N.UnsupportedType("comparison needs a column on one side")
+            left = self.column(l[1])
+            if r[0] == "col":
+                return left.compare(CMP[kind], self.column(r[1]))
+            if r[0] == "scalar":
+                return left.compare(CMP[kind], r[1])
+        raise N.UnsupportedType(f"BooleanFilter node {kind!r} is not on the path")
+
+    def calculate(self, calc: Calculation) -> "DeviceFrame":
+        fn = calc.function
+        if fn == "rename":
+            return DeviceFrame(OrderedDict(((calc.output if n == calc.inputs[0] else n), c) for n, c in self.columns.items()))
+        cols = [self.column(n) for n in calc.inputs]
+        if fn in ARITH:
+            if cols[0].dtype in (I8, U8) or cols[0].dtype == BOOL:
+                raise N.ReferencePanic("Unsupported operation")          # evaluation.rs:116-244 has no Int8/UInt8 arm
+            out = cols[0]._bin(ARITH[fn], cols[1])
+        elif fn in TRIG:
+            if not is_float(cols[0].dtype):
+                raise N.ReferencePanic(f"Expecting float datatype for operation, found {cols[0].dtype}")
+            out = getattr(cols[0], TRIG[fn])()
+        elif fn == "cast":
+            out = cols[0].cast(calc.dtype)
+        else:
+            raise N.ReferencePanic(f"Function {fn!r} not supported")
+        return self.with_column(calc.output, out)
+
+    def evaluate(self, transformations: Sequence[tuple], fuse: bool = True) -> "DeviceFrame":
+        steps = plan_fusion(self.schema, transformations) if fuse else list(transformations)
+        frame = self
+        for kind, arg in steps:
+            if kind == "calculate":
+                frame = frame.calculate(arg)
+            elif kind == "fused":
+                try:
+                    frame = frame.with_column(arg.output, eval_expr([frame.column(n) for n in arg.inputs], arg.nodes))
+                except N.UnsupportedType:      # e.g. more than two live intermediates: run the Calculations one by one
+                    for calc in arg.replaced:
+                        frame = frame.calculate(calc)
+            elif kind == "select":
+                frame = frame.select(arg)
+            elif kind == "drop":
+                frame = frame.drop(arg)
+            elif kind == "filter":
+                frame = frame.filter(arg)
+            elif kind == "limit":
+                frame = frame.limit(arg)
+            elif kind == "sort":
+                frame = frame.sort(arg)
+            elif kind == "group_aggregate":
+                raise N.ReferencePanic("aggregations not supported")       # evaluation.rs:73
+            else:
+                raise N.UnsupportedType(f"transformation {kind!r} is not on the path")
+        return frame

@@ -1,0 +1,178 @@
+"""The lazy-evaluator mirror (rust-dataframe_b200/frame.py): Evaluate::evaluate / calculate (src/evaluation.rs:66-323)
+over device columns, and the fusion pass of SURVEY 8(f) N3.  The planner is host logic (no GPU); the data tests
+compare a fused evaluation with the step-by-step one (bit for bit) and with the oracle."""
+from collections import OrderedDict
+
+import numpy as np
+import pytest
+
+from helpers import assert_same_array, random_mask
+
+
+def chain():
+    from rust_dataframe_b200.frame import calculate
+    return [calculate("add", ["a", "b"], "e"), calculate("multiply", ["e", "c"], "f"), calculate("divide", ["f", "d"], "g"),
+            calculate("sine", ["g"], "h")]
+
+
+def schema_of(rdf, **cols):
+    return OrderedDict((k, getattr(rdf, v)) for k, v in cols.items())
+
+
+def kinds(plan):
+    return [k for k, _ in plan]
+
+
+def test_planner_fuses_only_what_nobody_can_observe(rdf):
+    F = rdf.frame
+    sch = schema_of(rdf, a="F64", b="F64", c="F64", d="F64")
+    plan = F.plan_fusion(sch, chain() + [F.select(["h"])])
+    assert kinds(plan) == ["fused", "select"]
+    fused = plan[0][1]
+    assert fused.inputs == ["a", "b", "c", "d"] and fused.output == "h" and len(fused.replaced) == 4
+    N = rdf.native
+    assert fused.nodes == [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)]
+    # nothing removes e, f, g: they are columns of the result, every Calculation stays
+    assert kinds(F.plan_fusion(sch, chain())) == ["calculate"] * 4
+    # drop instead of select; an unrelated sort and filter in between do not keep the intermediates alive
+    plan = F.plan_fusion(sch, chain() + [F.sort([("h", True)]), F.filter_(("gt", F.col("a"), F.lit(0.0))), F.drop(["e", "f", "g"])])
+    assert kinds(plan) == ["fused", "sort", "filter", "drop"]
+    # ... but a filter that READS g does: the run is cut after g, which stays a real column
+    plan = F.plan_fusion(sch, chain() + [F.filter_(("lt", F.col("g"), F.lit(1.0))), F.select(["h"])])
+    assert kinds(plan) == ["fused", "calculate", "filter", "select"]
+    assert plan[0][1].output == "g" and len(plan[0][1].replaced) == 3 and plan[1][1].function == "sine"
+    # f kept by the final select: e can still be fused away into f; g is fused into h
+    plan = F.plan_fusion(sch, chain() + [F.select(["f", "h"])])
+    assert kinds(plan) == ["fused", "fused", "select"]
+    assert [p[1].output for p in plan[:2]] == ["f", "h"] and plan[1][1].inputs == ["f", "d"]
+
+
+def test_planner_type_and_size_rules(rdf):
+    F = rdf.frame
+    # integer arithmetic and casts are not fusable; the Float64 tail after the cast is
+    sch = schema_of(rdf, i="I64", j="I64", x="F64")
+    steps = [F.calculate("add", ["i", "j"], "k"), F.calculate("cast", ["k"], "kf", rdf.F64), F.calculate("multiply", ["kf", "x"], "m"),
+             F.calculate("cosine", ["m"], "n"), F.select(["n"])]
+    plan = F.plan_fusion(sch, steps)
+    assert kinds(plan) == ["calculate", "calculate", "fused", "select"] and plan[2][1].inputs == ["kf", "x"]
+    # Float32 chains are left alone (the fused kernel is Float64)
+    assert kinds(F.plan_fusion(schema_of(rdf, a="F32", b="F32"), [F.calculate("add", ["a", "b"], "e"), F.calculate("sine", ["e"], "h"), F.select(["h"])])) \
+        == ["calculate", "calculate", "select"]
+    # more than 12 nodes: the run is split, every piece still correct on its own
+    sch = schema_of(rdf, a="F64", b="F64")
+    long = [F.calculate("add", ["a", "b"], "t0")] + [F.calculate("multiply", [f"t{k}", "b"], f"t{k + 1}") for k in range(15)] + [F.select(["t15"])]
+    plan = F.plan_fusion(sch, long)
+    assert kinds(plan) == ["fused", "fused", "select"] and len(plan[0][1].replaced) + len(plan[1][1].replaced) == 16
+    assert all(len(p[1].nodes) <= 12 for p in plan[:2])
+    # more than 6 distinct inputs
+    sch = schema_of(rdf, **{f"c{k}": "F64" for k in range(9)})
+    wide = [F.calculate("add", ["c0", "c1"], "s1")] + [F.calculate("add", [f"s{k}", f"c{k + 1}"], f"s{k + 1}") for k in range(1, 8)] + [F.select(["s8"])]
+    plan = F.plan_fusion(sch, wide)
+    assert all(k in ("fused", "calculate", "select") for k in kinds(plan))
+    assert all(len(p[1].inputs) <= 6 for p in plan if p[0] == "fused") and kinds(plan)[0] == "fused"
+    # an intermediate that overwrites an input of the run, a name produced twice, a dead intermediate: not fused
+    sch = schema_of(rdf, a="F64", b="F64")
+    assert "fused" not in kinds(F.plan_fusion(sch, [F.calculate("add", ["a", "b"], "a"), F.calculate("sine", ["a"], "h"), F.select(["h"])]))
+    assert "fused" not in kinds(F.plan_fusion(sch, [F.calculate("add", ["a", "b"], "e"), F.calculate("subtract", ["a", "b"], "e"), F.select(["e"])]))
+    assert "fused" not in kinds(F.plan_fusion(sch, [F.calculate("divide", ["a", "b"], "e"), F.calculate("sine", ["a"], "h"), F.select(["h"])]))
+    # rename and select("*")
+    plan = F.plan_fusion(sch, [F.calculate("add", ["a", "b"], "e"), F.calculate("sine", ["e"], "h"), F.calculate("rename", ["h"], "out"), F.select(["*"])])
+    assert kinds(plan) == ["calculate", "calculate", "calculate", "select"]      # e is still visible through "*"
+
+
+# ---- data -----------------------------------------------------------------------------------------------
+
+def host_frame(rdf, rng, lens, nulls=True):
+    def colf(lo, hi, nf):
+        out = []
+        for n in lens:
+            a = rdf.PrimitiveArray.from_numpy(rng.uniform(lo, hi, n), random_mask(rng, n, nf) if nf else None)
+            out.append(a)
+        return out
+    return OrderedDict([("a", colf(-50, 50, 0)), ("b", colf(-50, 50, 0.2 if nulls else 0)), ("c", colf(-5, 5, 0)), ("d", colf(1, 9, 0.1 if nulls else 0)),
+                        ("k", [rdf.PrimitiveArray.from_numpy(rng.integers(-3, 4, n).astype(np.int32), random_mask(rng, n, 0.1)) for n in lens])])
+
+
+def frames_equal(x, y):
+    assert list(x.columns) == list(y.columns)
+    hx, hy = x.to_host(), y.to_host()
+    for name in hx:
+        assert len(hx[name]) == len(hy[name]), name
+        for cx, cy in zip(hx[name], hy[name]):
+            assert cx.length == cy.length, name
+            m = cx.valid_mask()
+            assert np.array_equal(m, cy.valid_mask()), name
+            vx, vy = cx.value_slice()[m], cy.value_slice()[m]
+            assert np.array_equal(vx.view(f"u{vx.dtype.itemsize}"), vy.view(f"u{vy.dtype.itemsize}")), name
+
+
+@pytest.mark.gpu
+def test_fused_and_stepwise_evaluation_agree(rdf, ctx, oracle):
+    F = rdf.frame
+    rng = np.random.default_rng(8)
+    lens = [0, 1, 2049, 70_001]
+    host = host_frame(rdf, rng, lens)
+    frame = rdf.DeviceFrame.from_host(host)
+    pipelines = [
+        chain() + [F.select(["a", "h"])],
+        chain() + [F.filter_(("and", ("gt", F.col("h"), F.lit(-0.5)), ("not", ("lt", F.col("k"), F.lit(0.0))))), F.sort([("k", True), ("h", False)]),
+                   F.drop(["e", "f", "g", "b"])],
+        [F.calculate("cast", ["k"], "kf", rdf.F64), F.calculate("multiply", ["kf", "a"], "m"), F.calculate("subtract", ["m", "c"], "n"),
+         F.calculate("tangent", ["n"], "t"), F.limit(1000), F.select(["k", "t"])],
+        chain() + [F.calculate("rename", ["h"], "out"), F.select(["out", "f"])],
+    ]
+    for steps in pipelines:
+        plan = F.plan_fusion(frame.schema, steps)
+        assert "fused" in [k for k, _ in plan]
+        frames_equal(frame.evaluate(steps, fuse=True), frame.evaluate(steps, fuse=False))
+    # against the oracle: the first pipeline, chunk by chunk
+    got = frame.evaluate(pipelines[0]).to_host()
+    assert list(got) == ["a", "h"]
+    for i in range(len(lens)):
+        _, e = oracle.col_binary(oracle.ADD, oracle.F64, [host["a"][i]], [host["b"][i]])
+        _, f = oracle.col_binary(oracle.MUL, oracle.F64, e, [host["c"][i]])
+        st, g = oracle.col_binary(oracle.DIV, oracle.F64, f, [host["d"][i]])
+        assert st == oracle.OK
+        _, h = oracle.col_unary(oracle.SIN, oracle.F64, g)
+        assert_same_array(got["h"][i], h[0], what=f"pipeline h chunk {i}", exact=False, max_ulp=3, check_payload=False)
+
+
+@pytest.mark.gpu
+def test_evaluator_rules_and_arrow_round_trip(rdf, ctx, tmp_path):
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    import pyarrow.ipc
+
+    F = rdf.frame
+    rng = np.random.default_rng(4)
+    n = 50_000
+    t = pa.table({"a": pa.array(rng.normal(0, 10, n)), "b": pa.array(rng.normal(0, 10, n), mask=rng.random(n) < 0.1),
+                  "name": pa.array([f"r{i}" for i in range(n)]), "k": pa.array(rng.integers(0, 5, n).astype(np.int8))})
+    src, dst = str(tmp_path / "in.arrow"), str(tmp_path / "out.arrow")
+    with pa.ipc.new_file(src, t.schema) as w:
+        for b in t.to_batches(max_chunksize=12_345):
+            w.write_batch(b)
+    frame = rdf.DeviceFrame.from_arrow(src)
+    assert list(frame.columns) == ["a", "b", "k"]                       # the Utf8 column stays with arrow's reader
+    out = frame.evaluate([F.calculate("subtract", ["a", "b"], "d"), F.calculate("multiply", ["d", "d"], "sq"), F.filter_(("ge", F.col("sq"), F.lit(1.0))),
+                          F.sort([("k", False), ("sq", True)]), F.select(["k", "sq"])])
+    out.to_arrow(dst)
+    got = pa.ipc.open_file(dst).read_all()
+    d = pc.subtract(t["a"], t["b"])
+    sq = pc.multiply(d, d)
+    want = pa.table({"k": t["k"], "sq": sq}).filter(pc.greater_equal(sq, 1.0), null_selection_behavior="drop")
+    want = want.take(pc.sort_indices(want, sort_keys=[("k", "ascending"), ("sq", "descending")], null_placement="at_end"))
+    assert got.column("k").combine_chunks().equals(want.column("k").combine_chunks())
+    assert got.column("sq").combine_chunks().equals(want.column("sq").combine_chunks())
+    # the reference's panics, mirrored
+    with pytest.raises(rdf.ReferencePanic):
+        frame.evaluate([F.calculate("add", ["k", "k"], "kk")])          # Int8: "Unsupported operation"
+    with pytest.raises(rdf.ReferencePanic):
+        frame.evaluate([F.calculate("sine", ["k"], "s")])               # "Expecting float datatype"
+    with pytest.raises(rdf.ReferencePanic):
+        frame.evaluate([("group_aggregate", None)])                     # "aggregations not supported"
+    with pytest.raises(rdf.ReferencePanic):
+        frame.evaluate([F.calculate("add", ["a", "nope"], "x")])
+    with pytest.raises(rdf.DivideByZero):
+        frame.evaluate([F.calculate("subtract", ["a", "a"], "z"), F.calculate("divide", ["a", "z"], "q"), F.select(["q"])])
+    assert list(frame.evaluate([F.calculate("add", ["a", "b"], "a")]).columns) == ["b", "k", "a"]   # with_column: drop + append
