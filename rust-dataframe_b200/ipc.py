@@ -32,7 +32,7 @@ class IpcFile:
         for i in range(self.num_columns):
             name, dt, nl = C.c_char_p(), C.c_int32(), C.c_int32()
             N.raise_for_status(N.lib().bdf_ipc_column(self.handle, i, C.byref(name), C.byref(dt), C.byref(nl)))
-            self.schema.append((name.value.decode(), dt.value, bool(nl.value)))
+            self.schema.append((name.value.decode("utf-8", "replace"), dt.value, bool(nl.value)))
 
     # -- lifetime --
     def close(self) -> None:

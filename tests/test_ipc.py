@@ -317,3 +317,40 @@ def test_large_file_read_1e7(rdf, ctx, tmp_path):
     assert abs(agg["sum"] - tot) <= 1e-6
     for bi, g in enumerate(c.download()):
         check_view_against_pyarrow(g, want[bi], f"a+b batch {bi}")
+
+
+def test_reader_survives_corrupted_files(rdf, tmp_path):
+    """Every offset in the footer and the messages is bounds-checked: a damaged file is an error (or still readable),
+    never a crash, and a view that is handed out stays inside the mapping."""
+    rng = np.random.default_rng(99)
+    schema, batches = mixed_batches(rng, [3, 40, 300])
+    good = str(tmp_path / "good.arrow")
+    write_file(good, schema, batches)
+    raw = np.frombuffer(open(good, "rb").read(), dtype=np.uint8)
+    # metadata lives in the footer (file end) and in the message headers; damage both regions, and the body a little
+    footer_len = int(np.frombuffer(raw[-10:-6].tobytes(), np.int32)[0])
+    regions = [(len(raw) - 10 - footer_len, len(raw) - 6), (8, 2000)]
+    opened = failed = 0
+    for trial in range(400):
+        bad = raw.copy()
+        lo, hi = regions[trial % 2]
+        for _ in range(int(rng.integers(1, 6))):
+            pos = int(rng.integers(lo, hi))
+            bad[pos] = rng.integers(0, 256) if trial % 3 else (0xFF if bad[pos] != 0xFF else 0x7F)
+        p = str(tmp_path / "bad.arrow")
+        bad.tofile(p)
+        try:
+            with rdf.IpcFile(p) as f:
+                opened += 1
+                for bi in range(f.num_batches):
+                    for name, dtype, _ in f.schema:
+                        if dtype >= 0:
+                            v = f.view(bi, name)
+                            if v.length:          # touching first and last byte must be legal
+                                _ = v.values[0] if dtype != 10 else v.values[(v.length - 1) // 8]
+                                _ = v.value_slice()[-1] if dtype != 10 else v.values[0]
+                                if v.validity is not None:
+                                    _ = v.validity[(v.length - 1) // 8]
+        except rdf.ArrowError:
+            failed += 1
+    assert opened + failed == 400 and failed > 50
