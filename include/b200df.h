@@ -167,8 +167,10 @@ int  bdf_filter_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* mask, bd
 /* ---- N3: consecutive Calculations fused into one pass -----------------------------------------------------------
  * Evaluate::evaluate (src/evaluation.rs:66-96) materialises every Calculation; when the intermediates are not kept, the
  * chain can be evaluated per element in ONE kernel: inputs are read once, only the final column is written
- * (config 2: 40 B/row instead of 88).  The program is straight-line: slots 0..n_inputs-1 are the input columns
- * (Float64), node k writes slot n_inputs+k and may read any earlier slot; the last node is the result.  Every node
+ * (config 2: 40 B/row instead of 88).  The program is straight-line: slots 0..n_inputs-1 are the input columns,
+ * node k writes slot n_inputs+k and may read any earlier slot; the last node is the result (Float64).  An input column
+ * of another numeric type is read through `as f64` -- a Function::Cast to Float64 (never fails, validity unchanged)
+ * folded into the load.  Every node
  * is the same operator the unfused call would run, so arithmetic chains are bit-identical; DivideByZero is raised iff
  * a slot valid for that divide node has a zero divisor.  At most 6 inputs and 12 nodes. */
 #define BDF_EXPR_UNARY 100 /* node.op = bdf_binop for binary nodes, BDF_EXPR_UNARY + bdf_unop for unary nodes (operand a) */

@@ -32,9 +32,10 @@ constexpr int kExprMaxTemps = 2;
 struct ExprProg {
     int n_inputs, n_ins, n_slots;   // n_slots = inputs + temporaries the program uses
     uint8_t op[kExprMaxIns], src[kExprMaxIns];
+    uint8_t in_dtype[kExprMaxInputs];   // element type of every input column (read through `as f64`: Function::Cast to Float64)
 };
 struct ExprDesc {
-    const double* in[kExprMaxInputs];
+    const void* in[kExprMaxInputs];
     const uint32_t* vin[kExprMaxInputs];
     int32_t off[kExprMaxInputs];
     double* out; uint32_t* vout;
@@ -100,6 +101,48 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
     const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gsrc) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+    const unsigned saddr = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(saddr), "l"(gsrc) : "memory");
+}
+// The two elements a lane staged for one step, as doubles.  Non-Float64 inputs were staged as raw bytes (2 x width in
+// the low bytes of the 16-byte slot) and are converted here: the infallible `as f64` of Function::Cast to Float64.
+__device__ __forceinline__ Vec<double, 2> expr_as_f64(int t, const Vec<double, 2>& raw) {
+    if (t == T_F64) return raw;
+    const unsigned long long lo = (unsigned long long)__double_as_longlong(raw.e[0]), hi = (unsigned long long)__double_as_longlong(raw.e[1]);
+    const uint32_t w0 = (uint32_t)lo, w1 = (uint32_t)(lo >> 32);
+    Vec<double, 2> r;
+    switch (t) {
+        case T_I64: r.e[0] = (double)(long long)lo; r.e[1] = (double)(long long)hi; break;
+        case T_U64: r.e[0] = (double)lo; r.e[1] = (double)hi; break;
+        case T_F32: r.e[0] = (double)__uint_as_float(w0); r.e[1] = (double)__uint_as_float(w1); break;
+        case T_I32: r.e[0] = (double)(int)w0; r.e[1] = (double)(int)w1; break;
+        case T_U32: r.e[0] = (double)w0; r.e[1] = (double)w1; break;
+        case T_I16: r.e[0] = (double)(short)(w0 & 0xffffu); r.e[1] = (double)(short)(w0 >> 16); break;
+        case T_U16: r.e[0] = (double)(w0 & 0xffffu); r.e[1] = (double)(w0 >> 16); break;
+        case T_I8: r.e[0] = (double)(signed char)(w0 & 0xffu); r.e[1] = (double)(signed char)((w0 >> 8) & 0xffu); break;
+        default: r.e[0] = (double)(w0 & 0xffu); r.e[1] = (double)((w0 >> 8) & 0xffu); break;
+    }
+    return r;
+}
+__device__ __forceinline__ double expr_load1(int t, const void* __restrict__ p, int64_t i) {
+    switch (t) {
+        case T_F64: return ((const double*)p)[i];
+        case T_I64: return (double)((const long long*)p)[i];
+        case T_U64: return (double)((const unsigned long long*)p)[i];
+        case T_F32: return (double)((const float*)p)[i];
+        case T_I32: return (double)((const int*)p)[i];
+        case T_U32: return (double)((const unsigned*)p)[i];
+        case T_I16: return (double)((const short*)p)[i];
+        case T_U16: return (double)((const unsigned short*)p)[i];
+        case T_I8: return (double)((const signed char*)p)[i];
+        default: return (double)((const unsigned char*)p)[i];
+    }
+}
 __device__ __forceinline__ void cp_async_wait_all() {
     asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
 }
@@ -140,7 +183,9 @@ __device__ __forceinline__ void expr_dispatch(int op, Vec<double, 2> (&out)[U], 
 
 // AGG: also fold sum/count of the RESULT column into one partial per tile (k_finish folds them, like K5); the result
 // column itself is optional then (d.out == nullptr: aggregate only, nothing is written but the partials).
-template <int U, int MINB, bool AGG>
+// TYPED: some input column is not Float64 (raw bytes are staged, `as f64` happens at operand fetch); the all-Float64
+// instantiation carries none of that code (with it, 64 registers spill in the node loop: 1.16 ms instead of 0.85 ms on config 2).
+template <int U, int MINB, bool AGG, bool TYPED>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, uint32_t* __restrict__ warp_counts, int* __restrict__ flags,
        AggDev* __restrict__ tile_partials) {
@@ -166,16 +211,24 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
     if (full) {
         // All descriptor fields first (independent loads, one latency), then every copy, then the validity words:
         // a rolled loop here serialises n_inputs descriptor->copy round trips before the tile is in flight.
-        const double* in[kExprMaxInputs];
+        const char* in[kExprMaxInputs];
         const uint32_t* vin[kExprMaxInputs];
         int32_t off[kExprMaxInputs];
 #pragma unroll
-        for (int i = 0; i < kExprMaxInputs; i++) { in[i] = d.in[i]; vin[i] = d.vin[i]; off[i] = d.off[i]; }
+        for (int i = 0; i < kExprMaxInputs; i++) { in[i] = (const char*)d.in[i]; vin[i] = d.vin[i]; off[i] = d.off[i]; }
 #pragma unroll
         for (int i = 0; i < kExprMaxInputs; i++)
             if (i < ni) {
+                const int w = TYPED ? dtype_width(prog.in_dtype[i]) : 8;   // warp-uniform
 #pragma unroll
-                for (int j = 0; j < U; j++) cp_async16(&sv[(i * U + j) * kThreads + tid], in[i] + e_first + (int64_t)j * kThreads * E);
+                for (int j = 0; j < U; j++) {
+                    void* dst = &sv[(i * U + j) * kThreads + tid];
+                    const char* src = in[i] + (e_first + (int64_t)j * kThreads * E) * w;
+                    if (w == 8) cp_async16(dst, src);
+                    else if (w == 4) cp_async8(dst, src);
+                    else if (w == 2) cp_async4(dst, src);
+                    else *reinterpret_cast<uint16_t*>(dst) = ld_stream2(src);
+                }
             }
         asm volatile("cp.async.commit_group;\n" ::: "memory");
 #pragma unroll
@@ -204,7 +257,7 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
                 x.e[0] = 0.0; x.e[1] = 0.0;
                 if (in_range) {
 #pragma unroll
-                    for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) x.e[e] = d.in[i][e0 + e];
+                    for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) x.e[e] = expr_load1(TYPED ? (int)prog.in_dtype[i] : (int)T_F64, d.in[i], e0 + e);
                     if (d.vin[i]) in_range &= load_bits<E>(d.vin[i], d.off[i] + e0);
                 }
                 sv[(i * U + j) * kThreads + tid] = x;
@@ -235,8 +288,9 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
 #pragma unroll
                 for (int j = 0; j < U; j++) o[j] = acc[j];
             } else {
+                const int t = (TYPED && full && src < ni) ? (int)prog.in_dtype[src] : (int)T_F64;   // tail tiles and temporaries hold doubles
 #pragma unroll
-                for (int j = 0; j < U; j++) o[j] = sv[(src * U + j) * kThreads + tid];
+                for (int j = 0; j < U; j++) o[j] = expr_as_f64(t, sv[(src * U + j) * kThreads + tid]);
                 om = sm[src * kThreads + tid];
             }
             if (op == XI_LOAD) {
@@ -304,7 +358,7 @@ int expr_max_nodes() { return kExprMaxNodes; }
 size_t expr_desc_size() { return sizeof(ExprDesc); }
 size_t expr_prog_size() { return sizeof(ExprProg); }
 
-void fill_expr_desc(void* base, int64_t i, int n_inputs, const double* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
+void fill_expr_desc(void* base, int64_t i, int n_inputs, const void* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
                     uint32_t* vout, int64_t len, int64_t tile0) {
     ExprDesc* d = (ExprDesc*)base + i;
     for (int k = 0; k < kExprMaxInputs; k++) {
@@ -364,8 +418,9 @@ struct ExprCompiler {
 };
 }  // namespace
 
-int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const int* b, void* prog) {
+int expr_compile(int n_inputs, const int* in_dtypes, int n_nodes, const int* op, const int* a, const int* b, void* prog) {
     ExprProg* p = (ExprProg*)prog;
+    for (int i = 0; i < kExprMaxInputs; i++) p->in_dtype[i] = (uint8_t)(i < n_inputs ? in_dtypes[i] : T_F64);
     ExprCompiler c{};
     c.ni = n_inputs; c.nn = n_nodes; c.op = op; c.a = a; c.b = b; c.p = p;
     p->n_inputs = n_inputs; p->n_ins = 0; p->n_slots = n_inputs;
@@ -382,13 +437,13 @@ int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const i
 
 size_t expr_smem_bytes(const ExprProg& p, int unroll) { return (size_t)p.n_slots * kThreads * ((size_t)unroll * 16 + 4); }
 
-template <int U, int MINB, bool AGG>
+template <int U, int MINB, bool AGG, bool TYPED>
 static cudaError_t launch_expr_u(const ExprDesc* dd, int n_chunks, int64_t tiles, const ExprProg& pp, uint32_t* warp_counts, int* flags,
                                  AggDev* tile_partials, cudaStream_t s) {
-    static const cudaError_t attr = cudaFuncSetAttribute(k_expr<U, MINB, AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    static const cudaError_t attr = cudaFuncSetAttribute(k_expr<U, MINB, AGG, TYPED>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                                          (int)((kExprMaxInputs + kExprMaxTemps) * kThreads * (U * 16 + 4)));
     if (attr != cudaSuccess) return attr;
-    k_expr<U, MINB, AGG><<<(unsigned)tiles, kThreads, expr_smem_bytes(pp, U), s>>>(dd, n_chunks, pp, warp_counts, flags, tile_partials);
+    k_expr<U, MINB, AGG, TYPED><<<(unsigned)tiles, kThreads, expr_smem_bytes(pp, U), s>>>(dd, n_chunks, pp, warp_counts, flags, tile_partials);
     return cudaGetLastError();
 }
 
@@ -399,8 +454,14 @@ cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const vo
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     const ExprDesc* dd = (const ExprDesc*)descs;
     const ExprProg& pp = *(const ExprProg*)prog;
-    if (tile_partials) return launch_expr_u<kExprUnroll, kExprMinCtas, true>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
-    return launch_expr_u<kExprUnroll, kExprMinCtas, false>(dd, n_chunks, tiles, pp, warp_counts, flags, nullptr, s);
+    bool typed = false;
+    for (int i = 0; i < pp.n_inputs; i++) typed = typed || pp.in_dtype[i] != T_F64;
+    if (tile_partials) {
+        if (typed) return launch_expr_u<kExprUnroll, kExprMinCtas, true, true>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
+        return launch_expr_u<kExprUnroll, kExprMinCtas, true, false>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
+    }
+    if (typed) return launch_expr_u<kExprUnroll, kExprMinCtas, false, true>(dd, n_chunks, tiles, pp, warp_counts, flags, nullptr, s);
+    return launch_expr_u<kExprUnroll, kExprMinCtas, false, false>(dd, n_chunks, tiles, pp, warp_counts, flags, nullptr, s);
 }
 
 }  // namespace bdf

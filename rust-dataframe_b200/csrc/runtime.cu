@@ -1246,10 +1246,10 @@ int expr_tile_elems();
 int expr_max_inputs();
 int expr_max_nodes();
 size_t expr_desc_size();
-void fill_expr_desc(void* base, int64_t i, int n_inputs, const double* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
+void fill_expr_desc(void* base, int64_t i, int n_inputs, const void* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
                     uint32_t* vout, int64_t len, int64_t tile0);
 size_t expr_prog_size();
-int expr_compile(int n_inputs, int n_nodes, const int* op, const int* a, const int* b, void* prog);
+int expr_compile(int n_inputs, const int* in_dtypes, int n_nodes, const int* op, const int* a, const int* b, void* prog);
 cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, AggDev* tile_partials,
                         cudaStream_t s);
 }  // namespace bdf
@@ -1273,7 +1273,14 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
     alignas(8) unsigned char prog[256];
     static_assert(sizeof(prog) >= 8 + 2 * 40, "ExprProg must fit");
     if (expr_prog_size() > sizeof(prog)) return fail(BDF_INVALID, "internal: expression program too large");
-    switch (expr_compile(n_inputs, n_nodes, op.data(), a.data(), b.data(), prog)) {
+    for (int i = 0; i < n_inputs; i++)
+        if (!inputs[i]) return fail(BDF_INVALID, "null input column");
+    int in_dtypes[8];
+    for (int i = 0; i < n_inputs; i++) {
+        in_dtypes[i] = inputs[i]->dtype;
+        if (in_dtypes[i] < 0 || in_dtypes[i] >= BDF_NTYPES) return fail(BDF_UNSUPPORTED, "fused expressions take numeric columns");
+    }
+    switch (expr_compile(n_inputs, in_dtypes, n_nodes, op.data(), a.data(), b.data(), prog)) {
         case 0: break;
         case 1: return fail(BDF_INVALID, "a node's result is never used: the materialised chain would still evaluate it, split the expression");
         case 2: return fail(BDF_UNSUPPORTED, "the expression keeps more than two intermediates alive at once: split it");
@@ -1283,7 +1290,6 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
         if (!inputs[i]) return fail(BDF_INVALID, "null input column");
     int64_t n = (int64_t)inputs[0]->chunks.size();
     for (int i = 0; i < n_inputs; i++) {
-        if (inputs[i]->dtype != BDF_F64) return fail(BDF_UNSUPPORTED, "fused expressions are evaluated over Float64 columns (cast first)");
         n = std::min<int64_t>(n, (int64_t)inputs[i]->chunks.size());
     }
     for (int64_t ch = 0; ch < n; ch++)
@@ -1317,13 +1323,13 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
     if (st == BDF_OK && e == cudaSuccess) {
         int64_t tiles = 0, bytes = 0;
         for (int64_t ch = 0; ch < n; ch++) {
-            const double* in[8]; const uint32_t* vin[8]; int32_t off[8];
+            const void* in[8]; const uint32_t* vin[8]; int32_t off[8];
             const int64_t len = plan[ch].len;
             for (int i = 0; i < n_inputs; i++) {
                 const DevChunk& x = inputs[i]->chunks[ch];
-                in[i] = (const double*)x.values; vin[i] = x.validity; off[i] = x.bit_off;
+                in[i] = x.values; vin[i] = x.validity; off[i] = x.bit_off;
                 if ((uintptr_t)x.values & 15) e = cudaErrorMisalignedAddress;
-                bytes += 8 * x.len + (x.validity ? bitmap_bytes(x.len) : 0);
+                bytes += (int64_t)dtype_width(inputs[i]->dtype) * x.len + (x.validity ? bitmap_bytes(x.len) : 0);
             }
             double* po = o ? (double*)o->chunks[ch].values : nullptr;
             uint32_t* vo = o ? o->chunks[ch].validity : nullptr;

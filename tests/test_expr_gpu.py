@@ -147,8 +147,9 @@ def test_argument_validation(rdf, ctx):
     i = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.arange(10, dtype=np.int64))])
     with pytest.raises(rdf.ComputeError):
         rdf.eval_expr([a, b], [(N.ADD, 0, 1)])
+    assert np.array_equal(rdf.eval_expr([a, i], [(N.ADD, 0, 1)]).download()[0].value_slice(), 2 * np.arange(10.0))   # Int64 input read `as f64`
     with pytest.raises(rdf.UnsupportedType):
-        rdf.eval_expr([a, i], [(N.ADD, 0, 1)])
+        rdf.eval_expr([a, a.gt(3.0)], [(N.ADD, 0, 1)])            # a boolean column is not numeric
     for bad in ([(N.ADD, 0, 2)], [(N.ADD, 0, 1), (N.MUL, 3, 0)], [(99, 0, 0)], [(N.EXPR_UNARY + 50, 0)], [(N.ADD, 0, 0)] * 13):
         with pytest.raises(rdf.ArrowError):
             rdf.eval_expr([a, a], bad)
@@ -197,6 +198,42 @@ def test_trailing_aggregate_matches_two_pass(rdf, ctx, oracle):
     nulls = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.ones(n), np.zeros(n, bool)) for n in lens])
     _, a0 = rdf.eval_expr_agg([cols[0], nulls], [(N.MUL, 0, 1)], materialise=False)
     assert a0["count"] == 0 and a0["sum"] == 0.0
+
+
+@pytest.mark.parametrize("tname", ["I8", "I16", "I32", "I64", "U8", "U16", "U32", "U64", "F32"])
+def test_non_float64_inputs_are_cast_on_load(rdf, ctx, oracle, tname):
+    """An input column of another numeric type = Function::Cast to Float64 (`as f64`, infallible, validity kept)
+    followed by the chain: compared with the oracle's cast + materialised chain, bit for bit."""
+    dtype = getattr(rdf, tname)
+    npdt = np.dtype(rdf.NP_DTYPES[dtype])
+    rng = np.random.default_rng(50 + dtype)
+    N = rdf.native
+    typed, other = [], []
+    for k, n in enumerate(RAGGED):
+        pad = (5 + 3 * k) % 17
+        if npdt.kind == "f":
+            v = rng.normal(0, 1e3, n + pad + 2).astype(npdt)
+        else:
+            info = np.iinfo(npdt)
+            v = rng.integers(info.min, info.max, n + pad + 2, dtype=npdt, endpoint=True)
+        a = rdf.PrimitiveArray.from_numpy(v, random_mask(rng, n + pad + 2, 0.2))
+        a.null_count = -1
+        typed.append(a.slice(pad, n))
+        other.append(rdf.PrimitiveArray.from_numpy(rng.uniform(1.0, 9.0, n)))
+    ct, co = rdf.Column.upload(typed), rdf.Column.upload(other)
+    prog = [(N.MUL, 0, 1), (N.SUB, 2, 0), (N.DIV, 3, 1), ("abs", 4)]
+    got = rdf.eval_expr([ct, co], prog).download()
+    st, as_f64 = oracle.col_cast(dtype, oracle.F64, typed)
+    assert st == oracle.OK
+    st, want = oracle_chain(oracle, [as_f64, other], prog)
+    assert st == oracle.OK
+    for i, (g, w) in enumerate(zip(got, want)):
+        assert_same_array(g, w, what=f"expr over {tname} chunk {i}", check_payload=False)
+    # and against the unfused device path: cast_dev, then the chain
+    unfused, _ = gpu_chain([ct.cast(rdf.F64), co], prog)
+    for g, u in zip(got, unfused.download()):
+        m = g.valid_mask()
+        assert np.array_equal(m, u.valid_mask()) and np.array_equal(g.value_slice()[m].view(np.uint64), u.value_slice()[m].view(np.uint64))
 
 
 def test_config2_chain_fused_1e8(rdf, ctx, oracle):

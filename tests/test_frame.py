@@ -55,6 +55,12 @@ def test_planner_type_and_size_rules(rdf):
              F.calculate("cosine", ["m"], "n"), F.select(["n"])]
     plan = F.plan_fusion(sch, steps)
     assert kinds(plan) == ["calculate", "calculate", "fused", "select"] and plan[2][1].inputs == ["kf", "x"]
+    plan = F.plan_fusion(sch, steps, fuse_casts=True)
+    assert kinds(plan) == ["calculate", "fused", "select"] and plan[1][1].inputs == ["k", "x"]      # the cast rides in the fused load
+    assert [c.function for c in plan[1][1].replaced] == ["cast", "multiply", "cosine"] and len(plan[1][1].nodes) == 2
+    # a cast to anything but Float64, or one whose result stays visible, is a real Calculation
+    assert kinds(F.plan_fusion(sch, [F.calculate("cast", ["i"], "i32", rdf.I32), F.calculate("cast", ["i32"], "f", rdf.F64), F.calculate("sine", ["f"], "s"),
+                                     F.select(["s", "f"])], fuse_casts=True)) == ["calculate", "calculate", "calculate", "select"]
     # Float32 chains are left alone (the fused kernel is Float64)
     assert kinds(F.plan_fusion(schema_of(rdf, a="F32", b="F32"), [F.calculate("add", ["a", "b"], "e"), F.calculate("sine", ["e"], "h"), F.select(["h"])])) \
         == ["calculate", "calculate", "select"]
@@ -118,13 +124,15 @@ def test_fused_and_stepwise_evaluation_agree(rdf, ctx, oracle):
         chain() + [F.filter_(("and", ("gt", F.col("h"), F.lit(-0.5)), ("not", ("lt", F.col("k"), F.lit(0.0))))), F.sort([("k", True), ("h", False)]),
                    F.drop(["e", "f", "g", "b"])],
         [F.calculate("cast", ["k"], "kf", rdf.F64), F.calculate("multiply", ["kf", "a"], "m"), F.calculate("subtract", ["m", "c"], "n"),
-         F.calculate("tangent", ["n"], "t"), F.limit(1000), F.select(["k", "t"])],
+         F.calculate("tangent", ["n"], "t"), F.limit(1000), F.select(["k", "t"])],                      # the cast is fused too
+        [F.calculate("cast", ["k"], "kf", rdf.F64), F.calculate("add", ["kf", "b"], "s"), F.select(["kf", "s"])],   # kf stays visible: no fusion
         chain() + [F.calculate("rename", ["h"], "out"), F.select(["out", "f"])],
     ]
     for steps in pipelines:
         plan = F.plan_fusion(frame.schema, steps)
-        assert "fused" in [k for k, _ in plan]
+        assert ("fused" in [k for k, _ in plan]) == ("kf" not in steps[-1][1])
         frames_equal(frame.evaluate(steps, fuse=True), frame.evaluate(steps, fuse=False))
+        frames_equal(frame.evaluate(steps, fuse=True, fuse_casts=True), frame.evaluate(steps, fuse=False))
     # against the oracle: the first pipeline, chunk by chunk
     got = frame.evaluate(pipelines[0]).to_host()
     assert list(got) == ["a", "h"]
