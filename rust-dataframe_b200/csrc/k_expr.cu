@@ -183,8 +183,9 @@ __device__ __forceinline__ void expr_dispatch(int op, Vec<double, 2> (&out)[U], 
 
 // AGG: also fold sum/count of the RESULT column into one partial per tile (k_finish folds them, like K5); the result
 // column itself is optional then (d.out == nullptr: aggregate only, nothing is written but the partials).
-// TYPED: some input column is not Float64 (raw bytes are staged, `as f64` happens at operand fetch); the all-Float64
-// instantiation carries none of that code (with it, 64 registers spill in the node loop: 1.16 ms instead of 0.85 ms on config 2).
+// TYPED: some input column is not Float64: its raw bytes are staged and converted to doubles in place (`as f64`) before
+// the node loop.  The all-Float64 instantiation carries none of that code (one kernel for both cost the Float64 chain
+// 0.85 -> 1.16 ms: 64 registers spilled in the node loop).
 template <int U, int MINB, bool AGG, bool TYPED>
 __global__ void __launch_bounds__(kThreads, MINB)
 k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, uint32_t* __restrict__ warp_counts, int* __restrict__ flags,
@@ -245,6 +246,18 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
                 sm[i * kThreads + tid] = m;
             }
         cp_async_wait_all();
+        if constexpr (TYPED) {   // raw bytes -> doubles, in place, once per tile (every thread converts the slots it staged itself)
+#pragma unroll 1
+            for (int i = 0; i < ni; i++) {
+                const int t = prog.in_dtype[i];
+                if (t == T_F64) continue;
+#pragma unroll
+                for (int j = 0; j < U; j++) {
+                    Vec<double, 2>* slot = &sv[(i * U + j) * kThreads + tid];
+                    *slot = expr_as_f64(t, *slot);
+                }
+            }
+        }
     } else {
 #pragma unroll 1
         for (int i = 0; i < ni; i++) {
@@ -288,9 +301,8 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
 #pragma unroll
                 for (int j = 0; j < U; j++) o[j] = acc[j];
             } else {
-                const int t = (TYPED && full && src < ni) ? (int)prog.in_dtype[src] : (int)T_F64;   // tail tiles and temporaries hold doubles
 #pragma unroll
-                for (int j = 0; j < U; j++) o[j] = expr_as_f64(t, sv[(src * U + j) * kThreads + tid]);
+                for (int j = 0; j < U; j++) o[j] = sv[(src * U + j) * kThreads + tid];
                 om = sm[src * kThreads + tid];
             }
             if (op == XI_LOAD) {

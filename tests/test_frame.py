@@ -53,14 +53,14 @@ def test_planner_type_and_size_rules(rdf):
     sch = schema_of(rdf, i="I64", j="I64", x="F64")
     steps = [F.calculate("add", ["i", "j"], "k"), F.calculate("cast", ["k"], "kf", rdf.F64), F.calculate("multiply", ["kf", "x"], "m"),
              F.calculate("cosine", ["m"], "n"), F.select(["n"])]
-    plan = F.plan_fusion(sch, steps)
+    plan = F.plan_fusion(sch, steps, fuse_casts=False)
     assert kinds(plan) == ["calculate", "calculate", "fused", "select"] and plan[2][1].inputs == ["kf", "x"]
-    plan = F.plan_fusion(sch, steps, fuse_casts=True)
+    plan = F.plan_fusion(sch, steps)
     assert kinds(plan) == ["calculate", "fused", "select"] and plan[1][1].inputs == ["k", "x"]      # the cast rides in the fused load
     assert [c.function for c in plan[1][1].replaced] == ["cast", "multiply", "cosine"] and len(plan[1][1].nodes) == 2
     # a cast to anything but Float64, or one whose result stays visible, is a real Calculation
     assert kinds(F.plan_fusion(sch, [F.calculate("cast", ["i"], "i32", rdf.I32), F.calculate("cast", ["i32"], "f", rdf.F64), F.calculate("sine", ["f"], "s"),
-                                     F.select(["s", "f"])], fuse_casts=True)) == ["calculate", "calculate", "calculate", "select"]
+                                     F.select(["s", "f"])])) == ["calculate", "calculate", "calculate", "select"]
     # Float32 chains are left alone (the fused kernel is Float64)
     assert kinds(F.plan_fusion(schema_of(rdf, a="F32", b="F32"), [F.calculate("add", ["a", "b"], "e"), F.calculate("sine", ["e"], "h"), F.select(["h"])])) \
         == ["calculate", "calculate", "select"]
@@ -132,7 +132,7 @@ def test_fused_and_stepwise_evaluation_agree(rdf, ctx, oracle):
         plan = F.plan_fusion(frame.schema, steps)
         assert ("fused" in [k for k, _ in plan]) == ("kf" not in steps[-1][1])
         frames_equal(frame.evaluate(steps, fuse=True), frame.evaluate(steps, fuse=False))
-        frames_equal(frame.evaluate(steps, fuse=True, fuse_casts=True), frame.evaluate(steps, fuse=False))
+        frames_equal(frame.evaluate(steps, fuse=True, fuse_casts=False), frame.evaluate(steps, fuse=False))
     # against the oracle: the first pipeline, chunk by chunk
     got = frame.evaluate(pipelines[0]).to_host()
     assert list(got) == ["a", "h"]
