@@ -14,7 +14,8 @@
 // k_radix_scan (one CTA, exclusive scan in digit-major order) -> k_radix_scatter (per tile: warp-level match_any ranks,
 // reorder through shared memory, write each digit's run contiguously).  A digit on which every key agrees is skipped:
 // k_sort_keys also folds the OR and the AND of the keys it builds.
-// HBM traffic per executed pass: 8 (hist) + 12 + 12 B/row; Float64/Int64 criterion = 8 value passes (+1 if nullable).
+// HBM traffic per executed pass: 8 (hist) + 12 + 12 B/row with 64-bit keys, 4 + 8 + 8 with 32-bit keys (criteria of at most
+// 4 bytes); a Float64/Int64 criterion = 8 value passes (+1 if nullable), Int32/Float32 = 4 (+1).
 #include "common.cuh"
 
 #include <algorithm>
@@ -78,10 +79,21 @@ template <> struct SortKey<double> {
 // Also folds the bitwise OR and AND of every key written into agree[0], agree[1]: a byte on which OR == AND is the
 // same in all keys, so its radix pass would be the identity and is skipped.  (A first version accumulated the full
 // 8 x 256 digit histogram with shared-memory atomics here; only "is the digit constant" was ever used.)
+// Key width: 32-bit keys for criteria of at most 4 bytes (and their null flags), 64-bit otherwise -- a pass moves
+// 4 + 8 + 8 B/row instead of 8 + 12 + 12.
+template <typename T> struct KeyOf { using type = unsigned long long; };
+template <> struct KeyOf<int8_t> { using type = uint32_t; };
+template <> struct KeyOf<int16_t> { using type = uint32_t; };
+template <> struct KeyOf<int32_t> { using type = uint32_t; };
+template <> struct KeyOf<uint8_t> { using type = uint32_t; };
+template <> struct KeyOf<uint16_t> { using type = uint32_t; };
+template <> struct KeyOf<uint32_t> { using type = uint32_t; };
+template <> struct KeyOf<float> { using type = uint32_t; };
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_sort_keys(const SortChunk* __restrict__ chunks, int n_chunks, const uint32_t* __restrict__ idx, int64_t n, int mode, int descending,
-            unsigned long long* __restrict__ keys, unsigned long long* __restrict__ agree) {
+            typename KeyOf<T>::type* __restrict__ keys, unsigned long long* __restrict__ agree) {
     constexpr unsigned long long MASK = sizeof(T) == 8 ? ~0ull : ((1ull << (8 * (sizeof(T) & 7))) - 1ull);
     unsigned long long acc_or = 0ull, acc_and = ~0ull;
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
@@ -99,7 +111,7 @@ k_sort_keys(const SortChunk* __restrict__ chunks, int n_chunks, const uint32_t* 
                 if (descending) k = ~k & MASK;
             }
         }
-        keys[i] = k;
+        keys[i] = (typename KeyOf<T>::type)k;
         acc_or |= k;
         acc_and &= k;
     }
@@ -117,8 +129,9 @@ __global__ void __launch_bounds__(kThreads) k_iota(uint32_t* __restrict__ out, i
 
 // ---- one radix pass -----------------------------------------------------------------------------------------------
 // CTA b owns tiles [b * tiles_per_cta, ...): block_hist[d * G + b] = number of its keys with digit d.
+template <typename K>
 __global__ void __launch_bounds__(kThreads)
-k_radix_hist(const unsigned long long* __restrict__ keys, int64_t n, int shift, int64_t tiles_per_cta, unsigned int* __restrict__ block_hist) {
+k_radix_hist(const K* __restrict__ keys, int64_t n, int shift, int64_t tiles_per_cta, unsigned int* __restrict__ block_hist) {
     __shared__ unsigned int s_hist[256];
     s_hist[threadIdx.x] = 0;
     __syncthreads();
@@ -158,12 +171,13 @@ __global__ void __launch_bounds__(1024) k_radix_scan(unsigned int* __restrict__ 
 // Stable scatter of the CTA's tiles.  Within a tile, warp w owns elements [w*256, (w+1)*256) as 8 rows of 32 lanes, so
 // (warp, row, lane) order is the input order; ranks come from match_any + per-warp digit counters.  Threads 0..255 own
 // one digit each in the counting phases.
-constexpr size_t kScatterSmem = (size_t)kSortTile * 12 + (size_t)kSortWarps * 256 * 4 + 2 * 256 * 4 + 8 * 4;
+template <typename K> constexpr size_t scatter_smem() { return (size_t)kSortTile * (sizeof(K) + 4) + (size_t)kSortWarps * 256 * 4 + 2 * 256 * 4 + 8 * 4; }
+template <typename K>
 __global__ void __launch_bounds__(kSortThreads)
-k_radix_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, int64_t n, int shift, int64_t tiles_per_cta,
-                const unsigned int* __restrict__ block_offsets, unsigned long long* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
+k_radix_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_in, int64_t n, int shift, int64_t tiles_per_cta,
+                const unsigned int* __restrict__ block_offsets, K* __restrict__ keys_out, uint32_t* __restrict__ idx_out) {
     extern __shared__ __align__(16) unsigned char sort_smem[];
-    unsigned long long* s_key = reinterpret_cast<unsigned long long*>(sort_smem);
+    K* s_key = reinterpret_cast<K*>(sort_smem);
     uint32_t* s_idx = reinterpret_cast<uint32_t*>(s_key + kSortTile);
     unsigned int (*s_cnt)[256] = reinterpret_cast<unsigned int (*)[256]>(s_idx + kSortTile);
     unsigned int* s_start = &s_cnt[kSortWarps][0];   // first slot of each digit's run in the sorted tile
@@ -179,14 +193,14 @@ k_radix_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* 
         const int in_tile = (int)min((int64_t)kSortTile, n - base);
         for (int i = tid; i < kSortWarps * 256; i += kSortThreads) (&s_cnt[0][0])[i] = 0;
         __syncthreads();
-        unsigned long long key[kSortItems];
+        K key[kSortItems];
         uint32_t id[kSortItems];
         unsigned int rank[kSortItems];
 #pragma unroll
         for (int it = 0; it < kSortItems; it++) {
             const int e = warp * (kSortItems * 32) + it * 32 + lane;
             const bool ok = e < in_tile;
-            key[it] = ok ? keys_in[base + e] : 0ull;
+            key[it] = ok ? keys_in[base + e] : (K)0;
             id[it] = ok ? idx_in[base + e] : 0u;
         }
 #pragma unroll
@@ -236,7 +250,7 @@ k_radix_scatter(const unsigned long long* __restrict__ keys_in, const uint32_t* 
         for (int k = 0; k < kSortItems; k++) {
             const int sl = k * kSortThreads + tid;
             if (sl < in_tile) {
-                const unsigned long long kk = s_key[sl];
+                const K kk = s_key[sl];
                 const unsigned int d = (unsigned int)((kk >> shift) & 0xff);
                 const unsigned int g = s_gbase[d] + ((unsigned int)sl - s_start[d]);
                 keys_out[g] = kk;
@@ -334,13 +348,15 @@ cudaError_t launch_iota(uint32_t* out, int64_t n, int sm_count, cudaStream_t s) 
     return cudaGetLastError();
 }
 
+int sort_key_bytes(int dtype) { return dtype_width(dtype) <= 4 ? 4 : 8; }
+
 cudaError_t launch_sort_keys(int dtype, const void* chunks, int n_chunks, const uint32_t* idx, int64_t n, int mode, int descending,
-                             unsigned long long* keys, unsigned long long* agree, int sm_count, cudaStream_t s) {
+                             void* keys, unsigned long long* agree, int sm_count, cudaStream_t s) {
     if (n <= 0) return cudaSuccess;
     const SortChunk* ch = (const SortChunk*)chunks;
     const int g = grid_for(n, sm_count);
     switch (dtype) {
-#define BDF_SORT_CASE(ID, T) case ID: k_sort_keys<T><<<g, kThreads, 0, s>>>(ch, n_chunks, idx, n, mode, descending, keys, agree); break;
+#define BDF_SORT_CASE(ID, T) case ID: k_sort_keys<T><<<g, kThreads, 0, s>>>(ch, n_chunks, idx, n, mode, descending, (typename KeyOf<T>::type*)keys, agree); break;
         BDF_SORT_CASE(0, int8_t) BDF_SORT_CASE(1, int16_t) BDF_SORT_CASE(2, int32_t) BDF_SORT_CASE(3, int64_t)
         BDF_SORT_CASE(4, uint8_t) BDF_SORT_CASE(5, uint16_t) BDF_SORT_CASE(6, uint32_t) BDF_SORT_CASE(7, uint64_t)
         BDF_SORT_CASE(8, float) BDF_SORT_CASE(9, double)
@@ -355,18 +371,24 @@ int sort_pass_ctas(int64_t n, int sm_count) {
     const int64_t tiles = (n + kSortTile - 1) / kSortTile;
     return (int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)sm_count * 4));
 }
-cudaError_t launch_radix_pass(const unsigned long long* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
-                              unsigned long long* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s) {
-    if (n <= 0) return cudaSuccess;
+template <typename K>
+static cudaError_t radix_pass(const K* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist, K* keys_out, uint32_t* idx_out,
+                              int sm_count, cudaStream_t s) {
     const int64_t tiles = (n + kSortTile - 1) / kSortTile;
     const int g = sort_pass_ctas(n, sm_count);
     const int64_t per = (tiles + g - 1) / g;
-    k_radix_hist<<<g, kThreads, 0, s>>>(keys_in, n, shift, per, block_hist);
-    k_radix_scan<<<1, 1024, 0, s>>>(block_hist, (int64_t)256 * g);
-    static const cudaError_t attr = cudaFuncSetAttribute(k_radix_scatter, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kScatterSmem);
+    static const cudaError_t attr = cudaFuncSetAttribute(k_radix_scatter<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)scatter_smem<K>());
     if (attr != cudaSuccess) return attr;
-    k_radix_scatter<<<g, kSortThreads, kScatterSmem, s>>>(keys_in, idx_in, n, shift, per, block_hist, keys_out, idx_out);
+    k_radix_hist<K><<<g, kThreads, 0, s>>>(keys_in, n, shift, per, block_hist);
+    k_radix_scan<<<1, 1024, 0, s>>>(block_hist, (int64_t)256 * g);
+    k_radix_scatter<K><<<g, kSortThreads, scatter_smem<K>(), s>>>(keys_in, idx_in, n, shift, per, block_hist, keys_out, idx_out);
     return cudaGetLastError();
+}
+cudaError_t launch_radix_pass(int key_bytes, const void* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
+                              void* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s) {
+    if (n <= 0) return cudaSuccess;
+    if (key_bytes == 4) return radix_pass<uint32_t>((const uint32_t*)keys_in, idx_in, n, shift, block_hist, (uint32_t*)keys_out, idx_out, sm_count, s);
+    return radix_pass<unsigned long long>((const unsigned long long*)keys_in, idx_in, n, shift, block_hist, (unsigned long long*)keys_out, idx_out, sm_count, s);
 }
 
 cudaError_t launch_take(int dtype, const void* vals, int n_vals, const void* idxs, int n_idxs, int64_t n, int64_t n_rows_values, void* out,

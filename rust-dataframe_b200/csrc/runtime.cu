@@ -1388,10 +1388,11 @@ int sort_tile_elems();
 int take_tile_elems();
 int sort_pass_ctas(int64_t n, int sm_count);
 cudaError_t launch_iota(uint32_t* out, int64_t n, int sm_count, cudaStream_t s);
+int sort_key_bytes(int dtype);
 cudaError_t launch_sort_keys(int dtype, const void* chunks, int n_chunks, const uint32_t* idx, int64_t n, int mode, int descending,
-                             unsigned long long* keys, unsigned long long* agree, int sm_count, cudaStream_t s);
-cudaError_t launch_radix_pass(const unsigned long long* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
-                              unsigned long long* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s);
+                             void* keys, unsigned long long* agree, int sm_count, cudaStream_t s);
+cudaError_t launch_radix_pass(int key_bytes, const void* keys_in, const uint32_t* idx_in, int64_t n, int shift, unsigned int* block_hist,
+                              void* keys_out, uint32_t* idx_out, int sm_count, cudaStream_t s);
 cudaError_t launch_take(int dtype, const void* vals, int n_vals, const void* idxs, int n_idxs, int64_t n, int64_t n_rows_values, void* out,
                         uint32_t* vout, uint32_t* warp_counts, int* flags, cudaStream_t s);
 }  // namespace bdf
@@ -1445,7 +1446,7 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&block_hist, (size_t)256 * sort_pass_ctas(n, c->sm_count) * sizeof(unsigned int), c->s_compute);
         if (e == cudaSuccess) e = cudaMallocAsync((void**)&agree, 2 * sizeof(unsigned long long), c->s_compute);
         int cur = 0;
-        int64_t passes = 0;
+        int64_t passes = 0, pass_bytes = 0;
         if (e == cudaSuccess) {
             LaunchTimer t(c, BDF_K_SORT, keys[0].column->dtype, n, 0);
             e = launch_iota(ibuf[0], n, c->sm_count, c->s_compute);
@@ -1463,9 +1464,11 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
                     const unsigned long long differ = e == cudaSuccess ? (c->h_sort_agree[0] ^ c->h_sort_agree[1]) : 0ull;   // bits that are not the same in all keys
                     for (int d = 0; d < digits && e == cudaSuccess; d++) {
                         if (((differ >> (8 * d)) & 0xff) == 0) continue;   // every key has the same digit: the pass would be the identity
-                        e = launch_radix_pass(kbuf[cur], ibuf[cur], n, 8 * d, block_hist, kbuf[cur ^ 1], ibuf[cur ^ 1], c->sm_count, c->s_compute);
+                        const int kb = sort_key_bytes(col->dtype);
+                        e = launch_radix_pass(kb, kbuf[cur], ibuf[cur], n, 8 * d, block_hist, kbuf[cur ^ 1], ibuf[cur ^ 1], c->sm_count, c->s_compute);
                         cur ^= 1;
                         passes++;
+                        pass_bytes += (int64_t)(3 * kb + 8) * n;   // histogram read + keys and indices read and written
                     }
                 }
             }
@@ -1473,7 +1476,7 @@ static int sort_indices_dev(bdf_ctx* c, int n_keys, const bdf_sort_key* keys, bd
                 e = cudaMemcpyAsync(o->chunks[0].values, ibuf[cur], (size_t)n * 4, cudaMemcpyDeviceToDevice, c->s_compute);
             c->last_sort_passes = passes;
         }
-        if (c->profiling && !c->prof.empty() && c->prof.back().rec.kernel == BDF_K_SORT) c->prof.back().rec.bytes = 8 * n + passes * 32 * n + 4 * n;
+        if (c->profiling && !c->prof.empty() && c->prof.back().rec.kernel == BDF_K_SORT) c->prof.back().rec.bytes = 8 * n + pass_bytes + 4 * n;
         for (int b = 0; b < 2; b++) { if (kbuf[b]) cudaFreeAsync(kbuf[b], c->s_compute); if (ibuf[b]) cudaFreeAsync(ibuf[b], c->s_compute); }
         if (block_hist) cudaFreeAsync(block_hist, c->s_compute);
         if (agree) cudaFreeAsync(agree, c->s_compute);
