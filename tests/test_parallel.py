@@ -168,3 +168,70 @@ def test_shard_map_properties():
 @pytest.mark.gpu
 def test_two_rank_combine_real_kernels():
     _check(_run(2, use_gpu=True), 2)
+
+
+# ---- sharded from_arrow: every rank opens the same IPC file and takes its RecordBatches by the shard map ---------------
+
+def _ipc_worker(rank, world, port, path, q):
+    import sys
+
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK="0")
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import pyoracle as orc
+        import rust_dataframe_b200 as rdf
+        from rust_dataframe_b200 import parallel
+
+        with rdf.IpcFile(path) as f:
+            lens = [f.batch_rows(b) for b in range(f.num_batches)]
+            mine = parallel.shard_indices(f.num_batches, rank, world, lens)
+            out = {"batches": mine}
+            for name, dtype, _ in f.schema:
+                if dtype < 0 or dtype == 10:
+                    continue
+                views = [f.view(b, name) for b in mine]          # zero-copy host views into the mapping
+                chunks = [Chunk(v.value_slice(), dtype, None if v.validity is None else v.valid_mask()) for v in views]
+                local = oracle_partials(orc, dtype, chunks)      # stands in for the per-GPU reduction of bdf_ipc_read_batches' columns
+                comb = parallel.combine_aggregates(local, dtype, device="cpu")
+                out[name] = {k: (None if v is None else (float(v) if k == "sum" and dtype >= 8 else (bool(v) if k == "would_panic" else int(v)))) for k, v in comb.items()}
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_sharded_ipc_read_world_size_2(tmp_path):
+    import pyarrow as pa
+    import pyarrow.ipc
+    from oracle import pyoracle as orc
+
+    rng = np.random.default_rng(17)
+    lens = [300, 0, 5000, 17, 2048, 900]
+    batches = [pa.record_batch([pa.array(rng.integers(-2 ** 62, 2 ** 62, n), pa.int64(), mask=rng.random(n) < 0.2), pa.array(rng.normal(0, 100, n), pa.float64()),
+                                pa.array([str(i) for i in range(n)], pa.string()), pa.array(rng.integers(0, 255, n).astype(np.uint8), pa.uint8())],
+                               names=["k", "x", "s", "u"]) for n in lens]
+    path = str(tmp_path / "sharded.arrow")
+    with pa.ipc.new_file(path, batches[0].schema) as w:
+        for b in batches:
+            w.write_batch(b)
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ipc_worker, args=(r, world, port, path, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=180) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert sorted(got[0]["batches"] + got[1]["batches"]) == list(range(len(lens)))
+    assert got[0]["k"] == got[1]["k"] and got[0]["x"] == got[1]["x"] and got[0]["u"] == got[1]["u"]
+    k = pa.chunked_array([b.column("k") for b in batches])
+    kv = k.drop_null().to_numpy()
+    assert got[0]["k"]["count"] == len(kv) and got[0]["k"]["rows"] == sum(lens)
+    assert got[0]["k"]["sum"] == int(np.sum(kv.astype(np.uint64), dtype=np.uint64).astype(np.int64))     # wrapping, order independent
+    assert got[0]["k"]["min"] == int(kv.min()) and got[0]["k"]["max"] == int(kv.max())
+    xv = np.concatenate([b.column("x").to_numpy() for b in batches])
+    assert abs(got[0]["x"]["sum"] - float(np.sum(xv.astype(np.longdouble)))) <= 1e-6
+    assert got[0]["u"]["sum"] == int(np.sum(np.concatenate([b.column("u").to_numpy() for b in batches]).astype(np.uint64)) % 256)
