@@ -267,6 +267,7 @@ int bdf_ipc_open(const char* path, bdf_ipc** out) {
         if (rb.field(3)) return ipc_fail(BDF_UNSUPPORTED, "compressed IPC bodies are not supported (write the file uncompressed)");
         IpcBatch b;
         b.rows = rb.scalar<int64_t>(0, 0);
+        if (b.rows < 0 || b.rows > (int64_t)f->size * 8) return ipc_fail(BDF_INVALID, "record batch %u: impossible row count %lld", k, (long long)b.rows);
         b.body = (size_t)off + (size_t)meta_len;
         b.body_len = body_len;
         size_t nfirst, bufirst; uint32_t ncnt, bucnt;
