@@ -184,3 +184,129 @@ def test_evaluator_rules_and_arrow_round_trip(rdf, ctx, tmp_path):
     with pytest.raises(rdf.DivideByZero):
         frame.evaluate([F.calculate("subtract", ["a", "a"], "z"), F.calculate("divide", ["a", "z"], "q"), F.select(["q"])])
     assert list(frame.evaluate([F.calculate("add", ["a", "b"], "a")]).columns) == ["b", "k", "a"]   # with_column: drop + append
+
+
+# ---- the planner's claim, checked on random pipelines without a GPU ---------------------------------------------------
+# A tiny numpy interpreter of the transformation list (values + validity per column, one chunk) stands in for the
+# device: what matters here is WHICH columns exist, in which order, with which values -- fused plan vs original list.
+
+class _NpFrame:
+    def __init__(self, cols):
+        self.cols = OrderedDict(cols)      # name -> (values float64 or int64, valid bool)
+
+    def run(self, steps):
+        import math
+        f = _NpFrame(self.cols)
+        for kind, arg in steps:
+            if kind == "calculate":
+                f = f._calc(arg.function, arg.inputs, arg.output, arg.dtype)
+            elif kind == "fused":
+                slots = [f.cols[n] for n in arg.inputs]
+                slots = [(v.astype(np.float64), m) for v, m in slots]
+                for nd in arg.nodes:
+                    if len(nd) == 2:
+                        v, m = slots[nd[1]]
+                        slots.append(({"sin": np.sin, "cos": np.cos, "tan": np.tan}[nd[0]](v), m))
+                    else:
+                        (a, ma), (b, mb) = slots[nd[1]], slots[nd[2]]
+                        with np.errstate(all="ignore"):
+                            r = [a + b, a - b, a * b, a / np.where(ma & mb, b, 1.0)][nd[0]]
+                        slots.append((r, ma & mb))
+                cols = OrderedDict((n, c) for n, c in f.cols.items() if n != arg.output)
+                cols[arg.output] = slots[-1]
+                f = _NpFrame(cols)
+            elif kind == "select":
+                f = _NpFrame((n, c) for n, c in f.cols.items() if "*" in arg or n in arg)
+            elif kind == "drop":
+                f = _NpFrame((n, c) for n, c in f.cols.items() if n not in arg)
+            elif kind == "filter":
+                _, (_, name), (_, thr) = arg
+                v, m = f.cols[name]
+                keep = m & (v.astype(np.float64) > thr)
+                f = _NpFrame((n, (cv[keep], cm[keep])) for n, (cv, cm) in f.cols.items())
+            elif kind == "sort":
+                name, desc = arg[0]
+                v, m = f.cols[name]
+                key = np.where(m, -v if desc else v, np.inf)
+                order = np.argsort(key, kind="stable")
+                f = _NpFrame((n, (cv[order], cm[order])) for n, (cv, cm) in f.cols.items())
+        return f
+
+    def _calc(self, fn, inputs, out, dtype):
+        if fn == "rename":
+            return _NpFrame(((out if n == inputs[0] else n), c) for n, c in self.cols.items())
+        a, ma = self.cols[inputs[0]]
+        if fn == "cast":
+            r, m = a.astype(np.float64), ma
+        elif fn in ("sine", "cosine", "tangent"):
+            r, m = {"sine": np.sin, "cosine": np.cos, "tangent": np.tan}[fn](a), ma
+        else:
+            b, mb = self.cols[inputs[1]]
+            m = ma & mb
+            with np.errstate(all="ignore"):
+                if a.dtype.kind == "i":
+                    r = {"add": a + b, "subtract": a - b, "multiply": a * b, "divide": a // np.where(m & (b != 0), b, 1)}[fn]
+                else:
+                    r = {"add": a + b, "subtract": a - b, "multiply": a * b, "divide": a / np.where(m, b, 1.0)}[fn]
+        cols = OrderedDict((n, c) for n, c in self.cols.items() if n != out)
+        cols[out] = (r, m)
+        return _NpFrame(cols)
+
+
+def test_random_pipelines_fused_plan_is_equivalent(rdf):
+    F = rdf.frame
+    rng = np.random.default_rng(2024)
+    n = 64
+    base = OrderedDict([("a", (rng.normal(0, 3, n), np.ones(n, bool))), ("b", (rng.normal(0, 3, n), rng.random(n) > 0.2)),
+                        ("c", (rng.uniform(1, 4, n), np.ones(n, bool))), ("i", (rng.integers(-5, 6, n), rng.random(n) > 0.1))])
+    schema = OrderedDict([("a", rdf.F64), ("b", rdf.F64), ("c", rdf.F64), ("i", rdf.I64)])
+    fused_plans = 0
+    for trial in range(600):
+        names = {"a": rdf.F64, "b": rdf.F64, "c": rdf.F64, "i": rdf.I64}
+        steps, fresh = [], 0
+        for _ in range(int(rng.integers(2, 12))):
+            floats = [k for k, t in names.items() if t == rdf.F64]
+            r = rng.random()
+            if r < 0.55 and len(floats) >= 2:
+                out = f"t{fresh}" if rng.random() < 0.85 else str(rng.choice(list(names)))   # sometimes overwrite an existing column
+                fresh += 1
+                if rng.random() < 0.7:
+                    x, y = rng.choice(floats, 2)
+                    if out in (x, y) and rng.random() < 0.5:
+                        out = f"t{fresh}"; fresh += 1
+                    steps.append(F.calculate(str(rng.choice(["add", "subtract", "multiply"])), [str(x), str(y)], out))
+                else:
+                    steps.append(F.calculate(str(rng.choice(["sine", "cosine"])), [str(rng.choice(floats))], out))
+                names[out] = rdf.F64
+            elif r < 0.62 and "i" in names and names["i"] == rdf.I64:
+                steps.append(F.calculate("cast", ["i"], f"t{fresh}", rdf.F64)); names[f"t{fresh}"] = rdf.F64; fresh += 1
+            elif r < 0.72 and len(names) > 2:
+                victims = [str(v) for v in rng.choice(list(names), int(rng.integers(1, 3)), replace=False)]
+                steps.append(F.drop(victims))
+                for v in victims:
+                    names.pop(v)
+            elif r < 0.80 and len(names) > 2:
+                keep = [str(v) for v in rng.choice(list(names), int(rng.integers(1, len(names))), replace=False)]
+                steps.append(F.select(keep))
+                names = {k: t for k, t in names.items() if k in keep}
+            elif r < 0.88 and floats:
+                steps.append(F.filter_(("gt", F.col(str(rng.choice(floats))), F.lit(float(rng.normal())))))
+            elif r < 0.94 and floats:
+                steps.append(F.sort([(str(rng.choice(floats)), bool(rng.random() < 0.5))]))
+            elif len(names) > 1:
+                old = str(rng.choice(list(names)))
+                steps.append(F.calculate("rename", [old], f"r{fresh}")); names[f"r{fresh}"] = names.pop(old); fresh += 1
+        if rng.random() < 0.6 and len(names) > 1:      # the usual end of a lazy pipeline: keep a few columns, the rest is dead
+            keep = [str(v) for v in rng.choice(list(names), int(rng.integers(1, 3)), replace=False)]
+            if fresh and f"t{fresh - 1}" in names:
+                keep.append(f"t{fresh - 1}")
+            steps.append(F.select(keep))
+        plan = F.plan_fusion(schema, steps)
+        fused_plans += any(k == "fused" for k, _ in plan)
+        want, got = _NpFrame(base).run(steps), _NpFrame(base).run(plan)
+        assert list(got.cols) == list(want.cols), (trial, steps, plan)
+        for name in want.cols:
+            (wv, wm), (gv, gm) = want.cols[name], got.cols[name]
+            assert np.array_equal(wm, gm), (trial, name)
+            assert np.array_equal(wv[wm], gv[gm], equal_nan=True) if wv.dtype.kind == "f" else np.array_equal(wv[wm], gv[gm]), (trial, name, steps, plan)
+    assert fused_plans > 60      # the generator does produce fusable runs (99 of 600 with this seed)
