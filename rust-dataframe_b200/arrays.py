@@ -160,10 +160,11 @@ class BooleanArray:
     """Arrow BooleanArray chunk: bit-packed values (LSB first) + optional validity; `offset` counts bits."""
 
     dtype = 10  # BDF_BOOL
-    __slots__ = ("values", "validity", "offset", "length", "null_count")
+    __slots__ = ("values", "validity", "offset", "length", "null_count", "_keepalive")
 
     def __init__(self, values: np.ndarray, validity: Optional[np.ndarray] = None, offset: int = 0, length: int = 0,
-                 null_count: int = -1):
+                 null_count: int = -1, keepalive=None):
+        self._keepalive = keepalive    # e.g. the mapped IPC file the buffers point into
         self.values = np.ascontiguousarray(values, dtype=np.uint8)
         self.validity = None if validity is None else np.ascontiguousarray(validity, dtype=np.uint8)
         self.offset, self.length = int(offset), int(length)
@@ -176,7 +177,7 @@ class BooleanArray:
         return cls(pack_validity(bits), validity, 0, bits.shape[0], 0 if mask is None else int((~np.asarray(mask, bool)).sum()))
 
     def slice(self, offset: int, length: int) -> "BooleanArray":
-        return BooleanArray(self.values, self.validity, self.offset + offset, length, -1)
+        return BooleanArray(self.values, self.validity, self.offset + offset, length, -1, keepalive=self._keepalive)
 
     def value_bits(self) -> np.ndarray:
         return np.unpackbits(self.values, bitorder="little")[self.offset:self.offset + self.length].astype(bool)

@@ -79,7 +79,7 @@ class IpcFile:
             validity = np.ctypeslib.as_array(C.cast(v.validity, C.POINTER(C.c_uint8)), shape=(nvb,)) if nvb else np.zeros(0, np.uint8)
         if dtype == BOOL:
             vals = np.ctypeslib.as_array(C.cast(v.values, C.POINTER(C.c_uint8)), shape=(nvb,)) if nvb else np.zeros(0, np.uint8)
-            return BooleanArray(vals, validity, 0, n, v.null_count)
+            return BooleanArray(vals, validity, 0, n, v.null_count, keepalive=self)
         npdt = np.dtype(NP_DTYPES[dtype])
         if n:
             raw = np.ctypeslib.as_array(C.cast(v.values, C.POINTER(C.c_uint8)), shape=(n * npdt.itemsize,))
