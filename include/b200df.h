@@ -177,6 +177,12 @@ int  bdf_filter_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* mask, bd
 typedef struct { int32_t op, a, b; } bdf_expr_node;
 int  bdf_eval_expr_dev(bdf_ctx* ctx, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes,
                        bdf_col** out);
+/* Would bdf_eval_expr_dev accept this program?  Needs no context and no GPU: validates the nodes and runs the host compiler,
+ * so a planner can decide what to fuse before it touches data.  input_dtypes may be NULL (all Float64).  Returns the status
+ * the evaluation would return for the program itself (BDF_OK, BDF_INVALID, BDF_UNSUPPORTED); on success reports the
+ * accumulator program's instruction count and how many of the two temporaries it uses. */
+int  bdf_expr_check(int32_t n_inputs, const int32_t* input_dtypes, int32_t n_nodes, const bdf_expr_node* nodes, int32_t* n_instructions,
+                    int32_t* n_temporaries);
 /* ... with a trailing aggregate (AggregateFunctions::sum / count of the chain's last column, src/functions/aggregate.rs:22-31,
  * 70-93) folded into the same pass, like bdf_binary_agg_dev.  `out` may be NULL: the column is then never written (the
  * chain is only aggregated: sum(sin(((a+b)*c)/d)) reads 32 B/row and writes nothing).  Float64 result: agg->sum and

@@ -369,6 +369,11 @@ int expr_max_inputs() { return kExprMaxInputs; }
 int expr_max_nodes() { return kExprMaxNodes; }
 size_t expr_desc_size() { return sizeof(ExprDesc); }
 size_t expr_prog_size() { return sizeof(ExprProg); }
+void expr_prog_stats(const void* prog, int* n_instructions, int* n_temporaries) {
+    const ExprProg* p = (const ExprProg*)prog;
+    *n_instructions = p->n_ins;
+    *n_temporaries = p->n_slots - p->n_inputs;
+}
 
 void fill_expr_desc(void* base, int64_t i, int n_inputs, const void* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
                     uint32_t* vout, int64_t len, int64_t tile0) {

@@ -1249,18 +1249,18 @@ size_t expr_desc_size();
 void fill_expr_desc(void* base, int64_t i, int n_inputs, const void* const* in, const uint32_t* const* vin, const int32_t* off, double* out,
                     uint32_t* vout, int64_t len, int64_t tile0);
 size_t expr_prog_size();
+void expr_prog_stats(const void* prog, int* n_instructions, int* n_temporaries);
 int expr_compile(int n_inputs, const int* in_dtypes, int n_nodes, const int* op, const int* a, const int* b, void* prog);
 cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const void* prog, uint32_t* warp_counts, int* flags, AggDev* tile_partials,
                         cudaStream_t s);
 }  // namespace bdf
 
-// out == nullptr (only with fut): aggregate only, the result column is never written.
-static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int n_nodes, const bdf_expr_node* nodes, bdf_col** out,
-                    bdf_future** fut = nullptr) {
+// Validation + host compilation of a fused program (shared by the evaluation entry and bdf_expr_check; needs no device).
+static int expr_prepare(int n_inputs, const int* in_dtypes, int n_nodes, const bdf_expr_node* nodes, unsigned char (&prog)[256], bool* has_div) {
     if (n_inputs < 1 || n_inputs > expr_max_inputs()) return fail(BDF_INVALID, "an expression takes 1..%d input columns", expr_max_inputs());
     if (n_nodes < 1 || n_nodes > expr_max_nodes()) return fail(BDF_INVALID, "an expression has 1..%d nodes", expr_max_nodes());
     std::vector<int> op(n_nodes), a(n_nodes), b(n_nodes);
-    bool has_div = false;
+    *has_div = false;
     for (int k = 0; k < n_nodes; k++) {
         op[k] = nodes[k].op; a[k] = nodes[k].a; b[k] = nodes[k].b;
         const bool unary = op[k] >= BDF_EXPR_UNARY;
@@ -1268,24 +1268,32 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
         if (a[k] < 0 || a[k] >= n_inputs + k || (!unary && (b[k] < 0 || b[k] >= n_inputs + k)))
             return fail(BDF_INVALID, "node %d refers to a slot that is not computed yet", k);
         if (unary) b[k] = a[k];
-        has_div = has_div || op[k] == BDF_DIV;
+        *has_div = *has_div || op[k] == BDF_DIV;
     }
-    alignas(8) unsigned char prog[256];
     static_assert(sizeof(prog) >= 8 + 2 * 40, "ExprProg must fit");
     if (expr_prog_size() > sizeof(prog)) return fail(BDF_INVALID, "internal: expression program too large");
     for (int i = 0; i < n_inputs; i++)
-        if (!inputs[i]) return fail(BDF_INVALID, "null input column");
-    int in_dtypes[8];
-    for (int i = 0; i < n_inputs; i++) {
-        in_dtypes[i] = inputs[i]->dtype;
         if (in_dtypes[i] < 0 || in_dtypes[i] >= BDF_NTYPES) return fail(BDF_UNSUPPORTED, "fused expressions take numeric columns");
-    }
     switch (expr_compile(n_inputs, in_dtypes, n_nodes, op.data(), a.data(), b.data(), prog)) {
-        case 0: break;
+        case 0: return BDF_OK;
         case 1: return fail(BDF_INVALID, "a node's result is never used: the materialised chain would still evaluate it, split the expression");
         case 2: return fail(BDF_UNSUPPORTED, "the expression keeps more than two intermediates alive at once: split it");
         default: return fail(BDF_UNSUPPORTED, "the expression is too long to fuse: split it");
     }
+}
+
+// out == nullptr (only with fut): aggregate only, the result column is never written.
+static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int n_nodes, const bdf_expr_node* nodes, bdf_col** out,
+                    bdf_future** fut = nullptr) {
+    if (!inputs) return fail(BDF_INVALID, "null argument");
+    int in_dtypes[8] = {0};
+    for (int i = 0; i < n_inputs && i < 8; i++) {
+        if (!inputs[i]) return fail(BDF_INVALID, "null input column");
+        in_dtypes[i] = inputs[i]->dtype;
+    }
+    alignas(8) unsigned char prog[256];
+    bool has_div = false;
+    TRY(expr_prepare(n_inputs, in_dtypes, n_nodes, nodes, prog, &has_div));
     for (int i = 0; i < n_inputs; i++)
         if (!inputs[i]) return fail(BDF_INVALID, "null input column");
     int64_t n = (int64_t)inputs[0]->chunks.size();
@@ -1795,6 +1803,21 @@ int bdf_future_wait(bdf_ctx* c, bdf_future* fut, bdf_agg4* out) {
     ENTER(c);
     if (!fut) return fail(BDF_INVALID, "null future");
     return future_wait(c, fut, out);
+}
+
+int bdf_expr_check(int32_t n_inputs, const int32_t* input_dtypes, int32_t n_nodes, const bdf_expr_node* nodes, int32_t* n_instructions,
+                   int32_t* n_temporaries) {
+    if (!nodes) return fail(BDF_INVALID, "null argument");
+    int dt[8];
+    for (int i = 0; i < 8; i++) dt[i] = (input_dtypes && i < n_inputs) ? input_dtypes[i] : BDF_F64;
+    alignas(8) unsigned char prog[256];
+    bool has_div = false;
+    TRY(expr_prepare(n_inputs, dt, n_nodes, nodes, prog, &has_div));
+    int ni = 0, nt = 0;
+    expr_prog_stats(prog, &ni, &nt);
+    if (n_instructions) *n_instructions = ni;
+    if (n_temporaries) *n_temporaries = nt;
+    return BDF_OK;
 }
 
 int bdf_eval_expr_dev(bdf_ctx* c, int32_t n_inputs, const bdf_col* const* inputs, int32_t n_nodes, const bdf_expr_node* nodes, bdf_col** out) {

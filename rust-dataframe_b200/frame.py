@@ -31,7 +31,7 @@ import numpy as np
 
 from . import _native as N
 from .arrays import F32, F64, I8, U8, PrimitiveArray, is_float
-from .functions import Column, eval_expr, sort_indices
+from .functions import Column, _expr_nodes, eval_expr, sort_indices
 from .ipc import BOOL, IpcFile, write_ipc
 
 ARITH = {"add": N.ADD, "subtract": N.SUB, "multiply": N.MUL, "divide": N.DIV}
@@ -238,6 +238,8 @@ def _try_fuse(run: List[Calculation], needed_after_run: set, max_inputs: int, ma
             prog.append((ARITH[fn], slot(ops[0]), slot(ops[1])))
         else:
             prog.append((TRIG[fn], slot(ops[0])))
+    if N.lib().bdf_expr_check(ni, None, len(prog), _expr_nodes(prog), None, None) != N.OK:
+        return None                                   # e.g. more than two intermediates alive at once: the caller tries a shorter run
     return Fused(inputs, prog, final, list(run))
 
 

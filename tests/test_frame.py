@@ -86,6 +86,38 @@ def test_planner_type_and_size_rules(rdf):
     assert kinds(plan) == ["calculate", "calculate", "calculate", "select"]      # e is still visible through "*"
 
 
+def test_expr_check_and_planner_respect_the_compiler_limits(rdf):
+    """bdf_expr_check runs the library's host compiler without a GPU; the planner asks it before it fuses."""
+    import ctypes as C
+
+    F, N = rdf.frame, rdf.native
+    from rust_dataframe_b200.functions import _expr_nodes
+
+    def check(n_inputs, prog):
+        ni, nt = C.c_int32(-1), C.c_int32(-1)
+        st = N.lib().bdf_expr_check(n_inputs, None, len(prog), _expr_nodes(prog), C.byref(ni), C.byref(nt))
+        return st, ni.value, nt.value
+
+    assert check(4, [(N.ADD, 0, 1), (N.MUL, 4, 2), (N.DIV, 5, 3), ("sin", 6)]) == (N.OK, 5, 0)        # load, add, mul, div, sin
+    assert check(4, [(N.ADD, 0, 1), (N.SUB, 2, 3), (N.MUL, 4, 5)])[::2] == (N.OK, 1)                   # one side parked in a temporary
+    assert check(2, [(N.ADD, 0, 1), (N.MUL, 2, 2), (N.SUB, 0, 2), (N.ADD, 3, 4)])[0] == N.OK             # a shared node
+    assert check(2, [(N.ADD, 0, 2)])[0] == N.INVALID                                                   # forward reference
+    assert check(2, [(N.DIV, 0, 1), (N.ADD, 0, 1)])[0] == N.INVALID                                    # dead node
+    assert check(2, [(99, 0, 1)])[0] == N.INVALID and check(7, [(N.ADD, 0, 1)])[0] == N.INVALID
+    three_shared = [(N.ADD, 0, 1), (N.SUB, 0, 1), (N.MUL, 0, 1), (N.MUL, 2, 3), (N.MUL, 5, 4), (N.ADD, 6, 2), (N.ADD, 7, 3), (N.ADD, 8, 4)]
+    assert check(2, three_shared)[0] == N.UNSUPPORTED
+    # the same shape as Calculations: the planner must not emit it as one step, and what it emits must compile
+    sch = schema_of(rdf, a="F64", b="F64")
+    steps = [F.calculate("add", ["a", "b"], "s1"), F.calculate("subtract", ["a", "b"], "s2"), F.calculate("multiply", ["a", "b"], "s3"),
+             F.calculate("multiply", ["s1", "s2"], "t"), F.calculate("multiply", ["t", "s3"], "u"), F.calculate("add", ["u", "s1"], "v"),
+             F.calculate("add", ["v", "s2"], "w"), F.calculate("add", ["w", "s3"], "z"), F.select(["z"])]
+    plan = F.plan_fusion(sch, steps)
+    assert sum(len(p[1].replaced) if p[0] == "fused" else 1 for p in plan if p[0] != "select") == 8
+    for kind, arg in plan:
+        if kind == "fused":
+            assert len(arg.replaced) < 8 and check(len(arg.inputs), arg.nodes)[0] == N.OK
+
+
 # ---- data -----------------------------------------------------------------------------------------------
 
 def host_frame(rdf, rng, lens, nulls=True):
