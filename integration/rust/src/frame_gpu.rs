@@ -1,0 +1,90 @@
+//! Device-resident frames: how `DataFrame::{from_arrow, to_arrow, sort}` and a fused run of Calculations map onto
+//! libb200df.so.  UNCOMPILED here (see ../README.md); the same flow is exercised from Python in
+//! rust-dataframe_b200/frame.py (tests/test_frame.py, tests/test_ipc.py, tests/test_sort_gpu.py).
+use std::ffi::{CStr, CString};
+use std::os::raw::c_char;
+
+use crate::ffi::*;
+
+/// Columns of a frame that live in HBM: one `BdfCol` per numeric/boolean column, one chunk per RecordBatch.
+pub struct DeviceColumns {
+    pub names: Vec<String>,
+    pub cols: Vec<*mut BdfCol>,
+}
+
+impl Drop for DeviceColumns {
+    fn drop(&mut self) {
+        for c in &self.cols {
+            unsafe { bdf_col_free(ctx(), *c) };
+        }
+    }
+}
+
+/// DataFrame::from_arrow (src/dataframe.rs:391-407) for the columns on the path: the file is mapped and its body buffers
+/// go straight to the device.  Columns reported with dtype -1 (Utf8, List, ...) keep coming from arrow's FileReader.
+pub fn from_arrow_device(path: &str) -> Result<DeviceColumns, String> {
+    let cpath = CString::new(path).unwrap();
+    let mut f: *mut BdfIpc = std::ptr::null_mut();
+    check(unsafe { bdf_ipc_open(cpath.as_ptr(), &mut f) })?;
+    let (mut n_cols, mut n_batches, mut n_rows) = (0i32, 0i64, 0i64);
+    unsafe { bdf_ipc_describe(f, &mut n_cols, &mut n_batches, &mut n_rows) };
+    let mut wanted = vec![];
+    let mut names = vec![];
+    for c in 0..n_cols {
+        let (mut name, mut dtype, mut nullable): (*const c_char, i32, i32) = (std::ptr::null(), -1, 0);
+        unsafe { bdf_ipc_column(f, c, &mut name, &mut dtype, &mut nullable) };
+        if dtype >= 0 {
+            wanted.push(c);
+            names.push(unsafe { CStr::from_ptr(name) }.to_string_lossy().into_owned());
+        }
+    }
+    let mut cols = vec![std::ptr::null_mut(); wanted.len()];
+    let st = unsafe { bdf_ipc_read(ctx(), f, wanted.len() as i32, wanted.as_ptr(), 0, cols.as_mut_ptr()) };
+    unsafe { bdf_ipc_close(f) };   // synchronous read: the copies are done
+    check(st)?;
+    Ok(DeviceColumns { names, cols })
+}
+
+/// DataFrame::to_arrow (src/dataframe.rs:515-525): chunk b of every column is RecordBatch b.
+pub fn to_arrow_device(frame: &DeviceColumns, path: &str) -> Result<(), String> {
+    let cpath = CString::new(path).unwrap();
+    let cnames: Vec<CString> = frame.names.iter().map(|s| CString::new(s.as_str()).unwrap()).collect();
+    let name_ptrs: Vec<*const c_char> = cnames.iter().map(|s| s.as_ptr()).collect();
+    let col_ptrs: Vec<*const BdfCol> = frame.cols.iter().map(|c| *c as *const BdfCol).collect();
+    check(unsafe { bdf_ipc_write(ctx(), cpath.as_ptr(), col_ptrs.len() as i32, name_ptrs.as_ptr(), col_ptrs.as_ptr()) })
+}
+
+/// DataFrame::sort (src/dataframe.rs:194-222): criteria = (column index, descending); nulls last like the reference.
+pub fn sort_device(frame: &DeviceColumns, criteria: &[(usize, bool)]) -> Result<DeviceColumns, String> {
+    if criteria.is_empty() {
+        return Err("Sort criteria cannot be empty".to_string());
+    }
+    let keys: Vec<BdfSortKey> = criteria.iter().map(|(c, d)| BdfSortKey { column: frame.cols[*c], descending: *d as i32 }).collect();
+    let mut indices: *mut BdfCol = std::ptr::null_mut();
+    check(unsafe { bdf_sort_indices_dev(ctx(), keys.len() as i32, keys.as_ptr(), &mut indices) })?;   // lexsort_to_indices
+    let mut out = vec![];
+    for c in &frame.cols {
+        let mut taken: *mut BdfCol = std::ptr::null_mut();
+        let st = unsafe { bdf_take_dev(ctx(), *c, indices, &mut taken) };                               // sort_by_indices -> Column::take
+        if st != BDF_OK {
+            unsafe { bdf_col_free(ctx(), indices) };
+            return check(st).map(|_| unreachable!());
+        }
+        out.push(taken);
+    }
+    unsafe { bdf_col_free(ctx(), indices) };
+    Ok(DeviceColumns { names: frame.names.clone(), cols: out })
+}
+
+/// A run of Float64 Calculations whose intermediates are not kept (config 2: h = sin(((a+b)*c)/d)) as one pass.
+/// `inputs` are column indices; node k writes slot inputs.len() + k (see include/b200df.h, bdf_eval_expr_dev).
+pub fn fused_chain(frame: &DeviceColumns, inputs: &[usize], nodes: &[BdfExprNode]) -> Result<*mut BdfCol, String> {
+    let cols: Vec<*const BdfCol> = inputs.iter().map(|i| frame.cols[*i] as *const BdfCol).collect();
+    let mut out: *mut BdfCol = std::ptr::null_mut();
+    check(unsafe { bdf_eval_expr_dev(ctx(), cols.len() as i32, cols.as_ptr(), nodes.len() as i32, nodes.as_ptr(), &mut out) })?;
+    Ok(out)
+}
+
+fn check(st: i32) -> Result<(), String> {
+    if st == BDF_OK { Ok(()) } else { Err(last_error()) }
+}
