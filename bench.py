@@ -3,21 +3,26 @@
 
     python bench.py --gpus 1 --steps 50 --warmup 5              # this framework (CUDA, sm_100a)
     python bench.py --impl reference --gpus 1 --steps 5 ...     # the reference's CPU path (C restatement, host cores)
-    torchrun --nproc-per-node N bench.py --gpus N ...           # N GPUs, weak scaling (1e8 rows per GPU)
+    torchrun --nproc-per-node N bench.py --gpus N ...           # N GPUs: weak series (1e8 rows per GPU) + strong series
+    python bench.py --config 3|4|5 [--gpus N]                   # the other BASELINE configs (benchmarks/configs_bench.py)
 
 A "step" is one pass of the hot path over one batch of synthetic input:
     c = ScalarFunctions::add(a, b)   (25 chunks x 4e6 rows of Float64, no nulls)   -> 24 B/row through HBM
     s = AggregateFunctions::sum(c)                                                  ->  8 B/row through HBM
 `value` = rows/s with a and b already resident in HBM (c is materialised in HBM every step, s comes back to
-the host every step; at N > 1 the per-GPU partial sums are combined with one NCCL all-reduce per step).
-`e2e`   = the same step through the public API with HOST buffers: a and b start in pinned host memory and
-are copied to the device inside the timed region, c is copied back to pinned host memory, s to the host.
+the host every step).  At N > 1 every rank owns a shard of the Vec<RecordBatch>; the per-GPU partial sums are
+combined by the LIBRARY with one grouped ncclAllReduce per step, enqueued on the stream that produced them
+(csrc/comm.cu) -- bench.py itself issues no collective inside the timed loop.
+`e2e`   = the same two operators through the drop-in host entries the Rust shim binds (bdf_binary + bdf_aggregate)
+with HOST buffers: a and b are copied to the device inside the timed region, c is copied back to host memory, then
+sum(c) reads the host copy of c again (two calls, as the reference API is two calls).
 Prints exactly one JSON line (rank 0).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -33,6 +38,12 @@ CHUNK = 4_000_000
 SEED = 20260924
 METRIC = "rows/s on 1e8-row f64 add+sum"
 WORKLOAD = "1e8 rows x 2 Float64 cols (25 chunks x 4e6 rows, no nulls): c = a + b, then sum(c)"
+
+
+def config_dict(n_gpus: int, scaling: str) -> dict:
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": WORKLOAD, "rows": ROWS, "chunks": ROWS // CHUNK, "chunk_rows": CHUNK, "n_gpus": n_gpus, "scaling": scaling,
+            "rows_are": "per GPU (weak)" if scaling == "weak" else "in total, split over the GPUs by row range (strong)"}
 
 
 def measured_peaks():
@@ -73,7 +84,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.002)
 
     def summary(self, t0: float, t1: float):
         if not self.ok:
@@ -122,17 +133,8 @@ def bind_to_gpu_numa_node(device_index: int):
         return None
 
 
-def dist_setup(n_gpus: int):
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        import torch
-        import torch.distributed as dist
-
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    return rank, world, local
+def env_ranks():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -174,12 +176,15 @@ def cpu_step_factory(rows: int):
     return step, n_chunks * CHUNK, threads
 
 
+REF_NOTE = ("CPU path of the reference: C restatement of rust-dataframe @ a8310afd + arrow-rs~2.0 semantics (oracle/oracle.c); "
+            "the Rust reference cannot be built in this image")
+
+
 def run_reference_arm(args, rank: int, world: int):
     if rank != 0:
         return
-    total_steps = args.steps + args.warmup
-    rows = int(min(ROWS, max(CHUNK, (60 * 2.5e8 / max(total_steps, 1)) // CHUNK * CHUNK)))
-    step, rows, threads = cpu_step_factory(rows)
+    step, rows, threads = cpu_step_factory(ROWS)   # always the full workload: the sample never shrinks silently
+    assert rows == ROWS
     for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
@@ -187,12 +192,13 @@ def run_reference_arm(args, rank: int, world: int):
         step()
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
-    sample = f"{rows} rows ({rows // CHUNK} chunks x {CHUNK}) per step, {args.steps} steps; add on {threads} threads (one per chunk, rayon mirror), sum on 1 thread"
+    sample = (f"{rows} rows ({rows // CHUNK} chunks x {CHUNK}) per step, {args.steps} steps; add on {threads} threads (one per chunk, rayon mirror), "
+              f"sum on 1 thread; output buffers allocated once")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_step": rows, "note": "CPU path of the reference: C restatement of rust-dataframe @ a8310afd + arrow-rs~2.0 semantics (oracle/oracle.c); the Rust reference cannot be built in this image"},
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": args.scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config_dict(args.gpus, args.scaling),
+        "detail": {"note": REF_NOTE, "rows_per_step": rows, "host_cpus": os.cpu_count()},
         "cpu_baseline": {"value": value, "unit": "rows/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -203,236 +209,283 @@ def run_reference_arm(args, rank: int, world: int):
 # ---------------------------------------------------------------------------------------------------------
 # GPU arm
 
-def run_gpu_arm(args, rank: int, world: int, local: int):
-    import rust_dataframe_b200 as rdf
-    from rust_dataframe_b200 import native as N
+def make_inputs(rdf, ctx, rank: int, world: int, scaling: str):
+    """This rank's shard of the two input columns, generated on the device (counter-based generator: the oracle can
+    regenerate any row).  weak: 25 x 4e6 rows per rank; strong: the same 1e8 rows split by row range."""
+    from rust_dataframe_b200 import parallel
 
-    ctx = rdf.Context(local)
-    lens = [CHUNK] * (ROWS // CHUNK)
-    row0 = rank * ROWS  # every rank owns its own 1e8-row shard of the Vec<RecordBatch> (weak scaling)
+    if scaling == "weak":
+        lens = [CHUNK] * (ROWS // CHUNK)
+        row0 = rank * ROWS
+        pieces = [(row0 + i * CHUNK, CHUNK) for i in range(len(lens))]
+    else:
+        full = [CHUNK] * (ROWS // CHUNK)
+        pieces = [(i * CHUNK + start, n) for i, start, n in parallel.shard_row_ranges(full, rank, world)]
+    # consecutive pieces form one generated column (row0 of piece k+1 = row0 of piece k + its length: contiguous ranges)
+    lens = [n for _, n in pieces]
+    row0 = pieces[0][0] if pieces else 0
     a = rdf.Column.generate(rdf.F64, lens, 0, -1e3, 1e3, seed=SEED, col_id=0, row0=row0, ctx=ctx)
     b = rdf.Column.generate(rdf.F64, lens, 0, -1e3, 1e3, seed=SEED, col_id=1, row0=row0, ctx=ctx)
     ctx.synchronize()
+    return a, b, lens
 
-    dist = None
-    torch = None
-    if world > 1:
-        import torch
-        import torch.distributed as dist
 
-    def combine(s: float, count: int):
-        """The one exchange step of the path: NCCL all-reduce of the per-GPU partial aggregates (blocking form)."""
-        if world == 1:
-            return s, count
-        return combine_finish(combine_start(s, count))
+class HotLoop:
+    """c = a + b materialised in HBM with sum(c) folded into the same pass (K5); the host keeps `depth` steps in flight:
+    step i's scalar (already combined across the ranks by the library) is fetched after step i+depth is enqueued."""
 
-    ring = [torch.zeros(2, dtype=torch.float64, device=f"cuda:{local}") for _ in range(8)] if world > 1 else []
-    ring_pos = [0]
+    def __init__(self, N, a, b, depth: int):
+        self.N, self.a, self.b, self.depth = N, a, b, depth
+        self.inflight = []
+        self.last = None
 
-    def combine_start(s: float, count: int):
-        """Enqueue the all-reduce of this step's partials; the result is read one step later."""
-        t = ring[ring_pos[0] % len(ring)]
-        ring_pos[0] += 1
-        t.copy_(torch.tensor([s, float(count)], dtype=torch.float64))
-        return t, dist.all_reduce(t, op=dist.ReduceOp.SUM, async_op=True)
-
-    def combine_finish(handle):
-        t, work = handle
-        work.wait()
-        r = t.cpu()
-        return float(r[0]), int(r[1])
-
-    def step_two_call():
-        """The reference's call sequence, blocking: c = add(a, b); s = sum(c) (two passes over c)."""
-        c = a.add(b)
-        s = c.sum()
-        c.free()
-        return combine(float(s), ROWS)
-
-    inflight = []
-    DEPTH = 1 if world == 1 else int(os.environ.get("BDF_BENCH_DEPTH", "3"))  # steps kept in flight by the host (the NCCL combine of step i runs under the next ones)
-
-    pending_combine = []
-
-    def retire():
-        c, fut = inflight.pop(0)
+    def retire(self):
+        c, fut = self.inflight.pop(0)
         r = fut.result()
         c.free()
-        if world == 1:
-            return float(r["sum"]), int(r["count"])
-        pending_combine.append(combine_start(float(r["sum"]), int(r["count"])))  # overlaps the next step
-        return combine_finish(pending_combine.pop(0)) if len(pending_combine) > 1 else None
+        self.last = (float(r["sum"]), int(r["count"]), int(r["rows"]))
 
-    def drain():
-        last = None
-        while inflight:
-            last = retire() or last
-        while pending_combine:
-            last = combine_finish(pending_combine.pop(0))
-        return last
+    def step(self):
+        self.inflight.append(self.a.binary_agg_async(self.N.ADD, self.b))
+        if len(self.inflight) > self.depth:
+            self.retire()
 
-    def step():
-        """c = a + b materialised in HBM with sum(c) folded into the same pass (K5); the host keeps one step in
-        flight: step i's scalar is fetched after step i+1 has been enqueued."""
-        inflight.append(a.binary_agg_async(N.ADD, b))
-        return retire() if len(inflight) > DEPTH else None
+    def drain(self):
+        while self.inflight:
+            self.retire()
+        return self.last
 
-    def barrier():
-        ctx.synchronize()
-        if world > 1:
-            import torch
 
-            dist.barrier(device_ids=[local])
-            torch.cuda.synchronize()
+def timed_loop(ctx, loop: HotLoop, steps: int, world: int):
+    """barrier; K steps between two events on the compute stream; drain; barrier.  Returns max-over-ranks ms."""
+    ctx.comm_barrier()
+    ctx.timer_start()
+    for _ in range(steps):
+        loop.step()
+    loop.drain()
+    ms = ctx.timer_stop()
+    ctx.comm_barrier()
+    if world > 1:
+        from rust_dataframe_b200 import native as N
 
-    for _ in range(max(args.warmup, 3)):
-        step()
-    drain()
-    # secondary figure: the unfused, blocking two-call sequence (what a caller of add() then sum() gets)
+        ms = float(ctx.comm_all_reduce([ms], N.MAX)[0])
+    return ms
+
+
+def run_gpu_arm(args, rank: int, world: int, local: int):
+    import rust_dataframe_b200 as rdf
+    from rust_dataframe_b200 import native as N
+    from rust_dataframe_b200 import parallel
+
+    ctx = rdf.Context(local)
+    if world > 1:
+        parallel.attach_communicator(ctx)   # ncclCommInitRank inside libb200df; aggregates are collective from here on
+    depth = 1 if world == 1 else int(os.environ.get("BDF_BENCH_DEPTH", "3"))
+    warmup = max(args.warmup, 3)
+
+    a, b, lens = make_inputs(rdf, ctx, rank, world, args.scaling)
+    rows_local = sum(lens)
+    rows_global = ROWS * world if args.scaling == "weak" else ROWS
+    loop = HotLoop(N, a, b, depth)
+    for _ in range(warmup):
+        loop.step()
+    loop.drain()
+
+    # secondary figure: the unfused, blocking two-call sequence (what a caller of add() then sum() gets on device columns)
+    def step_two_call():
+        c = a.add(b)
+        s = c.sum()          # collective at N > 1: the library returns the global sum
+        c.free()
+        return float(s)
+
+    two_steps = max(3, min(args.steps, 20))
     for _ in range(3):
         step_two_call()
-    barrier()
-    two_steps = max(3, min(args.steps, 20))
+    ctx.comm_barrier()
     ctx.timer_start()
     for _ in range(two_steps):
         step_two_call()
     two_call_ms = ctx.timer_stop() / two_steps
+
+    # cost of the combine alone: a blocking 4-in-1 aggregate of a tiny column with the collective on and off
+    combine_us = None
+    if world > 1:
+        tiny = rdf.Column.generate(rdf.I64, [1024], 3, seed=SEED, col_id=9, row0=rank * 1024, ctx=ctx)
+        reps = 200
+        t = {}
+        for mode in (True, False):
+            ctx.comm_collective(mode)
+            for _ in range(20):
+                tiny.aggregate_all_async().result()
+            ctx.comm_barrier() if mode else ctx.synchronize()
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                tiny.aggregate_all_async().result()
+            t[mode] = (time.perf_counter() - t0) / reps * 1e6
+        ctx.comm_collective(True)
+        tiny.free()
+        combine_us = {"blocking_aggregate_collective_us": t[True], "blocking_aggregate_local_us": t[False], "combine_us": t[True] - t[False]}
+
     sampler = ClockSampler(local)
     sampler.start()
     ctx.profile_read()  # drop warm-up records
     ctx.profile_enable(True)
-    barrier()
     launches0 = ctx.launch_count()
+    coll0 = ctx.comm_info()["collectives"]
     t_wall0 = time.perf_counter()
-    ctx.timer_start()
-    last = None
-    for _ in range(args.steps):
-        last = step() or last
-    last = drain() or last
-    ms = ctx.timer_stop()
-    barrier()
+    ms = timed_loop(ctx, loop, args.steps, world)
     t_wall1 = time.perf_counter()
     launches = ctx.launch_count() - launches0
+    collectives = ctx.comm_info()["collectives"] - coll0
     ctx.profile_enable(False)
     records = ctx.profile_read()
-    if sampler.ok and len([s for s in sampler.samples if t_wall0 <= s[0] <= t_wall1]) < 3:
-        t_extra = time.perf_counter()
-        while time.perf_counter() - t_extra < 0.15:  # same load, untimed, only to observe the clocks
-            step()
-        drain()
-        t_wall1_clk = time.perf_counter()
-    else:
-        t_wall1_clk = t_wall1
+    last = loop.last
+    # The timed window of the default run is a few ms: keep the same load running, untimed, for a FIXED number of extra steps
+    # (derived from the max-over-ranks time, so every rank runs the same count -- each step enqueues a collective) so that
+    # the NVML poller sees the clocks under this load.
+    extra = int(min(5000, max(0, math.ceil(150.0 / max(ms / args.steps, 1e-3)) - args.steps)))
+    for _ in range(extra):
+        loop.step()
+    loop.drain()
+    ctx.comm_barrier()
+    t_wall2 = time.perf_counter()
     sampler.stop_flag = True
     sampler.join(timeout=1)
-    clocks = sampler.summary(t_wall0, t_wall1_clk)
+    clocks = sampler.summary(t_wall0, t_wall2)
+    clocks["window"] = f"timed region + {extra} untimed steps of the same load"
 
-    if world > 1:
-        import torch
+    # ---- the other scaling series (N > 1): same loop over the other sharding ----
+    other = None
+    if world > 1 and not args.skip_other_series:
+        other_mode = "strong" if args.scaling == "weak" else "weak"
+        a.free(); b.free()
+        a, b, lens2 = make_inputs(rdf, ctx, rank, world, other_mode)
+        loop2 = HotLoop(N, a, b, depth)
+        for _ in range(warmup):
+            loop2.step()
+        loop2.drain()
+        ms2 = timed_loop(ctx, loop2, args.steps, world)
+        rows2 = ROWS * world if other_mode == "weak" else ROWS
+        other = {"scaling": other_mode, "value": rows2 * args.steps / (ms2 * 1e-3), "unit": "rows/s", "ms_per_step": ms2 / args.steps,
+                 "rows_total": rows2, "rows_this_rank": sum(lens2), "check": {"sum": loop2.last[0], "count": loop2.last[1]}}
+        a.free(); b.free()
+        a, b, lens = make_inputs(rdf, ctx, rank, world, args.scaling)
 
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-
-    # ---- e2e: host buffers in pinned memory, copies inside the timed region ----
-    e2e = None if args.skip_e2e else run_e2e(args, ctx, rdf, lens, a, b, world, local, combine, dist)
+    # ---- e2e: host buffers, copies inside the timed region ----
+    e2e = None if args.skip_e2e else run_e2e(args, ctx, rdf, N, lens, a, b, world, local)
 
     if rank != 0:
         return
     peak, peak_src = measured_peaks()
     bins = [r for r in records if r["kernel"] == "binary"]
-    reds = [r for r in records if r["kernel"] == "reduce"]
     add_ms = float(np.mean([r["ms"] for r in bins])) if bins else None
-    red_ms = float(np.mean([r["ms"] for r in reds])) if reds else None
-    add_bytes = bins[0]["bytes"] if bins else 24 * ROWS
+    add_bytes = bins[0]["bytes"] if bins else 24 * rows_local
     achieved = add_bytes / (add_ms * 1e-3) / 1e9 if add_ms else None
     roofline = {
-        "bound": "hbm", "kernel": "k_binary<double,ADD> (one launch over 25 chunks)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None, "peak_source": peak_src,
+        "bound": "hbm", "kernel": "k_binary<double,ADD,AGG> (one launch over this rank's chunks)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak if achieved else None, "traffic": None,
+        "traffic_source": None, "peak_source": peak_src,
         "algorithmic_bytes_per_launch": add_bytes, "avg_launch_ms": add_ms, "frac_of_8TBs_nominal": achieved / 8000.0 if achieved else None,
-        "sum_kernel": {"kernel": "k_reduce<double>", "avg_launch_ms": red_ms, "algorithmic_bytes_per_launch": reds[0]["bytes"] if reds else None,
-                       "achieved": (reds[0]["bytes"] / (red_ms * 1e-3) / 1e9) if red_ms else None},
-        "step_GBs_algorithmic_24B_per_row": 24 * ROWS / (ms / args.steps * 1e-3) / 1e9,
-        "two_call_unfused": {"ms_per_step": two_call_ms, "rows_per_s": ROWS * world / (two_call_ms * 1e-3),
-                             "note": "blocking add() then sum(): 32 B/row, two kernels + a host sync per step"},
+        "step_GBs_algorithmic_24B_per_row": 24 * rows_local / (ms / args.steps * 1e-3) / 1e9,
+        "two_call_unfused": {"ms_per_step": two_call_ms, "rows_per_s": rows_global / (two_call_ms * 1e-3),
+                             "note": "blocking add() then sum() on device columns: 32 B/row, two kernels + a host sync (+ the combine) per step"},
     }
     traffic_file = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(traffic_file):
+    if os.path.exists(traffic_file) and args.scaling == "weak":
         with open(traffic_file) as f:
-            roofline["traffic"] = json.load(f).get("k_binary_f64_add_bytes_per_launch")
+            tj = json.load(f)
+        roofline["traffic"] = tj.get("k_binary_f64_add_bytes_per_launch")
+        roofline["traffic_source"] = "static: ncu --set full capture committed under profiles/ (%s), not re-measured by this run" % tj.get("source", "profiles/traffic.json")
 
-    cpu = None
-    if (world == 1 or rank == 0) and not args.skip_cpu:
-        cpu = run_cpu_baseline()
+    cpu = None if args.skip_cpu else run_cpu_baseline()
 
-    value = ROWS * world * args.steps / (ms * 1e-3)
+    value = rows_global * args.steps / (ms * 1e-3)
     line = {
-        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": WORKLOAD, "rows_per_gpu": ROWS, "chunks": len(lens), "parallelism": f"shard{world}",
-                   "l2": "inputs (2.4 GB working set per step) are larger than the 126 MB L2; no flush needed",
+        "metric": METRIC, "value": value, "unit": "rows/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic", "config": config_dict(world, args.scaling),
+        "detail": {"rows_this_rank": rows_local, "chunks_this_rank": len(lens), "parallelism": f"shard{world}",
+                   "l2": "inputs (2.4 GB working set per step at 1e8 rows) are larger than the 126 MB L2; no flush needed",
                    "fused": "sum(c) is computed by the add kernel while c is written (c is still materialised): 24 B/row",
-                   "host_pipelining": f"{DEPTH} step(s) in flight: step i's scalar is read (and combined across ranks) after step i+{DEPTH} is enqueued",
-                   "collective": "none" if world == 1 else "1 NCCL all-reduce of the partial (sum,count) per step, enqueued asynchronously and read one step later"},
+                   "host_pipelining": f"{depth} step(s) in flight: step i's scalar is read after step i+{depth} is enqueued",
+                   "collective": "none" if world == 1 else "ONE grouped ncclAllReduce of the partial (sum,count,rows,min,max) per step, enqueued by libb200df on the stream that produced it; no collective is issued by bench.py inside the timed loop",
+                   "collectives_in_timed_region": int(collectives), "nccl_version": ctx.comm_info()["nccl_version"], "combine": combine_us},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
-        "check": {"sum": last[0], "count": last[1]},
+        "check": {"sum": last[0], "count": last[1], "rows": last[2]},
     }
+    if other is not None:
+        line["other_series"] = other
     print(json.dumps(line), flush=True)
 
 
-def run_e2e(args, ctx, rdf, lens, dev_a, dev_b, world, local, combine, dist):
-    """Same step through the public API with host buffers (pinned), H2D + D2H inside the timed region."""
-    from rust_dataframe_b200 import native as N
+def run_e2e(args, ctx, rdf, N, lens, dev_a, dev_b, world, local):
+    """The drop-in host entries with HOST buffers, H2D + D2H inside the timed region.  Variants:
+      dropin_pageable_fresh   a, b pageable; c into freshly allocated pageable buffers every step (MutableBuffer::new)
+      dropin_pageable_reused  a, b pageable; c into the same pageable buffers every step (an allocator that recycles)
+      dropin_registered       a, b and c in memory pinned once outside the loop (bdf_host_alloc / bdf_host_register)
+      device_chain_pinned     upload_many -> add with the sum folded in -> download (one PCIe crossing of c, pinned)
+    Each drop-in step = ScalarFunctions.add(a, b) [bdf_binary] then AggregateFunctions.sum(c) [bdf_aggregate]."""
+    steps = max(3, min(args.steps, 6))
+    n_rows = sum(lens)
+    # host copies of the same synthetic columns
+    pin_a = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    pin_b = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    host_a_pin = dev_a.download(into=pin_a)
+    host_b_pin = dev_b.download(into=pin_b)
+    host_a = [rdf.PrimitiveArray.from_numpy(x.value_slice().copy()) for x in host_a_pin]   # plain malloc'ed memory
+    host_b = [rdf.PrimitiveArray.from_numpy(x.value_slice().copy()) for x in host_b_pin]
+    pin_out = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    reuse_out = N.alloc_outputs(rdf.F64, lens, ctx, pinned=False)
+    for v, _, _ in reuse_out[1]:
+        v[:] = 0.0  # fault the pages in once
 
-    steps = max(3, min(args.steps, 8))
-    # host copies of the same synthetic columns, in pinned memory (what the Rust shim would hand over as Arrow buffers)
-    bufs_a = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
-    bufs_b = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
-    host_a = dev_a.download(into=bufs_a)
-    host_b = dev_b.download(into=bufs_b)
-    out_bufs = N.alloc_outputs(rdf.F64, lens, ctx, pinned=True)
+    def dropin(a, b, into):
+        outs, bufs = into if into is not None else N.alloc_outputs(rdf.F64, lens, ctx, pinned=False)
+        for i in range(len(bufs)):
+            outs[i].len = bufs[i][0].shape[0]
+        N.raise_for_status(N.lib().bdf_binary(ctx.handle, N.ADD, rdf.F64, len(a), N.make_views(a), len(b), N.make_views(b), outs))
+        c = N.collect_outputs(rdf.F64, outs, bufs)
+        return float(rdf.AggregateFunctions.sum(c, dtype=rdf.F64, ctx=ctx))
 
-    def step():
-        ca, cb = rdf.Column.upload_many([host_a, host_b], ctx=ctx, asynchronous=True)  # a0,b0,a1,b1,... over PCIe
+    def chain():
+        ca, cb = rdf.Column.upload_many([host_a_pin, host_b_pin], ctx=ctx, asynchronous=True)  # a0,b0,a1,b1,... over PCIe
         cc, fut = ca.binary_agg_async(N.ADD, cb)      # per upload group, as soon as its chunks have landed
-        cc.download_begin(out_bufs)                   # D2H of group g overlaps H2D of group g+1
+        cc.download_begin(pin_out)                    # D2H of group g overlaps H2D of group g+1
         r = fut.result()
-        cc.download_end(out_bufs)
+        cc.download_end(pin_out)
         for col in (ca, cb, cc):
             col.free()
-        return combine(float(r["sum"]), int(r["count"]))
+        return float(r["sum"])
 
-    def barrier():
+    variants = {
+        "dropin_pageable_fresh": (lambda: dropin(host_a, host_b, None), 3 * 8 * n_rows, 8 * n_rows + 8),
+        "dropin_pageable_reused": (lambda: dropin(host_a, host_b, reuse_out), 3 * 8 * n_rows, 8 * n_rows + 8),
+        "dropin_registered": (lambda: dropin(host_a_pin, host_b_pin, pin_out), 3 * 8 * n_rows, 8 * n_rows + 8),
+        "device_chain_pinned": (chain, 2 * 8 * n_rows, 8 * n_rows + 8),
+    }
+    out = {}
+    for name, (fn, h2d, d2h) in variants.items():
+        for _ in range(2):
+            fn()
+        ctx.comm_barrier()
+        t0 = time.perf_counter()
+        last = None
+        for _ in range(steps):
+            last = fn()
         ctx.synchronize()
+        ms = (time.perf_counter() - t0) * 1e3
+        ctx.comm_barrier()
         if world > 1:
-            import torch
-
-            dist.barrier(device_ids=[local])
-            torch.cuda.synchronize()
-
-    for _ in range(2):
-        step()
-    barrier()
-    ctx.timer_start()
-    last = None
-    for _ in range(steps):
-        last = step()
-    ms = ctx.timer_stop()
-    barrier()
-    if world > 1:
-        import torch
-
-        t = torch.tensor([ms], dtype=torch.float64, device=f"cuda:{local}")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    h2d = 2 * 8 * ROWS
-    d2h = 8 * ROWS + 8
-    return {"value": ROWS * world * steps / (ms * 1e-3), "unit": "rows/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-            "check_sum": last[0] if last else None,
-            "ms_per_step": ms / steps, "steps": steps,
-            "api": "Column.upload_many([a,b]) [pinned host, async] -> binary_agg_async(ADD) -> download_begin/end(c) [pinned host] + scalar",
-            "pcie_GBs": (h2d + d2h) / (ms / steps * 1e-3) / 1e9}
+            ms = float(ctx.comm_all_reduce([ms], N.MAX)[0])
+        rows_total = ROWS * world if args.scaling == "weak" else ROWS
+        out[name] = {"value": rows_total * steps / (ms * 1e-3), "unit": "rows/s", "ms_per_step": ms / steps, "h2d_bytes_per_step": h2d,
+                     "d2h_bytes_per_step": d2h, "pcie_GBs_this_rank": (h2d + d2h) / (ms / steps * 1e-3) / 1e9, "check_sum": last}
+    head = dict(out["dropin_pageable_fresh"])
+    head.update({"steps": steps, "timer": "host wall clock around the blocking calls (they return when the results are in host memory), max over ranks",
+                 "api": "ScalarFunctions.add(a, b) -> bdf_binary(ADD) on pageable host buffers, c into freshly allocated pageable buffers; "
+                        "then AggregateFunctions.sum(c) -> bdf_aggregate(SUM) re-reading c from the host (two calls, like the reference API)",
+                 "variants": {k: v for k, v in out.items() if k != "dropin_pageable_fresh"}})
+    return head
 
 
 def run_cpu_baseline():
@@ -460,7 +513,7 @@ def run_cpu_baseline():
         except Exception as e:  # pragma: no cover
             res_pa = {"rows_per_s": None, "note": f"unavailable: {e}"}
         return {"value": rows * reps / dt, "unit": "rows/s", "cores": threads, "kind": "port", "arrow_cpp_pyarrow": res_pa,
-                "sample": f"{reps} passes over the full {rows}-row workload; add on {threads} threads (one per chunk, like rayon), sum sequential on 1 thread; host has {os.cpu_count()} cpus",
+                "sample": f"{reps} passes over the full {rows}-row workload; add on {threads} threads (one per chunk, like rayon), sum sequential on 1 thread; output buffers allocated once; host has {os.cpu_count()} cpus",
                 "ms_per_step": dt / reps * 1e3}
     except Exception as e:  # pragma: no cover
         return {"value": None, "unit": "rows/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
@@ -472,22 +525,23 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="primary series; at N > 1 the other one is measured too and reported under other_series")
+    ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4, 5], help="1 = the headline metric; 3/4/5 = the other BASELINE configs")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the CPU baseline leg")
+    ap.add_argument("--skip-other-series", action="store_true", help="N > 1: measure only the primary scaling series")
     args = ap.parse_args()
-    if args.impl == "reference":
-        rank = int(os.environ.get("RANK", "0"))
-        run_reference_arm(args, rank, int(os.environ.get("WORLD_SIZE", "1")))
-        return
-    rank, world, local = dist_setup(args.gpus)
-    bind_to_gpu_numa_node(local)
-    try:
-        run_gpu_arm(args, rank, world, local)
-    finally:
-        if world > 1:
-            import torch.distributed as dist
+    rank, world, local = env_ranks()
+    if args.config != 1:
+        from benchmarks import configs_bench
 
-            dist.destroy_process_group()
+        configs_bench.main(args, rank, world, local)
+        return
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+    bind_to_gpu_numa_node(local)
+    run_gpu_arm(args, rank, world, local)
 
 
 if __name__ == "__main__":

@@ -48,7 +48,7 @@ extern "C" {
 #pragma GCC visibility push(default) /* the library is built with -fvisibility=hidden; these are its exports */
 #endif
 
-#define BDF_ABI_VERSION 1
+#define BDF_ABI_VERSION 2
 
 /* Arrow primitive types, in arrow::datatypes::DataType order. */
 typedef enum {
@@ -73,7 +73,7 @@ typedef enum { BDF_AND = 0, BDF_OR, BDF_NOT } bdf_boolop;
 
 typedef enum {
     BDF_OK = 0, BDF_LENGTH_MISMATCH = 1, BDF_DIVIDE_BY_ZERO = 2, BDF_UNSUPPORTED = 3, BDF_CUDA = 4,
-    BDF_NCCL = 5 /* reserved */, BDF_OOM = 6, BDF_WOULD_PANIC = 7, BDF_INVALID = 8
+    BDF_NCCL = 5 /* the communicator (bdf_comm_*) or a collective failed */, BDF_OOM = 6, BDF_WOULD_PANIC = 7, BDF_INVALID = 8
 } bdf_status;
 
 /* One chunk = one PrimitiveArray<T> in Arrow memory layout (ArrayData: buffers[0], null bitmap, len, offset). */
@@ -103,6 +103,7 @@ typedef struct {
     int64_t  rows;           /* total slots                                                            */
     int32_t  any_valid;      /* 0 => min/max are None                                                  */
     int32_t  would_panic;    /* 1 => some chunk is empty/all-null: reference max/min .unwrap() panics  */
+    int64_t  n_chunks;       /* chunks aggregated (0 => Iterator::max over an empty Vec: None)         */
 } bdf_agg4;
 
 typedef struct bdf_ctx bdf_ctx;
@@ -116,6 +117,28 @@ int          bdf_init(int device, bdf_ctx** out);   /* one context per GPU (one 
 void         bdf_destroy(bdf_ctx* ctx);
 int          bdf_synchronize(bdf_ctx* ctx);
 int          bdf_device_info(bdf_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);
+
+/* ---- multi-GPU: one context per GPU, the contexts of a job form a communicator ---------------------
+ * The Vec<RecordBatch> is sharded over the GPUs by chunk (parallel over the same axis as the reference's rayon
+ * par_iter, src/functions/scalar.rs:28-31,99-102): elementwise operators and casts need no exchange at all.  The
+ * cross-chunk fold of an aggregate (src/functions/aggregate.rs:12-31,70-93) becomes [this GPU's chunks] -> ONE grouped
+ * ncclAllReduce over NVLink (sum/count/rows: ncclSum on the wrapping 64-bit patterns; min/max: ncclMin/ncclMax on
+ * order-preserving keys; float sums: all-gathered and folded in rank order), enqueued by the library on the stream
+ * that produced the partials -- no host round trip.  After bdf_comm_attach every aggregate entry (bdf_aggregate*,
+ * bdf_avg*, bdf_binary_agg_dev*, bdf_eval_expr_agg_dev*) is COLLECTIVE: all ranks make the same calls in the same
+ * order and every rank receives the aggregate of the whole column; DivideByZero is agreed on by all ranks.
+ * bdf_comm_collective(ctx, 0) switches back to per-rank results.  NCCL is bound at run time (libnccl.so.2).
+ *   process per GPU:  rank 0 calls bdf_comm_unique_id, ships the 128 bytes to the others (any side channel), every
+ *                     rank calls bdf_comm_attach(ctx, id, rank, world)  [ncclCommInitRank];
+ *   one process:      bdf_init_multi (below) owns all GPUs of the box  [ncclCommInitAll]. */
+#define BDF_COMM_ID_BYTES 128
+int  bdf_comm_unique_id(uint8_t* id /* BDF_COMM_ID_BYTES */);
+int  bdf_comm_attach(bdf_ctx* ctx, const uint8_t* id, int rank, int world);
+int  bdf_comm_detach(bdf_ctx* ctx);
+int  bdf_comm_info(bdf_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version, int64_t* collectives_enqueued);
+int  bdf_comm_collective(bdf_ctx* ctx, int on);
+int  bdf_comm_barrier(bdf_ctx* ctx);    /* drains this context's streams, then returns once every rank has arrived */
+int  bdf_comm_all_reduce_f64(bdf_ctx* ctx, int op /* BDF_SUM | BDF_MIN | BDF_MAX */, int64_t n, double* inout); /* blocking */
 
 /* Pinned host memory ("Arrow buffers are pinned and copied to device once per batch"). */
 int          bdf_host_alloc(bdf_ctx* ctx, size_t bytes, void** out);
@@ -204,7 +227,13 @@ int  bdf_binary_agg_dev(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col
  * the result has reached the host, converts it and CONSUMES the future (out may be NULL to discard). */
 int  bdf_binary_agg_dev_async(bdf_ctx* ctx, int op, const bdf_col* left, const bdf_col* right, bdf_col** out, bdf_future** fut);
 int  bdf_aggregate_all_dev_async(bdf_ctx* ctx, const bdf_col* in, bdf_future** fut);
-int  bdf_future_wait(bdf_ctx* ctx, bdf_future* fut, bdf_agg4* out);
+/* sum/min/max/count of up to 64 columns in one call (BASELINE config 3: 8 x Int64): one reduction per column, ONE host
+ * wait and -- on a rank of a communicator -- ONE grouped collective for all of them.  out / the future carry n_cols
+ * records in column order; the blocking form also evaluates would_panic. */
+int  bdf_aggregate_all_many_dev(bdf_ctx* ctx, int32_t n_cols, const bdf_col* const* cols, bdf_agg4* out /* n_cols */);
+int  bdf_aggregate_all_many_dev_async(bdf_ctx* ctx, int32_t n_cols, const bdf_col* const* cols, bdf_future** fut);
+int  bdf_future_count(const bdf_future* fut);   /* records bdf_future_wait will write */
+int  bdf_future_wait(bdf_ctx* ctx, bdf_future* fut, bdf_agg4* out /* bdf_future_count(fut) records */);
 void bdf_col_free(bdf_ctx* ctx, bdf_col* col);
 
 /* ---- DataFrame::sort (src/dataframe.rs:194-222): lexsort_to_indices + take ------------------------------------------

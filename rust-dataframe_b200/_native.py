@@ -40,7 +40,7 @@ class Out(C.Structure):
 
 class Agg4(C.Structure):
     _fields_ = [("sum", C.c_uint64), ("min", C.c_uint64), ("max", C.c_uint64), ("count", C.c_int64),
-                ("rows", C.c_int64), ("any_valid", C.c_int32), ("would_panic", C.c_int32)]
+                ("rows", C.c_int64), ("any_valid", C.c_int32), ("would_panic", C.c_int32), ("n_chunks", C.c_int64)]
 
 
 class ExprNode(C.Structure):
@@ -98,6 +98,16 @@ def lib() -> C.CDLL:
         "bdf_destroy": ([vp], None),
         "bdf_synchronize": ([vp], C.c_int),
         "bdf_device_info": ([vp, P(i32), P(i32), P(i32), P(i64)], C.c_int),
+        "bdf_comm_unique_id": ([P(C.c_uint8)], C.c_int),
+        "bdf_comm_attach": ([vp, P(C.c_uint8), C.c_int, C.c_int], C.c_int),
+        "bdf_comm_detach": ([vp], C.c_int),
+        "bdf_comm_info": ([vp, P(i32), P(i32), P(i32), P(i64)], C.c_int),
+        "bdf_comm_collective": ([vp, C.c_int], C.c_int),
+        "bdf_comm_barrier": ([vp], C.c_int),
+        "bdf_comm_all_reduce_f64": ([vp, C.c_int, i64, P(C.c_double)], C.c_int),
+        "bdf_aggregate_all_many_dev": ([vp, i32, P(vp), P(Agg4)], C.c_int),
+        "bdf_aggregate_all_many_dev_async": ([vp, i32, P(vp), P(vp)], C.c_int),
+        "bdf_future_count": ([vp], C.c_int),
         "bdf_host_alloc": ([vp, C.c_size_t, P(vp)], C.c_int),
         "bdf_host_free": ([vp, vp], C.c_int),
         "bdf_host_register": ([vp, vp, C.c_size_t], C.c_int),
@@ -159,7 +169,7 @@ def lib() -> C.CDLL:
         fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
         fn.argtypes = args
         fn.restype = res
-    if L.bdf_abi_version() != 1:
+    if L.bdf_abi_version() != 2:
         raise RuntimeError("libb200df.so ABI version mismatch")
     _lib = L
     return L
@@ -167,6 +177,8 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "bdf_abi_version", "bdf_last_error", "bdf_init", "bdf_destroy", "bdf_synchronize", "bdf_device_info",
+    "bdf_comm_unique_id", "bdf_comm_attach", "bdf_comm_detach", "bdf_comm_info", "bdf_comm_collective", "bdf_comm_barrier",
+    "bdf_comm_all_reduce_f64", "bdf_aggregate_all_many_dev", "bdf_aggregate_all_many_dev_async", "bdf_future_count",
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
     "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_upload_many", "bdf_col_wait", "bdf_col_describe",
     "bdf_col_chunk_info", "bdf_binary_dev", "bdf_unary_dev", "bdf_cast_dev", "bdf_aggregate_dev",
@@ -266,6 +278,39 @@ class Context:
 
     def pinned(self, nbytes: int) -> PinnedBuffer:
         return PinnedBuffer(self, nbytes)
+
+    # -- multi-GPU: this context as a rank of a communicator (include/b200df.h "multi-GPU") --
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = (C.c_uint8 * 128)()
+        raise_for_status(lib().bdf_comm_unique_id(buf))
+        return bytes(buf)
+
+    def comm_attach(self, unique_id: bytes, rank: int, world: int):
+        """ncclCommInitRank: afterwards every aggregate entry is collective and returns the aggregate of the whole
+        (sharded) column on every rank."""
+        buf = (C.c_uint8 * 128)(*unique_id)
+        raise_for_status(lib().bdf_comm_attach(self.handle, buf, int(rank), int(world)))
+
+    def comm_detach(self):
+        raise_for_status(lib().bdf_comm_detach(self.handle))
+
+    def comm_info(self) -> dict:
+        r, w, v, n = C.c_int32(), C.c_int32(), C.c_int32(), C.c_int64()
+        raise_for_status(lib().bdf_comm_info(self.handle, C.byref(r), C.byref(w), C.byref(v), C.byref(n)))
+        return {"rank": r.value, "world": w.value, "nccl_version": v.value, "collectives": n.value}
+
+    def comm_collective(self, on: bool):
+        raise_for_status(lib().bdf_comm_collective(self.handle, 1 if on else 0))
+
+    def comm_barrier(self):
+        raise_for_status(lib().bdf_comm_barrier(self.handle))
+
+    def comm_all_reduce(self, values, op: int = SUM):
+        """Blocking all-reduce of a few float64 values (timing max-over-ranks and the like)."""
+        arr = np.ascontiguousarray(np.atleast_1d(np.asarray(values, dtype=np.float64))).copy()
+        raise_for_status(lib().bdf_comm_all_reduce_f64(self.handle, op, arr.shape[0], arr.ctypes.data_as(C.POINTER(C.c_double))))
+        return arr
 
     def pinned_array(self, dtype: int, values: np.ndarray, mask: Optional[np.ndarray] = None) -> PrimitiveArray:
         """Copy a numpy array (and optional bool mask, True = valid) into pinned host memory."""

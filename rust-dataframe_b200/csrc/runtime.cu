@@ -22,6 +22,7 @@
 
 #include "../../include/b200df.h"
 #include "common.cuh"
+#include "comm.cuh"
 
 using namespace bdf;
 
@@ -48,6 +49,18 @@ int set_error(int status, const char* msg) {   // for the host-only translation 
 }  // namespace bdf
 
 static int cuda_status(cudaError_t e) { return e == cudaErrorMemoryAllocation ? BDF_OOM : BDF_CUDA; }
+
+// Set by the communicator layer (comm.cu reports NCCL failures as text + cudaErrorUnknown): turns the next
+// fail_cuda into BDF_NCCL.
+static thread_local std::string g_nccl_err;
+static int fail_cuda(cudaError_t e, const char* what) {
+    if (!g_nccl_err.empty()) {
+        const std::string m = g_nccl_err;
+        g_nccl_err.clear();
+        return fail(BDF_NCCL, "%s: %s", what, m.c_str());
+    }
+    return fail(cuda_status(e), "%s failed: %s", what, cudaGetErrorString(e));
+}
 
 #define CK(call)                                                                                       \
     do {                                                                                               \
@@ -100,11 +113,16 @@ struct bdf_col {
 
 // Result of an aggregate that is still in flight (or done): a pinned slot + the event that guards it.
 struct bdf_future {
-    int dtype;
-    int fused;       // which kernel produced the keys: 1 = k_binary AGG, 2 = k_reduce (see convert_agg)
-    int slot;        // index into h_agg
-    int64_t rows;
-    cudaEvent_t ev;
+    int n = 1;                   // number of aggregates the future carries (one per column of a multi-column call)
+    int fused = 1;               // which kernel produced the keys: 1 = k_binary AGG, 2 = k_reduce (see convert_agg)
+    int slot = 0;                // first index into h_agg: n records, or 2n ({AggDev, {rows, panics, chunks}}) when global
+    bool global = false;         // combined across the ranks of the communicator (comm.cuh)
+    int lslot = 0;               // global only: first index into d_local (the per-rank records the collective reads)
+    std::vector<int> dtypes;
+    std::vector<int64_t> rows;   // local rows per aggregate
+    std::vector<uint32_t> panics;  // local chunks that are empty or all-null (max/min .unwrap() would panic)
+    std::vector<uint32_t> chunks;  // local chunk count
+    cudaEvent_t ev = nullptr;
 };
 
 struct ProfEntry {
@@ -210,6 +228,12 @@ struct bdf_ctx {
     bool profiling = false;
     std::vector<ProfEntry> prof;
     int64_t launches = 0;
+    // multi-GPU: the communicator this context is a rank of (nullptr = a lone GPU) -- comm.cuh
+    Comm* comm = nullptr;
+    bool collective = true;             // aggregates are combined across the ranks (every rank makes the same calls)
+    AggDev* d_local = nullptr;          // per-rank aggregate records awaiting their collective (ring of kAggSlots)
+    int local_next = 0;
+    int64_t collectives = 0;            // grouped NCCL calls enqueued since the communicator was attached
 };
 
 static constexpr int kAggSlots = 4096;
@@ -422,8 +446,9 @@ static int64_t reduce_bytes(const bdf_col* col, int64_t begin, int64_t end) {
     return b;
 }
 
-// Launch one reduce over chunks [begin,end) of col into h_agg[slot] (device-mapped host memory).  Caller has made the stream wait.
-static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t end, int slot) {
+// Launch one reduce over chunks [begin,end) of col into *result (device-mapped host memory: c->h_agg_dev + slot, or a
+// device record that a collective will read).  Caller has made the stream wait.
+static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t end, AggDev* result) {
     const int64_t n = end - begin;
     const int tile = elems_per_tile(col->dtype);
     void *hp = nullptr, *dp = nullptr;
@@ -450,7 +475,7 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
         LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // k_reduce + k_finish
         CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->s_compute));
         c->launches++;
-        CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, c->h_agg_dev + slot, c->s_compute));
+        CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, result, c->s_compute));
     }
     return BDF_OK;
 }
@@ -466,7 +491,7 @@ static int ensure_null_counts(bdf_ctx* c, bdf_col* col) {
     wait_groups(c->s_compute, col, 0, (int64_t)col->chunks.size());
     for (size_t k = 0; k < unknown.size(); k += kAggSlots) {
         const size_t m = std::min<size_t>(kAggSlots, unknown.size() - k);
-        for (size_t j = 0; j < m; j++) TRY(reduce_range(c, col, unknown[k + j], unknown[k + j] + 1, (int)j));
+        for (size_t j = 0; j < m; j++) TRY(reduce_range(c, col, unknown[k + j], unknown[k + j] + 1, c->h_agg_dev + j));
         CK(cudaStreamSynchronize(c->s_compute));
         for (size_t j = 0; j < m; j++) {
             const int64_t i = unknown[k + j];
@@ -713,7 +738,18 @@ static bool cast_is_fallible(int from, int to) {
     return tw <= fw;            // unsigned -> signed: needs a strictly wider target
 }
 
-static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out);
+static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out, int n = 1);
+static bool is_global(const bdf_ctx* c) { return c->comm != nullptr && c->collective; }
+static AggDev* future_target(bdf_ctx* c, const bdf_future* f, int i);
+static cudaError_t future_combine(bdf_ctx* c, bdf_future* f, cudaStream_t s);
+// The DivideByZero flag of a sharded divide: max over the ranks, so that every rank returns the same status.
+static cudaError_t flag_allreduce(bdf_ctx* c) {
+    std::string err;
+    c->collectives++;
+    cudaError_t e = comm_allreduce_max_i32(c->comm, c->d_flag, 1, c->s_compute, &err);
+    if (e != cudaSuccess && !err.empty()) g_nccl_err = err;
+    return e;
+}
 
 // One of three rotating per-tile partial buffers (K5 and fused expressions): grown on demand, reused once the
 // k_finish that last read it has run.
@@ -808,14 +844,17 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
             // fold the per-tile partials on the finish stream: the next operator on the compute stream does not wait
             c->launches++;
             for (auto& g : o->groups) cudaStreamWaitEvent(c->s_fin, g.ev, 0);
-            e = launch_finish(dtype_is_float(dtype), partials, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->h_agg_dev + f->slot, c->s_fin);
-            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
+            e = launch_finish(dtype_is_float(dtype), partials, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, future_target(c, f, 0), c->s_fin);
             if (e == cudaSuccess) e = cudaEventRecord(pb->done, c->s_fin);
             pb->used = true;
+            f->chunks[0] = (uint32_t)n;
+            if (e == cudaSuccess) e = future_combine(c, f, c->s_fin);   // ranks of a communicator: one grouped NCCL reduction
+            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
         }
         if (e == cudaSuccess && op == BDF_DIV) {
-            // DivideByZero must be returned INSTEAD of data: wait for the flag.
-            e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
+            // DivideByZero must be returned INSTEAD of data: wait for the flag (every rank of a communicator takes the same exit).
+            if (is_global(c)) e = flag_allreduce(c);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
             if (e == cudaSuccess && *c->h_flag) {
                 col_release(c, o);
@@ -828,7 +867,7 @@ static int binary_dev(bdf_ctx* c, int op, const bdf_col* l, const bdf_col* r, bd
         cudaGetLastError();
         col_release(c, o);
         if (f) { ev_put(c, f->ev); delete f; }
-        return st != BDF_OK ? st : fail(cuda_status(e), "binary op failed: %s", cudaGetErrorString(e));
+        return st != BDF_OK ? st : fail_cuda(e, "binary op");
     }
     *out = o;
     if (fut) *fut = f;
@@ -913,15 +952,49 @@ static int realign(bdf_ctx* c, const bdf_col* in, bdf_col** out) {
     return map_dev(c, true, in->dtype, in, out);
 }
 
-static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out) {
+// A future over n aggregates.  On a context that is a rank of a communicator (collective mode) the kernels write their
+// per-rank records to device memory (d_local) and future_combine enqueues the grouped NCCL reduction that delivers the
+// GLOBAL records to the pinned slots; otherwise the kernels write the pinned slots themselves.
+static int future_new(bdf_ctx* c, int dtype, int fused, int64_t rows, bdf_future** out, int n) {
+    if (n < 1 || n > kCommMaxCols) return fail(BDF_INVALID, "an aggregate call takes 1..%d columns", kCommMaxCols);
     bdf_future* f = new (std::nothrow) bdf_future();
     if (!f) return fail(BDF_OOM, "host allocation failed");
-    f->dtype = dtype; f->fused = fused; f->rows = rows; f->ev = nullptr;
-    f->slot = kAggSlots + (c->fut_next++ % kAggSlots);  // upper half of h_agg/d_agg is the future ring
+    f->n = n; f->fused = fused; f->global = is_global(c);
+    f->dtypes.assign((size_t)n, dtype); f->rows.assign((size_t)n, rows); f->panics.assign((size_t)n, 0u); f->chunks.assign((size_t)n, 1u);
+    const int words = f->global ? 2 * n : n;
+    if (c->fut_next % kAggSlots + words > kAggSlots) c->fut_next += kAggSlots - c->fut_next % kAggSlots;  // keep the block contiguous
+    f->slot = kAggSlots + c->fut_next % kAggSlots;  // upper half of h_agg is the future ring
+    c->fut_next += words;
+    if (f->global) {
+        if (c->local_next % kAggSlots + n > kAggSlots) c->local_next += kAggSlots - c->local_next % kAggSlots;
+        f->lslot = c->local_next % kAggSlots;
+        c->local_next += n;
+    }
     cudaError_t e = ev_get(c, &f->ev);
     if (e != cudaSuccess) { delete f; return fail(cuda_status(e), "event creation failed: %s", cudaGetErrorString(e)); }
     *out = f;
     return BDF_OK;
+}
+
+// Where the kernels of aggregate i of the future deliver their folded record.
+static AggDev* future_target(bdf_ctx* c, const bdf_future* f, int i) {
+    return f->global ? c->d_local + f->lslot + i : c->h_agg_dev + f->slot + i;
+}
+
+// Global futures: enqueue the ONE grouped collective on the stream that produced the records (no host round trip).
+static cudaError_t future_combine(bdf_ctx* c, bdf_future* f, cudaStream_t s) {
+    if (!f->global) return cudaSuccess;
+    unsigned long long fmask = 0, rows[kCommMaxCols];
+    for (int i = 0; i < f->n; i++) {
+        if (dtype_is_float(f->dtypes[i])) fmask |= 1ull << i;
+        rows[i] = (unsigned long long)f->rows[i];
+    }
+    std::string err;
+    c->collectives++;
+    c->launches += 2;  // pack + unpack (the NCCL kernel itself is not ours)
+    cudaError_t e = comm_combine(c->comm, fmask, f->n, c->d_local + f->lslot, rows, f->panics.data(), f->chunks.data(), c->h_agg_dev + f->slot, s, &err);
+    if (e != cudaSuccess && !err.empty()) g_nccl_err = err;
+    return e;
 }
 
 // AggDev (device format) -> bdf_agg4 (ABI format: T::Native bit patterns)
@@ -948,26 +1021,69 @@ static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf
     out->any_valid = a.count > 0;
 }
 
-static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
-    if (col->dtype == kBool) return fail(BDF_UNSUPPORTED, "aggregate of a boolean column");
-    const int64_t n = (int64_t)col->chunks.size();
+// Chunks of the column that are empty or all-null: the reference's max/min .unwrap() a None there (aggregate.rs:19,29).
+static int count_panic_chunks(bdf_ctx* c, bdf_col* col, uint32_t* out) {
+    TRY(ensure_null_counts(c, col));
+    uint32_t k = 0;
+    for (size_t i = 0; i < col->chunks.size(); i++)
+        if (col->chunks[i].len - col->null_counts[i] == 0) k++;
+    *out = k;
+    return BDF_OK;
+}
+
+// sum/min/max/count of n columns: one k_reduce + k_finish per column on the compute stream and -- on a rank of a
+// communicator -- ONE grouped collective for all of them.  need_counts: also evaluate the would-panic rule (may
+// synchronise to learn null counts of uploaded columns).
+static int aggregate_many_dev_async(bdf_ctx* c, int n_cols, bdf_col* const* cols, bool need_counts, bdf_future** fut) {
+    if (n_cols < 1 || n_cols > kCommMaxCols) return fail(BDF_INVALID, "an aggregate call takes 1..%d columns", kCommMaxCols);
+    for (int k = 0; k < n_cols; k++) {
+        if (!cols[k]) return fail(BDF_INVALID, "null column");
+        if (cols[k]->dtype == kBool) return fail(BDF_UNSUPPORTED, "aggregate of a boolean column");
+    }
+    std::vector<uint32_t> panics((size_t)n_cols, 0u);
+    if (need_counts)
+        for (int k = 0; k < n_cols; k++) TRY(count_panic_chunks(c, cols[k], &panics[k]));
     bdf_future* f = nullptr;
-    TRY(future_new(c, col->dtype, 2, col->total_len, &f));
-    wait_groups(c->s_compute, col, 0, n);
-    int st = reduce_range(c, col, 0, n, f->slot);
+    TRY(future_new(c, cols[0]->dtype, 2, 0, &f, n_cols));
+    int st = BDF_OK;
+    for (int k = 0; k < n_cols && st == BDF_OK; k++) {
+        bdf_col* col = cols[k];
+        const int64_t n = (int64_t)col->chunks.size();
+        f->dtypes[k] = col->dtype; f->rows[k] = col->total_len; f->panics[k] = panics[k]; f->chunks[k] = (uint32_t)n;
+        wait_groups(c->s_compute, col, 0, n);
+        st = reduce_range(c, col, 0, n, future_target(c, f, k));
+    }
     cudaError_t e = cudaSuccess;
-    if (st == BDF_OK) e = cudaEventRecord(f->ev, c->s_compute);
+    if (st == BDF_OK) e = future_combine(c, f, c->s_compute);
+    if (st == BDF_OK && e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
     if (st != BDF_OK || e != cudaSuccess) {
         ev_put(c, f->ev); delete f;
-        return st != BDF_OK ? st : fail(cuda_status(e), "aggregate failed: %s", cudaGetErrorString(e));
+        return st != BDF_OK ? st : fail_cuda(e, "aggregate");
     }
     *fut = f;
     return BDF_OK;
 }
 
+static int aggregate_all_dev_async(bdf_ctx* c, bdf_col* col, bdf_future** fut) {
+    return aggregate_many_dev_async(c, 1, &col, false, fut);
+}
+
+// Waits for the future, converts its n records into out[0..n) and consumes it.
 static int future_wait(bdf_ctx* c, bdf_future* f, bdf_agg4* out) {
     cudaError_t e = cudaEventSynchronize(f->ev);
-    if (e == cudaSuccess && out) convert_agg(f->dtype, f->fused, c->h_agg[f->slot], f->rows, out);
+    if (e == cudaSuccess && out)
+        for (int i = 0; i < f->n; i++) {
+            if (f->global) {
+                const AggDev& x = c->h_agg[f->slot + 2 * i + 1];   // {rows, panics, chunks} summed over the ranks
+                convert_agg(f->dtypes[i], f->fused, c->h_agg[f->slot + 2 * i], (int64_t)x.sum_bits, &out[i]);
+                out[i].would_panic = x.min_bits != 0;
+                out[i].n_chunks = (int64_t)x.max_bits;
+            } else {
+                convert_agg(f->dtypes[i], f->fused, c->h_agg[f->slot + i], f->rows[i], &out[i]);
+                out[i].would_panic = f->panics[i] != 0;
+                out[i].n_chunks = (int64_t)f->chunks[i];
+            }
+        }
     ev_put(c, f->ev);
     delete f;
     if (e != cudaSuccess) return fail(cuda_status(e), "waiting for an aggregate failed: %s", cudaGetErrorString(e));
@@ -975,15 +1091,21 @@ static int future_wait(bdf_ctx* c, bdf_future* f, bdf_agg4* out) {
 }
 
 static int aggregate_all_dev(bdf_ctx* c, bdf_col* col, bool need_counts, bdf_agg4* out) {
-    const int64_t n = (int64_t)col->chunks.size();
     bdf_future* f = nullptr;
-    TRY(aggregate_all_dev_async(c, col, &f));
-    TRY(future_wait(c, f, out));
-    if (need_counts) {
-        TRY(ensure_null_counts(c, col));
-        for (int64_t i = 0; i < n; i++)
-            if (col->chunks[i].len - col->null_counts[i] == 0) out->would_panic = 1;
-    }
+    TRY(aggregate_many_dev_async(c, 1, &col, need_counts, &f));
+    return future_wait(c, f, out);
+}
+
+// count is metadata (aggregate.rs:70-80); on a rank of a communicator the other ranks' chunks count too.
+static int count_global(bdf_ctx* c, int64_t* total) {
+    if (!is_global(c)) return BDF_OK;
+    std::vector<int64_t> all((size_t)comm_world(c->comm));
+    std::string err;
+    c->collectives++;
+    cudaError_t e = comm_host_allgather(c->comm, total, all.data(), sizeof(int64_t), c->s_compute, &err);
+    if (e != cudaSuccess) { g_nccl_err = err; return fail_cuda(e, "count"); }
+    *total = 0;
+    for (int64_t v : all) *total += v;
     return BDF_OK;
 }
 
@@ -995,6 +1117,7 @@ static int aggregate_dev(bdf_ctx* c, int op, bdf_col* col, void* out_scalar, int
         TRY(ensure_null_counts(c, col));
         int64_t total = 0;
         for (size_t i = 0; i < col->chunks.size(); i++) total += col->chunks[i].len - col->null_counts[i];
+        TRY(count_global(c, &total));
         *(int64_t*)out_scalar = total;
         *is_some = 1;
         return BDF_OK;
@@ -1009,7 +1132,7 @@ static int aggregate_dev(bdf_ctx* c, int op, bdf_col* col, void* out_scalar, int
         return BDF_OK;
     }
     if (a.would_panic) return fail(BDF_WOULD_PANIC, "max/min on an empty or all-null chunk: the reference unwraps None");
-    *is_some = col->chunks.empty() ? 0 : 1;
+    *is_some = a.n_chunks == 0 ? 0 : 1;   // Iterator::max of an empty Vec is None
     if (*is_some) memcpy(out_scalar, op == BDF_MIN ? &a.min : &a.max, (size_t)w);
     return BDF_OK;
 }
@@ -1025,7 +1148,7 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
     int64_t count = 0;
     for (int64_t k = 0; k < n; k += kAggSlots) {
         const int64_t m = std::min<int64_t>(kAggSlots, n - k);
-        for (int64_t j = 0; j < m; j++) TRY(reduce_range(c, col, k + j, k + j + 1, (int)j));
+        for (int64_t j = 0; j < m; j++) TRY(reduce_range(c, col, k + j, k + j + 1, c->h_agg_dev + j));
         CK(cudaStreamSynchronize(c->s_compute));
         for (int64_t j = 0; j < m; j++) {
             const AggDev& a = c->h_agg[j];
@@ -1037,6 +1160,22 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
             const double mch = len ? s / (double)len : 0.0;
             count += len;
             mean = mean + ((mch - mean) * (double)len) / (double)count;
+        }
+    }
+    if (is_global(c)) {
+        // The reference merges per-chunk means in chunk order (aggregate.rs:44-63); the chunks of the other ranks are
+        // merged as one (mean, count) pair per rank, in rank order, with the same formula.
+        struct Pair { double mean; int64_t count; } mine{mean, count};
+        std::vector<Pair> all((size_t)comm_world(c->comm));
+        std::string err;
+        c->collectives++;
+        cudaError_t e = comm_host_allgather(c->comm, &mine, all.data(), sizeof(Pair), c->s_compute, &err);
+        if (e != cudaSuccess) { g_nccl_err = err; return fail_cuda(e, "avg"); }
+        mean = 0.0; count = 0;
+        for (const Pair& p : all) {
+            if (!p.count) continue;
+            count += p.count;
+            mean = mean + ((p.mean - mean) * (double)p.count) / (double)count;
         }
     }
     *is_some = count != 0;
@@ -1359,14 +1498,17 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
             e = ev_get(c, &ev_done);
             if (e == cudaSuccess) e = cudaEventRecord(ev_done, c->s_compute);
             if (e == cudaSuccess) e = cudaStreamWaitEvent(c->s_fin, ev_done, 0);
-            if (e == cudaSuccess) e = launch_finish(true, pb->p, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, c->h_agg_dev + f->slot, c->s_fin);
-            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
+            if (e == cudaSuccess) e = launch_finish(true, pb->p, total_tiles, c->sm_count, c->d_stage, c->d_ticket + 1, future_target(c, f, 0), c->s_fin);
             if (e == cudaSuccess) e = cudaEventRecord(pb->done, c->s_fin);
             pb->used = true;
+            f->chunks[0] = (uint32_t)n;
+            if (e == cudaSuccess) e = future_combine(c, f, c->s_fin);
+            if (e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_fin);
             if (ev_done) ev_put(c, ev_done);
         }
         if (e == cudaSuccess && has_div) {
-            e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
+            if (is_global(c)) e = flag_allreduce(c);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(c->h_flag, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->s_compute);
             if (e == cudaSuccess) e = cudaStreamSynchronize(c->s_compute);
             if (e == cudaSuccess && *c->h_flag) {
                 if (o) col_release(c, o);
@@ -1379,7 +1521,7 @@ static int expr_dev(bdf_ctx* c, int n_inputs, const bdf_col* const* inputs, int 
         cudaGetLastError();
         if (o) col_release(c, o);
         if (f) { ev_put(c, f->ev); delete f; }
-        return st != BDF_OK ? st : fail(cuda_status(e), "fused expression failed: %s", cudaGetErrorString(e));
+        return st != BDF_OK ? st : fail_cuda(e, "fused expression");
     }
     if (out) *out = o;
     if (fut) *fut = f;
@@ -1567,6 +1709,8 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->flush_buf) cudaFree(c->flush_buf);
+    if (c->comm) { comm_destroy(c->comm); c->comm = nullptr; }
+    if (c->d_local) cudaFree(c->d_local);
     if (c->ev_tmp) cudaEventDestroy(c->ev_tmp);
     if (c->ev_t0) cudaEventDestroy(c->ev_t0);
     if (c->ev_t1) cudaEventDestroy(c->ev_t1);
@@ -1611,6 +1755,7 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaMalloc((void**)&c->d_stage, (size_t)c->sm_count * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
+    CK(cudaMalloc((void**)&c->d_local, (size_t)kAggSlots * sizeof(AggDev)));
     CK(cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned int)));
     CK(cudaMemset(c->d_flag, 0, sizeof(int)));
     CK(cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming));
@@ -1671,6 +1816,93 @@ int bdf_host_unregister(bdf_ctx* c, void* p) {
     CK(cudaHostUnregister(p));
     return BDF_OK;
 }
+
+// ---- multi-GPU: communicator -------------------------------------------------------------------------
+
+int bdf_comm_unique_id(uint8_t* id) {
+    if (!id) return fail(BDF_INVALID, "null id");
+    std::string err;
+    if (comm_unique_id(id, &err) != 0) return fail(BDF_NCCL, "%s", err.c_str());
+    return BDF_OK;
+}
+
+int bdf_comm_attach(bdf_ctx* c, const uint8_t* id, int rank, int world) {
+    ENTER(c);
+    if (!id || world < 1 || rank < 0 || rank >= world) return fail(BDF_INVALID, "bad communicator arguments (rank %d of %d)", rank, world);
+    if (c->comm) return fail(BDF_INVALID, "the context already belongs to a communicator");
+    CK(cudaStreamSynchronize(c->s_compute));
+    std::string err;
+    Comm* cm = comm_create(id, rank, world, &err);
+    if (!cm) return fail(BDF_NCCL, "%s", err.c_str());
+    c->comm = cm;
+    c->collective = true;
+    c->collectives = 0;
+    return BDF_OK;
+}
+
+int bdf_comm_detach(bdf_ctx* c) {
+    ENTER(c);
+    if (!c->comm) return BDF_OK;
+    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(c->s_fin));
+    comm_destroy(c->comm);
+    c->comm = nullptr;
+    return BDF_OK;
+}
+
+int bdf_comm_info(bdf_ctx* c, int32_t* rank, int32_t* world, int32_t* nccl_version, int64_t* collectives) {
+    if (!c) return fail(BDF_INVALID, "null context");
+    if (rank) *rank = c->comm ? comm_rank(c->comm) : 0;
+    if (world) *world = c->comm ? comm_world(c->comm) : 1;
+    if (nccl_version) *nccl_version = c->comm ? comm_version() : 0;
+    if (collectives) *collectives = c->collectives;
+    return BDF_OK;
+}
+
+int bdf_comm_collective(bdf_ctx* c, int on) {
+    ENTER(c);
+    c->collective = on != 0;
+    return BDF_OK;
+}
+
+int bdf_comm_all_reduce_f64(bdf_ctx* c, int op, int64_t n, double* inout) {
+    ENTER(c);
+    if (n < 0 || (n && !inout) || (op != BDF_SUM && op != BDF_MIN && op != BDF_MAX)) return fail(BDF_INVALID, "bad arguments");
+    if (!c->comm || n == 0) return BDF_OK;   // a lone GPU: the value is already the result
+    std::string err;
+    c->collectives++;
+    cudaError_t e = comm_host_allreduce_f64(c->comm, op == BDF_SUM ? 0 : op == BDF_MIN ? 1 : 2, inout, (int)n, c->s_compute, &err);
+    if (e != cudaSuccess) { g_nccl_err = err; return fail_cuda(e, "all-reduce"); }
+    return BDF_OK;
+}
+
+int bdf_comm_barrier(bdf_ctx* c) {
+    {
+        ENTER(c);
+        CK(cudaStreamSynchronize(c->s_h2d));
+        CK(cudaStreamSynchronize(c->s_compute));
+        CK(cudaStreamSynchronize(c->s_fin));
+        CK(cudaStreamSynchronize(c->s_d2h));
+    }
+    double one = 1.0;
+    return bdf_comm_all_reduce_f64(c, BDF_SUM, 1, &one);   // returns once every rank has arrived
+}
+
+int bdf_aggregate_all_many_dev_async(bdf_ctx* c, int32_t n_cols, const bdf_col* const* cols, bdf_future** fut) {
+    ENTER(c);
+    if (!cols || !fut) return fail(BDF_INVALID, "null argument");
+    return aggregate_many_dev_async(c, n_cols, const_cast<bdf_col* const*>(cols), false, fut);
+}
+
+int bdf_aggregate_all_many_dev(bdf_ctx* c, int32_t n_cols, const bdf_col* const* cols, bdf_agg4* out) {
+    ENTER(c);
+    if (!cols || !out) return fail(BDF_INVALID, "null argument");
+    bdf_future* f = nullptr;
+    TRY(aggregate_many_dev_async(c, n_cols, const_cast<bdf_col* const*>(cols), true, &f));
+    return future_wait(c, f, out);
+}
+
+int bdf_future_count(const bdf_future* fut) { return fut ? fut->n : 0; }
 
 // ---- device-resident API -----------------------------------------------------------------------
 
@@ -1938,7 +2170,7 @@ int bdf_aggregate(bdf_ctx* c, int op, int dtype, int64_t n, const bdf_view* in, 
             if (in[i].validity && in[i].null_count < 0) known = false;
             total += in[i].len - (in[i].validity ? in[i].null_count : 0);
         }
-        if (known) { *(int64_t*)out_scalar = total; *is_some = 1; return BDF_OK; }
+        if (known) { TRY(count_global(c, &total)); *(int64_t*)out_scalar = total; *is_some = 1; return BDF_OK; }
     }
     std::vector<bdf_col*> cols;
     TRY(upload_many(c, {UploadSpec{dtype, n, in}}, true, cols));

@@ -197,7 +197,7 @@ N_I64_FALLBACK = 3  # Int64: only used to type an empty Vec (results do not depe
 
 def _agg4_to_dict(dtype: int, a: "N.Agg4") -> dict:
     res = {"sum": _scalar_from_bits(dtype, a.sum), "count": int(a.count), "rows": int(a.rows),
-           "would_panic": bool(a.would_panic), "min": None, "max": None}
+           "would_panic": bool(a.would_panic), "n_chunks": int(a.n_chunks), "min": None, "max": None}
     if not is_float(dtype) and a.any_valid:
         res["min"] = _scalar_from_bits(dtype, a.min)
         res["max"] = _scalar_from_bits(dtype, a.max)
@@ -398,6 +398,22 @@ class Column:
         N.raise_for_status(N.lib().bdf_avg_dev(self.ctx.handle, self.handle, C.byref(out), C.byref(some)))
         return out.value if some.value else None
 
+    @staticmethod
+    def aggregate_all_many(columns: Sequence["Column"], asynchronous: bool = False):
+        """sum/min/max/count of several columns in ONE call: one reduction per column, one host wait and (on a rank of
+        a communicator) one grouped collective for all of them.  Returns a list of dicts (or an AggFuture of one)."""
+        ctx = columns[0].ctx
+        k = len(columns)
+        cols = (C.c_void_p * k)(*[c.handle for c in columns])
+        dtypes = [c.dtype for c in columns]
+        if asynchronous:
+            f = C.c_void_p()
+            N.raise_for_status(N.lib().bdf_aggregate_all_many_dev_async(ctx.handle, k, cols, C.byref(f)))
+            return AggFuture(ctx, f, dtypes)
+        out = (N.Agg4 * k)()
+        N.raise_for_status(N.lib().bdf_aggregate_all_many_dev(ctx.handle, k, cols, out))
+        return [_agg4_to_dict(dtypes[i], out[i]) for i in range(k)]
+
     # -- back to the host --
     def download(self, pinned: bool = False, into=None) -> List[PrimitiveArray]:
         dtype, n, _ = self.describe()
@@ -508,16 +524,19 @@ def eval_expr_agg(inputs: Sequence["Column"], nodes: Sequence[tuple], materialis
 class AggFuture:
     """An aggregate whose kernels are enqueued; result() blocks until the value is on the host."""
 
-    def __init__(self, ctx: N.Context, handle: C.c_void_p, dtype: int):
+    def __init__(self, ctx: N.Context, handle: C.c_void_p, dtype):
+        """dtype: an int (one aggregate -> result() is a dict) or a list (multi-column call -> a list of dicts)."""
         self.ctx, self.handle, self.dtype = ctx, handle, dtype
         self._value = None
 
-    def result(self) -> dict:
+    def result(self):
         if self.handle is not None:
-            a = N.Agg4()
-            N.raise_for_status(N.lib().bdf_future_wait(self.ctx.handle, self.handle, C.byref(a)))
+            many = isinstance(self.dtype, (list, tuple))
+            k = len(self.dtype) if many else 1
+            a = (N.Agg4 * k)()
+            N.raise_for_status(N.lib().bdf_future_wait(self.ctx.handle, self.handle, a))
             self.handle = None
-            self._value = _agg4_to_dict(self.dtype, a)
+            self._value = [_agg4_to_dict(self.dtype[i], a[i]) for i in range(k)] if many else _agg4_to_dict(self.dtype, a[0])
         return self._value
 
     def __del__(self):

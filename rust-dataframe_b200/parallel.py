@@ -3,26 +3,33 @@ the all-reduce of the per-GPU partial aggregates -- where the path has a real ex
 
 The reference parallelises over the same axis with rayon (``par_iter`` over chunks in
 ``ScalarFunctions::add`` / ``par_multiply``, src/functions/scalar.rs:28-31, 99-102): chunks are independent,
-so elementwise operators and casts need no communication at all; an aggregate is an associative fold, so
-each rank reduces its own chunks on its GPU and the partials (a few 8-byte scalars per column) are combined
-with ``torch.distributed`` (NCCL over NVLink on GPUs, gloo in the CPU tests).
+so elementwise operators and casts need no communication at all; an aggregate is an associative fold
+(src/functions/aggregate.rs:12-31,70-93), so each rank reduces its own chunks on its GPU and the partials (a few
+8-byte scalars per column) are combined.
 
-Combine rules:
-  sum    integers: wrapping 64-bit add (all_reduce SUM on the two's-complement bit pattern) -> bit-identical to
-         the single-GPU result for every world size; floats: partial sums are all-gathered and folded in rank
-         order (deterministic for a given world size; covered by the float-sum tolerance);
-  min/max all_reduce MIN / MAX on an order-preserving int64 key (unsigned values get their top bit flipped);
-  count  all_reduce SUM;  any_valid (min/max is None iff no rank saw a valid slot) all_reduce MAX.
+On GPUs the combine lives INSIDE libb200df.so (csrc/comm.cu): ``attach_communicator`` makes the context a rank of
+an NCCL communicator and from then on every aggregate entry enqueues one grouped ``ncclAllReduce`` on the stream
+that produced the partials and returns the aggregate of the whole column -- this module only ships the 128-byte
+NCCL id between the ranks (through torch.distributed's rendezvous store: plumbing, no process group needed).
+
+``combine_aggregates`` is the host-side statement of the same combine rules over ``torch.distributed`` (gloo in
+the CPU tests), used where no GPU exists:
+  sum    integers: wrapping 64-bit add of the two's-complement bit patterns -> bit-identical to the single-GPU result
+         for every world size; floats: partial sums folded in rank order (deterministic for a given world size;
+         covered by the float-sum tolerance);
+  min/max on order-preserving keys;  count/rows added;  would_panic / "has chunks" OR-ed.
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence
+import os
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
 
 from .arrays import NP_DTYPES, is_float
 
 _SIGN = np.uint64(1 << 63)
+_MASK64 = (1 << 64) - 1
 
 
 def shard_indices(n_chunks: int, rank: int, world: int, lens: Optional[Sequence[int]] = None) -> List[int]:
@@ -47,6 +54,81 @@ def shard(chunks: Sequence, rank: int, world: int, balanced: bool = False) -> Li
     return [chunks[i] for i in shard_indices(len(chunks), rank, world, lens)]
 
 
+def shard_row_ranges(lens: Sequence[int], rank: int, world: int, align: int = 64) -> List[Tuple[int, int, int]]:
+    """Contiguous, row-balanced split of a chunked column ("contiguous blocks of chunks balanced by row
+    count; a single huge chunk is split by row range on 64-row boundaries so bitmap words do not straddle GPUs").
+    Returns this rank's pieces as (chunk index, first row in the chunk, rows); cuts are multiples of ``align``
+    rows inside a chunk, so a piece is a zero-copy Arrow slice whose validity starts on a byte boundary."""
+    total = int(sum(int(n) for n in lens))
+    if world <= 1:
+        return [(i, 0, int(n)) for i, n in enumerate(lens)]
+
+    def cut(r: int) -> int:  # global row where rank r starts
+        if r >= world:
+            return total
+        return total * r // world
+
+    starts = []
+    acc = 0
+    for n in lens:
+        starts.append(acc)
+        acc += int(n)
+    lo, hi = cut(rank), cut(rank + 1)
+
+    def snap(g: int) -> int:  # move a global cut to an aligned row of the chunk it falls into (never past the chunk)
+        if g <= 0 or g >= total:
+            return max(0, min(g, total))
+        for i, n in enumerate(lens):
+            if starts[i] <= g < starts[i] + int(n):
+                off = (g - starts[i]) // align * align
+                return starts[i] + off
+        return total
+
+    lo, hi = snap(lo), snap(hi)
+    out = []
+    for i, n in enumerate(lens):
+        b, e = max(lo, starts[i]), min(hi, starts[i] + int(n))
+        if e > b:
+            out.append((i, b - starts[i], e - b))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
+# GPUs: the library owns the collective; only the NCCL id travels through here
+
+
+def rendezvous_store():
+    """The key-value store of the job's rendezvous (torchrun's agent store, or a TCPStore rank 0 hosts at
+    MASTER_ADDR:MASTER_PORT).  Returns (store, rank, world)."""
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    store, rank, world = next(iter(dist.rendezvous("env://", rank=rank, world_size=world)))
+    return store, rank, world
+
+
+def attach_communicator(ctx, store=None, rank: Optional[int] = None, world: Optional[int] = None, key: str = "bdf/nccl_id") -> Tuple[int, int]:
+    """Make ``ctx`` a rank of the job's NCCL communicator (bdf_comm_attach).  Rank 0 creates the id and publishes it
+    in the store; every rank attaches.  Returns (rank, world).  With world == 1 nothing is attached."""
+    if store is None:
+        store, r, w = rendezvous_store()
+        rank = r if rank is None else rank
+        world = w if world is None else world
+    if world <= 1:
+        return 0, 1
+    if rank == 0:
+        store.set(key, type(ctx).comm_unique_id())
+    uid = bytes(store.get(key))
+    ctx.comm_attach(uid, rank, world)
+    ctx._rendezvous_store = store   # the agent connection stays open for the life of the context
+    return rank, world
+
+
+# ---------------------------------------------------------------------------------------------------------
+# host-side statement of the combine (CPU tests over gloo)
+
+
 def _to_key(dtype: int, value) -> int:
     """Order-preserving map of a T::Native integer onto int64."""
     npdt = NP_DTYPES[dtype]
@@ -62,10 +144,56 @@ def _from_key(dtype: int, key: int):
     return npdt.type(key)
 
 
+def _i64(x: int) -> int:
+    x &= _MASK64
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def pack_partial(local: Dict, dtype: int) -> np.ndarray:
+    """One rank's record, as 8 int64 words: [sum bits, count, rows, would_panic, has_chunks, min key, max key, any_valid]."""
+    i64 = np.iinfo(np.int64)
+    any_valid = 1 if (local.get("count", 0) > 0) else 0
+    if is_float(dtype):
+        sum_bits = int(np.array([float(local["sum"])], dtype=np.float64).view(np.int64)[0])
+        kmin, kmax = i64.max, i64.min
+    else:
+        sum_bits = _i64(int(local["sum"]))
+        kmin = _to_key(dtype, local["min"]) if any_valid and local.get("min") is not None else i64.max
+        kmax = _to_key(dtype, local["max"]) if any_valid and local.get("max") is not None else i64.min
+    has_chunks = int(local.get("n_chunks", 1 if local.get("rows", 0) or any_valid else 0) > 0)
+    return np.array([sum_bits, int(local["count"]), int(local.get("rows", 0)), 1 if local.get("would_panic") else 0, has_chunks,
+                     kmin, kmax, any_valid], dtype=np.int64)
+
+
+def fold_partials(records: np.ndarray, dtype: int) -> Dict:
+    """Fold the ranks' records (world x 8 int64, rank order) into the aggregates of the whole column."""
+    npdt = NP_DTYPES[dtype]
+    out: Dict = {"count": int(records[:, 1].sum()), "rows": int(records[:, 2].sum()), "would_panic": bool(records[:, 3].any()),
+                 "n_chunks": int(records[:, 4].sum()), "min": None, "max": None}
+    if is_float(dtype):
+        total = 0.0
+        for bits in records[:, 0]:  # fixed rank order -> deterministic
+            total = total + float(np.array([bits], dtype=np.int64).view(np.float64)[0])
+        out["sum"] = npdt.type(total)
+        return out
+    bits = 8 * npdt.itemsize
+    s = 0
+    for v in records[:, 0]:
+        s = (s + int(v)) & _MASK64  # wrapping 64-bit add: associative, so any order gives the same bits
+    s &= (1 << bits) - 1
+    if npdt.kind == "i" and s >= 1 << (bits - 1):
+        s -= 1 << bits
+    out["sum"] = npdt.type(s)
+    if records[:, 7].any():
+        out["min"] = _from_key(dtype, int(records[:, 5].min()))
+        out["max"] = _from_key(dtype, int(records[:, 6].max()))
+    return out
+
+
 def combine_aggregates(local: Dict, dtype: int, group=None, device: Optional[str] = None) -> Dict:
-    """All-reduce the partial aggregates of this rank's shard (the dict returned by
-    ``AggregateFunctions.all`` / ``Column.aggregate_all``) into the aggregates of the whole column.
-    Every rank gets the same result."""
+    """Combine the partial aggregates of this rank's shard (the dict returned by ``AggregateFunctions.all`` /
+    ``Column.aggregate_all``) into the aggregates of the whole column with ONE collective (an all-gather of the
+    8-word records, folded in rank order on every rank).  Every rank gets the same result."""
     import torch
     import torch.distributed as dist
 
@@ -74,53 +202,24 @@ def combine_aggregates(local: Dict, dtype: int, group=None, device: Optional[str
     if device is None:
         device = "cuda" if dist.get_backend(group) == "nccl" else "cpu"
     world = dist.get_world_size(group)
+    mine = torch.from_numpy(pack_partial(local, dtype)).to(device)
+    parts = [torch.zeros_like(mine) for _ in range(world)]
+    dist.all_gather(parts, mine, group=group)
+    records = np.stack([p.cpu().numpy() for p in parts])
     out = dict(local)
-    any_valid = 1 if (local.get("count", 0) > 0) else 0
-    counts = torch.tensor([int(local["count"]), int(local.get("rows", 0))], dtype=torch.int64, device=device)
-    dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
-    out["count"], out["rows"] = int(counts[0]), int(counts[1])
-    flags = torch.tensor([any_valid, 1 if local.get("would_panic") else 0], dtype=torch.int64, device=device)
-    dist.all_reduce(flags, op=dist.ReduceOp.MAX, group=group)
-    out["would_panic"] = bool(flags[1])
-    if is_float(dtype):
-        mine = torch.tensor([float(local["sum"])], dtype=torch.float64, device=device)
-        parts = [torch.zeros_like(mine) for _ in range(world)]
-        dist.all_gather(parts, mine, group=group)
-        total = 0.0
-        for p in parts:  # fixed rank order -> deterministic
-            total = total + float(p[0])
-        out["sum"] = NP_DTYPES[dtype].type(total)
-        out["min"] = out["max"] = None
-        return out
-    npdt = NP_DTYPES[dtype]
-    bits = 8 * npdt.itemsize
-    s = int(local["sum"]) & ((1 << 64) - 1)
-    s = s - (1 << 64) if s >= (1 << 63) else s  # two's-complement bit pattern as int64
-    t = torch.tensor([s], dtype=torch.int64, device=device)
-    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)  # int64 add wraps: same bits as a 64-bit wrapping add
-    total = int(t[0]) & ((1 << bits) - 1)
-    if npdt.kind == "i" and total >= 1 << (bits - 1):
-        total -= 1 << bits
-    out["sum"] = npdt.type(total)
-    i64 = np.iinfo(np.int64)
-    kmin = _to_key(dtype, local["min"]) if any_valid and local.get("min") is not None else i64.max
-    kmax = _to_key(dtype, local["max"]) if any_valid and local.get("max") is not None else i64.min
-    tmin = torch.tensor([kmin], dtype=torch.int64, device=device)
-    tmax = torch.tensor([kmax], dtype=torch.int64, device=device)
-    dist.all_reduce(tmin, op=dist.ReduceOp.MIN, group=group)
-    dist.all_reduce(tmax, op=dist.ReduceOp.MAX, group=group)
-    if int(flags[0]):
-        out["min"], out["max"] = _from_key(dtype, int(tmin[0])), _from_key(dtype, int(tmax[0]))
-    else:
-        out["min"] = out["max"] = None
+    out.update(fold_partials(records, dtype))
     return out
 
 
 def sharded_aggregate_all(chunks_of_this_rank: Sequence, dtype: int, ctx=None, group=None) -> Dict:
-    """sum/min/max/count of a column whose chunks are spread over the ranks: one fused reduction kernel on
-    this rank's GPU, then the partial-aggregate all-reduce."""
+    """sum/min/max/count of a column whose chunks are spread over the ranks.  On a context that is attached to a
+    communicator the library call already returns the global aggregates; otherwise (CPU tests) the per-rank
+    result goes through ``combine_aggregates``."""
     from .functions import AggregateFunctions
 
-    local = AggregateFunctions.all(chunks_of_this_rank, dtype=dtype, ctx=ctx) if len(chunks_of_this_rank) else \
-        {"sum": NP_DTYPES[dtype].type(0), "min": None, "max": None, "count": 0, "rows": 0, "would_panic": False}
-    return combine_aggregates(local, dtype, group=group)
+    attached = ctx is not None and ctx.comm_info()["world"] > 1
+    if len(chunks_of_this_rank) or attached:
+        local = AggregateFunctions.all(chunks_of_this_rank, dtype=dtype, ctx=ctx)
+    else:
+        local = {"sum": NP_DTYPES[dtype].type(0), "min": None, "max": None, "count": 0, "rows": 0, "would_panic": False, "n_chunks": 0}
+    return local if attached else combine_aggregates(local, dtype, group=group)

@@ -1,0 +1,59 @@
+"""Multi-GPU parity: the grouped ncclAllReduce that libb200df enqueues behind the per-GPU reductions.
+Needs >= 2 GPUs on the box (skipped otherwise; the host-side shard/fold logic is covered on CPU by tests/test_parallel.py).
+One process per GPU, launched exactly like the driver launches bench.py."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _gpu_count() -> int:
+    try:
+        import torch
+
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+def _free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _launch(world: int, script: str, *extra: str, timeout: int = 900) -> str:
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, script), *extra]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    assert r.returncode == 0, f"rc={r.returncode}\n{r.stdout[-4000:]}\n{r.stderr[-6000:]}"
+    return r.stdout
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_aggregates_match_the_oracle(world):
+    if _gpu_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    out = _launch(world, "tests/comm_worker.py")
+    assert "COMM-OK" in out, out[-2000:]
+
+
+@pytest.mark.gpu
+def test_bench_line_with_the_driver_command_line():
+    """The exact launch the driver uses for the scaling run (--steps 20 --warmup 5), at the largest N the box has."""
+    n = _gpu_count()
+    world = 8 if n >= 8 else 4 if n >= 4 else 2 if n >= 2 else 0
+    if not world:
+        pytest.skip("needs >= 2 GPUs")
+    import json
+
+    out = _launch(world, "bench.py", "--gpus", str(world), "--steps", "20", "--warmup", "5", "--skip-cpu", timeout=1500)
+    line = json.loads([l for l in out.splitlines() if l.startswith("{")][-1])
+    assert line["n_gpus"] == world and line["value"] > 0 and line["detail"]["collectives_in_timed_region"] >= 20
+    assert line["check"]["rows"] == 100_000_000 * world and line["check"]["count"] == 100_000_000 * world
+    assert line["other_series"]["scaling"] == "strong" and line["other_series"]["check"]["count"] == 100_000_000
