@@ -106,12 +106,15 @@ struct IpcField {
     std::string name;
     int dtype = -1;       // bdf_dtype, BDF_BOOL, or -1: a type outside the path
     bool nullable = false;
-    int n_nodes = 0, n_buffers = 0;   // what the field (with its children) occupies in every RecordBatch
+    int64_t n_nodes = 0, n_buffers = 0;   // what the field (with its children) occupies in every RecordBatch
 };
 
 // Field table -> IpcField; recursion only to count the nodes/buffers of nested children.
-bool parse_field(const FbTable& f, IpcField* out, int depth, std::string* why) {
+// `budget` bounds the TOTAL number of field tables visited while decoding a schema: child offsets of a crafted file may
+// all point at the same table, so depth alone does not bound the work (k children per level -> k^depth visits).
+bool parse_field(const FbTable& f, IpcField* out, int depth, int64_t* budget, std::string* why) {
     if (depth > 32) { *why = "schema nested too deeply"; return false; }
+    if (--*budget < 0) { *why = "schema describes more fields than the footer can hold"; return false; }
     if (!f.str(0, &out->name)) { *why = "bad field name"; return false; }
     out->nullable = f.scalar<uint8_t>(1, 0) != 0;
     const int tt = f.scalar<uint8_t>(2, 0);
@@ -158,7 +161,7 @@ bool parse_field(const FbTable& f, IpcField* out, int depth, std::string* why) {
             FbTable ch;
             if (!f.b->rd(first + 4 * i, &o) || !ch.init(f.b, first + 4 * i + o)) { *why = "bad child field"; return false; }
             IpcField c;
-            if (!parse_field(ch, &c, depth + 1, why)) return false;
+            if (!parse_field(ch, &c, depth + 1, budget, why)) return false;
             out->n_nodes += c.n_nodes;
             out->n_buffers += c.n_buffers;
         }
@@ -233,14 +236,15 @@ int bdf_ipc_open(const char* path, bdf_ipc** out) {
     if (schema.scalar<int16_t>(0, 0) != 0) return ipc_fail(BDF_UNSUPPORTED, "big-endian IPC file");
     size_t first; uint32_t cnt;
     if (!schema.vec(1, &first, &cnt, 4)) return ipc_fail(BDF_INVALID, "malformed schema");
-    int nodes_per_batch = 0, buffers_per_batch = 0;
+    int64_t nodes_per_batch = 0, buffers_per_batch = 0;
+    int64_t field_budget = (int64_t)flen / 8 + 16;   // a Field table cannot be smaller than its vtable + offset
     for (uint32_t i = 0; i < cnt; i++) {
         uint32_t o;
         FbTable ft;
         if (!fb.rd(first + 4 * i, &o) || !ft.init(&fb, first + 4 * i + o)) return ipc_fail(BDF_INVALID, "malformed field %u", i);
         IpcField fld;
         std::string why;
-        if (!parse_field(ft, &fld, 0, &why)) return ipc_fail(BDF_UNSUPPORTED, "%s", why.c_str());
+        if (!parse_field(ft, &fld, 0, &field_budget, &why)) return ipc_fail(BDF_UNSUPPORTED, "%s", why.c_str());
         nodes_per_batch += fld.n_nodes;
         buffers_per_batch += fld.n_buffers;
         f->fields.push_back(std::move(fld));
@@ -251,7 +255,9 @@ int bdf_ipc_open(const char* path, bdf_ipc** out) {
     for (uint32_t k = 0; k < bcnt; k++) {
         int64_t off, body_len; int32_t meta_len;
         fb.rd(bfirst + 24 * (size_t)k, &off); fb.rd(bfirst + 24 * (size_t)k + 8, &meta_len); fb.rd(bfirst + 24 * (size_t)k + 16, &body_len);
-        if (off < 8 || meta_len < 8 || body_len < 0 || (uint64_t)off + (uint64_t)meta_len + (uint64_t)body_len > f->size)
+        // overflow-free: every term is compared with what is left of the file, nothing is added up first
+        if (off < 8 || meta_len < 8 || body_len < 0 || (uint64_t)off > f->size || (uint64_t)meta_len > f->size - (uint64_t)off ||
+            (uint64_t)body_len > f->size - (uint64_t)off - (uint64_t)meta_len)
             return ipc_fail(BDF_INVALID, "record batch %u lies outside the file", k);
         // encapsulated message: [0xFFFFFFFF] <int32 metadata size> <flatbuffer> <padding> <body>
         size_t p = (size_t)off;
@@ -272,8 +278,8 @@ int bdf_ipc_open(const char* path, bdf_ipc** out) {
         b.body_len = body_len;
         size_t nfirst, bufirst; uint32_t ncnt, bucnt;
         if (!rb.vec(1, &nfirst, &ncnt, 16) || !rb.vec(2, &bufirst, &bucnt, 16)) return ipc_fail(BDF_INVALID, "record batch %u: malformed nodes/buffers", k);
-        if ((int)ncnt != nodes_per_batch || (int)bucnt != buffers_per_batch)
-            return ipc_fail(BDF_INVALID, "record batch %u: %u nodes / %u buffers, the schema needs %d / %d", k, ncnt, bucnt, nodes_per_batch, buffers_per_batch);
+        if ((int64_t)ncnt != nodes_per_batch || (int64_t)bucnt != buffers_per_batch)
+            return ipc_fail(BDF_INVALID, "record batch %u: %u nodes / %u buffers, the schema needs %lld / %lld", k, ncnt, bucnt, (long long)nodes_per_batch, (long long)buffers_per_batch);
         b.cols.resize(f->fields.size());
         size_t ni = 0, bi = 0;
         for (size_t c = 0; c < f->fields.size(); c++) {
@@ -286,9 +292,12 @@ int bdf_ipc_open(const char* path, bdf_ipc** out) {
                 int64_t need = 0;
                 dtype_bytes(fld.dtype, cc.len, &need);
                 const bool has_v = cc.null_count > 0;
-                if (cc.len != b.rows || cc.null_count < 0 || cc.null_count > cc.len || cc.values.off < 0 || cc.values.len < need ||
-                    cc.values.off + cc.values.len > body_len || (has_v && (cc.validity.off < 0 || cc.validity.len < (cc.len + 7) / 8 ||
-                    cc.validity.off + cc.validity.len > body_len)))
+                // offsets and lengths come from the file: compare each with what is left of the body (off + len may wrap)
+                auto fits = [body_len](const IpcBuf& bf, int64_t min_len) {
+                    return bf.off >= 0 && bf.len >= min_len && bf.off <= body_len && bf.len <= body_len - bf.off;
+                };
+                if (cc.len != b.rows || cc.null_count < 0 || cc.null_count > cc.len || !fits(cc.values, need) ||
+                    (has_v && !fits(cc.validity, (cc.len + 7) / 8)))
                     return ipc_fail(BDF_INVALID, "record batch %u, column '%s': buffers do not fit the batch", k, fld.name.c_str());
             }
             ni += fld.n_nodes;
@@ -587,31 +596,45 @@ void plan_file(int n_cols, const char* const* names, const int32_t* dtypes, int6
     plan->meta.push_back(std::move(tail));
 }
 
-// A new file of the planned size, mapped read/write, metadata already in place.
+// A new file of the planned size, mapped read/write, metadata already in place.  The data goes to `<path>.tmp.<pid>`
+// whose blocks are RESERVED up front (posix_fallocate: a full disk is an error return here, not a SIGBUS on the first
+// store through the mapping); commit() renames it over `path`, any failure before that unlinks it, so `path` either
+// keeps its old contents or holds a complete file.
 struct OutFile {
     int fd = -1;
     uint8_t* map = nullptr;
     size_t size = 0;
+    std::string tmp;
     int open_planned(const char* path, const FilePlan& plan) {
-        fd = open(path, O_RDWR | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
-        if (fd < 0) return ipc_fail(BDF_INVALID, "cannot create %s: %s", path, strerror(errno));
+        tmp = std::string(path) + ".tmp." + std::to_string((long long)getpid());
+        fd = open(tmp.c_str(), O_RDWR | O_CREAT | O_TRUNC | O_CLOEXEC, 0644);
+        if (fd < 0) { const int e = errno; tmp.clear(); return ipc_fail(BDF_INVALID, "cannot create %s: %s", path, strerror(e)); }
         size = (size_t)plan.size;
-        if (ftruncate(fd, (off_t)size) != 0) return ipc_fail(BDF_INVALID, "cannot size %s to %zu bytes: %s", path, size, strerror(errno));
+        const int fe = posix_fallocate(fd, 0, (off_t)size);
+        if (fe != 0) return ipc_fail(fe == ENOSPC || fe == EDQUOT ? BDF_OOM : BDF_INVALID, "cannot reserve %zu bytes for %s: %s", size, path, strerror(fe));
         void* m = mmap(nullptr, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
         if (m == MAP_FAILED) return ipc_fail(BDF_INVALID, "cannot map %s: %s", path, strerror(errno));
         map = (uint8_t*)m;
         for (const FilePlan::Piece& pc : plan.meta) memcpy(map + pc.pos, pc.bytes.data(), pc.bytes.size());
         return BDF_OK;
     }
-    int finish(const char* path) {
-        int st = BDF_OK;
-        if (map && munmap(map, size) != 0) st = ipc_fail(BDF_INVALID, "unmapping %s failed: %s", path, strerror(errno));
+    // status: what the caller has seen so far; the file is published only when everything succeeded
+    int commit(const char* path, int status) {
+        int st = status;
+        if (map && munmap(map, size) != 0 && st == BDF_OK) st = ipc_fail(BDF_INVALID, "unmapping %s failed: %s", path, strerror(errno));
         map = nullptr;
         if (fd >= 0 && close(fd) != 0 && st == BDF_OK) st = ipc_fail(BDF_INVALID, "closing %s failed: %s", path, strerror(errno));
         fd = -1;
+        if (st == BDF_OK && rename(tmp.c_str(), path) != 0) st = ipc_fail(BDF_INVALID, "cannot move the finished file to %s: %s", path, strerror(errno));
+        if (st != BDF_OK && !tmp.empty()) unlink(tmp.c_str());
+        tmp.clear();
         return st;
     }
-    ~OutFile() { if (map) munmap(map, size); if (fd >= 0) close(fd); }
+    ~OutFile() {
+        if (map) munmap(map, size);
+        if (fd >= 0) close(fd);
+        if (!tmp.empty()) unlink(tmp.c_str());   // abandoned before commit
+    }
 };
 
 }  // namespace
@@ -653,7 +676,7 @@ int bdf_ipc_write_host(const char* path, int32_t n_cols, const char* const* name
             if (dtypes[c] == BDF_BOOL) copy_bits((const uint8_t*)v.values, v.offset, cs.rows, of.map + cs.values_pos);
             else memcpy(of.map + cs.values_pos, (const uint8_t*)v.values + v.offset * w[dtypes[c]], (size_t)cs.values_len);
         }
-    return of.finish(path);
+    return of.commit(path, BDF_OK);
 }
 
 int bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* const* names, const bdf_col* const* cols) {
@@ -700,8 +723,7 @@ int bdf_ipc_write(bdf_ctx* ctx, const char* path, int32_t n_cols, const char* co
         const int s2 = bdf_download_end(ctx, cols[c], outs[c].data());
         if (st == BDF_OK) st = s2;
     }
-    const int s3 = of.finish(path);
-    return st != BDF_OK ? st : s3;
+    return of.commit(path, st);
 }
 
 }  // extern "C"

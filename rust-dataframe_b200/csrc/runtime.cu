@@ -516,15 +516,26 @@ static bool is_pageable(const void* p) {
 
 static int ensure_stage(bdf_ctx* c) {
     if (!c->stage.empty()) return BDF_OK;
-    c->stage.resize(kStageSlots);
-    for (auto& sl : c->stage) {
-        CK(cudaHostAlloc((void**)&sl.p, kStageBytes, cudaHostAllocDefault));
-        CK(cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming));
+    // built in locals and committed to the context only when complete: a failure part-way leaves the context unstaged
+    std::vector<bdf_ctx::StageSlot> slots(kStageSlots);
+    cudaError_t e = cudaSuccess;
+    for (auto& sl : slots) {
+        if (e == cudaSuccess) e = cudaHostAlloc((void**)&sl.p, kStageBytes, cudaHostAllocDefault);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.ev, cudaEventDisableTiming);
     }
     const char* t = getenv("BDF_COPY_THREADS");
     const int hw = (int)std::thread::hardware_concurrency();
-    c->copy_threads = t && atoi(t) > 0 ? atoi(t) : std::max(1, std::min(8, hw > 0 ? hw : 8));
-    c->pool.reset(new CopyPool(c->copy_threads - 1));   // the calling thread is the last worker
+    const int threads = t && atoi(t) > 0 ? atoi(t) : std::max(1, std::min(8, hw > 0 ? hw : 8));
+    std::unique_ptr<CopyPool> pool;
+    if (e == cudaSuccess) pool.reset(new (std::nothrow) CopyPool(threads - 1));   // the calling thread is the last worker
+    if (e != cudaSuccess || !pool) {
+        cudaGetLastError();
+        for (auto& sl : slots) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
+        return e != cudaSuccess ? fail(cuda_status(e), "pinned staging allocation failed: %s", cudaGetErrorString(e)) : fail(BDF_OOM, "host allocation failed");
+    }
+    c->copy_threads = threads;
+    c->pool = std::move(pool);
+    c->stage = std::move(slots);
     return BDF_OK;
 }
 
@@ -1323,10 +1334,21 @@ static int filter_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* mask, bd
     void *hp = nullptr, *dp = nullptr;
     TRY(ring_alloc(c, (size_t)n * filter_desc_size(), &hp, &dp));
     unsigned int* d_counts = nullptr; long long *d_offsets = nullptr, *d_totals = nullptr;
-    CK(cudaMallocAsync((void**)&d_counts, std::max<size_t>(1, (size_t)tiles) * sizeof(unsigned int), c->s_compute));
-    CK(cudaMallocAsync((void**)&d_offsets, std::max<size_t>(1, (size_t)tiles) * sizeof(long long), c->s_compute));
-    CK(cudaMallocAsync((void**)&d_totals, std::max<size_t>(1, (size_t)n) * sizeof(long long), c->s_compute));
-    auto free_scratch = [&]() { cudaFreeAsync(d_counts, c->s_compute); cudaFreeAsync(d_offsets, c->s_compute); cudaFreeAsync(d_totals, c->s_compute); };
+    auto free_scratch = [&]() {
+        if (d_counts) cudaFreeAsync(d_counts, c->s_compute);
+        if (d_offsets) cudaFreeAsync(d_offsets, c->s_compute);
+        if (d_totals) cudaFreeAsync(d_totals, c->s_compute);
+    };
+    {   // three scratch arrays; a failure part-way frees what was already obtained
+        cudaError_t ea = cudaMallocAsync((void**)&d_counts, std::max<size_t>(1, (size_t)tiles) * sizeof(unsigned int), c->s_compute);
+        if (ea == cudaSuccess) ea = cudaMallocAsync((void**)&d_offsets, std::max<size_t>(1, (size_t)tiles) * sizeof(long long), c->s_compute);
+        if (ea == cudaSuccess) ea = cudaMallocAsync((void**)&d_totals, std::max<size_t>(1, (size_t)n) * sizeof(long long), c->s_compute);
+        if (ea != cudaSuccess) {
+            cudaGetLastError();
+            free_scratch();
+            return fail(cuda_status(ea), "filter scratch allocation failed: %s", cudaGetErrorString(ea));
+        }
+    }
     // pass 1: counts + scan (output pointers are not needed yet)
     for (int64_t i = 0; i < n; i++) {
         const DevChunk &v = values->chunks[i], &m = mask->chunks[i];

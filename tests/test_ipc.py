@@ -354,3 +354,100 @@ def test_reader_survives_corrupted_files(rdf, tmp_path):
         except rdf.ArrowError:
             failed += 1
     assert opened + failed == 400 and failed > 50
+
+
+def _patch_i64(raw: np.ndarray, pos: int, value: int) -> np.ndarray:
+    out = raw.copy()
+    out[pos:pos + 8] = np.frombuffer(np.array([value], dtype=np.int64).tobytes(), dtype=np.uint8)
+    return out
+
+
+def test_reader_rejects_offsets_that_wrap_int64(rdf, tmp_path):
+    """Buffer and block offsets/lengths near INT64_MAX: `off + len` would wrap negative and pass a naive bound check
+    (the advisor's reproduction: values-buffer offset 2^63-101 was accepted and the first read of the view segfaulted).
+    Every such file must be refused at open."""
+    n = 12345
+    batch = pa.record_batch([pa.array(np.arange(n, dtype=np.int64)), pa.array(np.arange(n, dtype=np.float64), mask=np.arange(n) % 5 == 0)], names=["k", "x"])
+    good = str(tmp_path / "good.arrow")
+    write_file(good, batch.schema, [batch])
+    with rdf.IpcFile(good) as f:
+        assert f.num_batches == 1 and f.view(0, "k").value_slice()[-1] == n - 1
+    raw = np.frombuffer(open(good, "rb").read(), dtype=np.uint8)
+    data = raw.tobytes()
+    vlen = np.array([n * 8], dtype=np.int64).tobytes()
+    # Buffer structs {offset:int64, length:int64} of the two values buffers: find the length words in the message metadata
+    hits = []
+    pos = data.find(vlen)
+    while pos >= 0:
+        hits.append(pos)
+        pos = data.find(vlen, pos + 1)
+    assert len(hits) >= 2, "values-buffer lengths not found in the metadata"
+    i64max = (1 << 63) - 1
+    cases = []
+    for h in hits:
+        cases.append(_patch_i64(raw, h - 8, i64max - 100))      # offset near INT64_MAX: off + len wraps
+        cases.append(_patch_i64(raw, h - 8, -(1 << 62)))         # negative offset
+        cases.append(_patch_i64(raw, h, i64max - 7))             # length near INT64_MAX
+        both = _patch_i64(raw, h - 8, i64max - 100)
+        cases.append(_patch_i64(both, h, i64max - 100))
+    # the footer's Block {offset:int64, metaDataLength:int32, pad, bodyLength:int64}: bodyLength and offset near INT64_MAX
+    footer_len = int(np.frombuffer(raw[-10:-6].tobytes(), np.int32)[0])
+    fstart = len(raw) - 10 - footer_len
+    for off in range(fstart, len(raw) - 10 - 24 + 1):
+        o, ml, _, bl = np.frombuffer(raw[off:off + 24].tobytes(), dtype=[("o", "<i8"), ("m", "<i4"), ("p", "<i4"), ("b", "<i8")])[0]
+        if 8 <= o < len(raw) and 8 <= ml < 4096 and 0 < bl < len(raw) and o + ml + bl <= len(raw):
+            cases.append(_patch_i64(raw, off + 16, i64max - 3))
+            cases.append(_patch_i64(raw, off, i64max - 3))
+            cases.append(_patch_i64(_patch_i64(raw, off, i64max - 64), off + 16, i64max - 64))
+            break
+    else:
+        raise AssertionError("record batch block not found in the footer")
+    for k, bad in enumerate(cases):
+        p = str(tmp_path / f"wrap{k}.arrow")
+        bad.tofile(p)
+        with pytest.raises(rdf.ArrowError):
+            with rdf.IpcFile(p) as f:
+                for name, dtype, _ in f.schema:   # if it were accepted, touching the view must still be legal -- but it must not be
+                    v = f.view(0, name)
+                    _ = v.value_slice()[-1]
+                raise AssertionError(f"case {k}: a file with wrapping offsets was accepted")
+
+
+def test_reader_bounds_schema_work(rdf, tmp_path):
+    """A schema whose nested fields all point at the same child table costs k^depth visits unless the total is bounded:
+    build a Struct field whose children vector lists ITSELF many times and check that open fails fast."""
+    import time
+
+    inner = pa.struct([("x", pa.int64())])
+    batch = pa.record_batch([pa.array([{"x": 1}], inner)], names=["s"])
+    good = str(tmp_path / "nest.arrow")
+    write_file(good, batch.schema, [batch])
+    raw = np.frombuffer(open(good, "rb").read(), dtype=np.uint8).copy()
+    footer_len = int(np.frombuffer(raw[-10:-6].tobytes(), np.int32)[0])
+    fstart = len(raw) - 10 - footer_len
+    # find a children vector of length 1 inside the footer (u32 count == 1 followed by a u32 offset to a table) and make the
+    # single child offset point back at the PARENT field table (a cycle): unbounded recursion without a budget
+    patched = 0
+    for vec in range(fstart, len(raw) - 10 - 8, 4):
+        cnt = int(np.frombuffer(raw[vec:vec + 4].tobytes(), np.uint32)[0])
+        if cnt != 1:
+            continue
+        for target in range(fstart, len(raw) - 10 - 4, 4):
+            rel = target - (vec + 4)
+            if rel <= 0:
+                continue
+            bad = raw.copy()
+            bad[vec + 4:vec + 8] = np.frombuffer(np.array([rel], dtype=np.uint32).tobytes(), dtype=np.uint8)
+            p = str(tmp_path / "cycle.arrow")
+            bad.tofile(p)
+            t0 = time.perf_counter()
+            try:
+                with rdf.IpcFile(p):
+                    pass
+            except rdf.ArrowError:
+                pass
+            assert time.perf_counter() - t0 < 2.0, "schema decoding did not terminate quickly"
+            patched += 1
+            if patched >= 300:
+                return
+    assert patched > 0
