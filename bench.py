@@ -525,12 +525,15 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"], help="primary series; at N > 1 the other one is measured too and reported under other_series")
+    ap.add_argument("--scaling", default=None, choices=["weak", "strong"],
+                    help="primary series (default: weak for the headline metric, strong for configs 3/4/5); at N > 1 the headline run measures the other one too and reports it under other_series")
     ap.add_argument("--config", type=int, default=1, choices=[1, 3, 4, 5], help="1 = the headline metric; 3/4/5 = the other BASELINE configs")
     ap.add_argument("--skip-e2e", action="store_true", help="profiling runs only: skip the host-buffer leg")
     ap.add_argument("--skip-cpu", action="store_true", help="profiling runs only: skip the CPU baseline leg")
     ap.add_argument("--skip-other-series", action="store_true", help="N > 1: measure only the primary scaling series")
     args = ap.parse_args()
+    if args.scaling is None:
+        args.scaling = "weak" if args.config == 1 else "strong"
     rank, world, local = env_ranks()
     if args.config != 1:
         from benchmarks import configs_bench

@@ -114,8 +114,9 @@ def main():
     # f32 trig
     f32 = G(rdf.F32, lens, 0, -1e3, 1e3, col_id=6)
     report("sin f32", "extra", timed(ctx, lambda: f32.sin()), "unary")
-    report("add f32", "extra", timed(ctx, lambda: f32.add(f32)), "binary")
-    f32.free()
+    f32b = G(rdf.F32, lens, 0, -1e3, 1e3, col_id=16)   # two DISTINCT inputs: a column added to itself moves 2w, not 3w, bytes per row
+    report("add f32", "extra", timed(ctx, lambda: f32.add(f32b)), "binary")
+    f32.free(); f32b.free()
     # ---- config 3: int64 aggregates with 10% nulls ----
     i64n = G(rdf.I64, lens, 3, col_id=7, null_mod=10)
     i64 = G(rdf.I64, lens, 3, col_id=8)
@@ -131,8 +132,18 @@ def main():
     report("cast f64 -> f32", "extra", timed(ctx, lambda: a.cast(rdf.F32)), "cast")
     report("cast i64 -> i8 (fallible, narrow out)", "extra", timed(ctx, lambda: i64.cast(rdf.I8)), "cast")
     i8 = i64.cast(rdf.I8)
-    report("add i8", "extra", timed(ctx, lambda: i8.add(i8)), "binary")
+    i8b = i64n.cast(rdf.I8)
+    report("add i8", "extra", timed(ctx, lambda: i8.add(i8b)), "binary")
     report("sum/min/max/count i8", "extra", timed(ctx, lambda: i8.aggregate_all()), "reduce")
+    i8v = G(rdf.I8, lens, 2, col_id=17, null_mod=10)
+    i16v = G(rdf.I16, lens, 2, col_id=18, null_mod=10)
+    u16 = G(rdf.U16, lens, 2, col_id=19)
+    report("sum/min/max/count i8 full range, 10% nulls", "extra", timed(ctx, lambda: i8v.aggregate_all()), "reduce")
+    report("sum/min/max/count i16 full range, 10% nulls", "extra", timed(ctx, lambda: i16v.aggregate_all()), "reduce")
+    report("sum/min/max/count u16, no nulls", "extra", timed(ctx, lambda: u16.aggregate_all()), "reduce")
+    report("sum/min/max/count i32 full range, 10% nulls", "extra", timed(ctx, lambda: i32n.aggregate_all()), "reduce")
+    for col in (i8b, i8v, i16v, u16):
+        col.free()
     # ---- N2 (next row): BooleanFilter compare + ChunkedArray::filter ----
     report("compare f64 > scalar", "N2", timed(ctx, lambda: a.gt(0.0)), "compare")
     report("compare f64 > f64", "N2", timed(ctx, lambda: a.gt(b)), "compare")

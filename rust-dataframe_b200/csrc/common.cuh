@@ -123,13 +123,18 @@ struct MaskRaw {
 };
 template <int E, int U>
 __device__ __forceinline__ void mask_issue(MaskRaw<E, U>& r, const uint32_t* __restrict__ v, int64_t bit0, int64_t stride_bits) {
+    // Every caller steps by kThreads * E bits, a whole number of 32-bit words: the shift is the same for all U steps and
+    // the word addresses are one base pointer plus constants (the 64-bit shift/LEA chain per step that the general form
+    // costs is most of the instruction count of a nullable tile).
+    const uint32_t* __restrict__ p = v + (bit0 >> 5);
+    const int sh = (int)(bit0 & 31);
+    const int stride_words = (int)(stride_bits >> 5);
+    const bool two = sh + E > 32;
 #pragma unroll
     for (int j = 0; j < U; j++) {
-        const int64_t bit = bit0 + (int64_t)j * stride_bits;
-        const int64_t w = bit >> 5;
-        r.sh[j] = (int)(bit & 31);
-        r.lo[j] = __ldg(v + w);
-        r.hi[j] = (r.sh[j] + E > 32) ? __ldg(v + w + 1) : 0u;
+        r.sh[j] = sh;
+        r.lo[j] = __ldg(p + j * stride_words);
+        r.hi[j] = two ? __ldg(p + j * stride_words + 1) : 0u;
     }
 }
 template <int E, int U>
@@ -261,8 +266,10 @@ cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, i
                         uint32_t* d_warp_counts, cudaStream_t s);
 // K4: one AggDev partial per tile (integer min/max as unsigned keys: extended value ^ 2^63 for signed types);
 // fold with launch_finish.
+// hint: 16 bytes of device scratch for the 8-byte integer instantiations ({min key, max key} published by the CTAs
+// of the launch; reset by the launcher) or nullptr.
 cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, AggDev* d_cta_partials,
-                          cudaStream_t s);
+                          cudaStream_t s, unsigned long long* hint = nullptr);
 int64_t reduce_partials(int dtype, int64_t tiles);  // number of partials launch_reduce writes
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
                             const GenDesc* d_descs, int n_chunks, int64_t total_tiles,

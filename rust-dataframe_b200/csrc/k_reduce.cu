@@ -11,7 +11,21 @@
 //     count.  No floating-point atomics anywhere => run-to-run deterministic.
 //     The reference folds strictly left-to-right; the difference is covered by the stated tolerance.
 //
-// Roofline: HBM, sizeof(T) + [nullable]/8 bytes/row (8 B/row for f64/i64, 8.125 with a bitmap).
+// Roofline: HBM, sizeof(T) + [nullable]/8 bytes/row (8 B/row for f64/i64, 8.125 with a bitmap).  The integer
+// instantiations are limited by the ALU pipe (64 lanes/clk/SM: ISETP/SEL/LOP3/VIMNMX), not by memory, unless the
+// per-element instruction count is kept down -- round 1 measured 30 instructions per Int64 element (ALU pipe 79 %
+// busy, DRAM 69 %).  What each width does about it:
+//   8-byte   min/max cost 4 ISETP + 4 SEL per element when done naively.  A thread's running extremes converge after
+//            a few elements, so the tile is first FILTERED (4 ISETP per element: does any valid element beat the running
+//            min or max?) and the update path runs only when a lane of the warp says yes.  CTAs start from a device-wide
+//            hint (the extremes earlier CTAs of the same launch have published -- real elements of the column, so a
+//            CTA whose own elements never beat the hint still reports a correct partial), which makes the update
+//            path rare after the first wave.  The sum is a predicated 64-bit add.
+//   4-byte   predicated VIMNMX for min/max, predicated IMAD.WIDE (FMA pipe) for the 64-bit sum.
+//   1/2-byte SIMD in a register: a 32-bit word holds 4 or 2 elements; validity bits are expanded to byte / half-word
+//            masks with two multiplies, nulls are replaced by the identity with one LOP3 per word, min/max run on
+//            packed 16-bit lanes (VIMNMX.U16x2 / .S16x2 -- bytes are split into even and odd lanes first), the sum
+//            is IDP.4A / IDP.2A against 0x01010101.
 #include <type_traits>
 
 #include "common.cuh"
@@ -33,28 +47,22 @@ template <typename T, bool IsFloat = RedInfo<T>::is_float> struct RedState;
 
 template <typename T>
 struct RedState<T, false> {
-    // narrow types fold a tile into a 32-bit accumulator (<= 64 elements of <= 16 bits per thread and tile),
-    // min/max are compared in T's own width and signedness; keys are formed once per CTA in to_dev
-    using Acc = typename std::conditional<(sizeof(T) <= 2), typename std::conditional<RedInfo<T>::is_signed, int, unsigned int>::type,
-                                          typename std::conditional<RedInfo<T>::is_signed, long long, unsigned long long>::type>::type;
-    static constexpr unsigned long long kFlip = RedInfo<T>::is_signed ? (1ull << 63) : 0ull;
-    unsigned long long sum; Acc acc; T mn, mx;
-    __device__ __forceinline__ void init() {
-        sum = 0; acc = 0;
-        mn = RedInfo<T>::is_signed ? (T)((1ull << (8 * sizeof(T) - 1)) - 1ull) : (T)~0ull;
-        mx = RedInfo<T>::is_signed ? (T)(-(long long)((1ull << (8 * sizeof(T) - 1)) - 1ull) - 1) : (T)0;
-    }
+    static constexpr bool kSigned = RedInfo<T>::is_signed;
+    static constexpr unsigned long long kFlip = kSigned ? (1ull << 63) : 0ull;
+    unsigned long long sum; T mn, mx;
+    __device__ __forceinline__ static T id_min() { return kSigned ? (T)((1ull << (8 * sizeof(T) - 1)) - 1ull) : (T)~0ull; }
+    __device__ __forceinline__ static T id_max() { return kSigned ? (T)(-(long long)((1ull << (8 * sizeof(T) - 1)) - 1ull) - 1) : (T)0; }
+    __device__ __forceinline__ void init() { sum = 0; mn = id_min(); mx = id_max(); }
     __device__ __forceinline__ void add(T x, bool valid) {
-        acc += valid ? (Acc)x : (Acc)0;
-        mn = (valid && x < mn) ? x : mn;
-        mx = (valid && x > mx) ? x : mx;
+        if (valid) {
+            sum += (unsigned long long)(long long)x;   // sign-/zero-extended, wrapping
+            mn = x < mn ? x : mn;
+            mx = x > mx ? x : mx;
+        }
     }
-    __device__ __forceinline__ void add_all_valid(T x) { acc += (Acc)x; mn = x < mn ? x : mn; mx = x > mx ? x : mx; }
-    __device__ __forceinline__ void end_tile() { sum += (unsigned long long)(long long)acc; acc = 0; }  // sign-/zero-extend, wrap
     __device__ __forceinline__ void merge(const RedState& o) { sum += o.sum; mn = o.mn < mn ? o.mn : mn; mx = o.mx > mx ? o.mx : mx; }
     __device__ __forceinline__ RedState shfl_xor(int o) const {
         RedState r;
-        r.acc = 0;
         r.sum = __shfl_xor_sync(0xffffffffu, sum, o);
         if constexpr (sizeof(T) == 8) {
             r.mn = (T)__shfl_xor_sync(0xffffffffu, (long long)mn, o);
@@ -65,11 +73,10 @@ struct RedState<T, false> {
         }
         return r;
     }
+    __device__ __forceinline__ static unsigned long long key(T v) { return (unsigned long long)(long long)v ^ kFlip; }
+    __device__ __forceinline__ static T from_key(unsigned long long k) { return (T)(long long)(k ^ kFlip); }
     __device__ __forceinline__ void to_dev(AggDev* d, unsigned long long cnt) const {
-        d->sum_bits = sum;
-        d->min_bits = (unsigned long long)(long long)mn ^ kFlip;  // order-preserving unsigned keys
-        d->max_bits = (unsigned long long)(long long)mx ^ kFlip;
-        d->count = cnt;
+        d->sum_bits = sum; d->min_bits = key(mn); d->max_bits = key(mx); d->count = cnt;
     }
 };
 
@@ -79,7 +86,6 @@ struct RedState<T, true> {
     __device__ __forceinline__ void init() { sum = 0.0; }
     __device__ __forceinline__ void add(T x, bool valid) { sum = __dadd_rn(sum, valid ? (double)x : 0.0); }
     __device__ __forceinline__ void add_all_valid(T x) { sum = __dadd_rn(sum, (double)x); }
-    __device__ __forceinline__ void end_tile() {}
     __device__ __forceinline__ void merge(const RedState& o) { sum = __dadd_rn(sum, o.sum); }
     __device__ __forceinline__ RedState shfl_xor(int o) const {
         RedState r;
@@ -91,20 +97,188 @@ struct RedState<T, true> {
     }
 };
 
+// ---- one full tile, per element width -----------------------------------------------------------------------------
+// x[kUnroll]: the thread's vectors of the tile; HAS_V: rv holds the raw validity words (mask_get(rv, j) = the E bits
+// of vector j).  Returns the number of valid elements.
+
+// 8-byte integers: filter, then (rarely) update.
+template <typename T, bool HAS_V>
+__device__ __forceinline__ unsigned int tile_int64(RedState<T>& st, const Vec<T, 2> (&x)[kUnroll], const MaskRaw<2, kUnroll>& rv) {
+    unsigned int cnt = 0;
+    bool beat = false;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t m = HAS_V ? mask_get<2, kUnroll>(rv, j) : 3u;
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const T v = x[j].e[e];
+            const bool ok = !HAS_V || ((m >> e) & 1u);
+            if (ok) st.sum += (unsigned long long)v;
+            beat = beat | (ok & ((v < st.mn) | (v > st.mx)));   // bitwise on purpose: predicates, no branches
+        }
+        cnt += HAS_V ? __popc(m) : 2;
+    }
+    if (__any_sync(0xffffffffu, beat)) {   // some lane holds a new extreme: rare once the running min/max have converged
+#pragma unroll
+        for (int j = 0; j < kUnroll; j++) {
+            const uint32_t m = HAS_V ? mask_get<2, kUnroll>(rv, j) : 3u;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const T v = x[j].e[e];
+                if (!HAS_V || ((m >> e) & 1u)) { st.mn = v < st.mn ? v : st.mn; st.mx = v > st.mx ? v : st.mx; }
+            }
+        }
+    }
+    return cnt;
+}
+
+// 4-byte integers: predicated min/max, 64-bit sum by a widening multiply-add (x * valid + sum on the FMA pipe).
+template <typename T, bool HAS_V>
+__device__ __forceinline__ unsigned int tile_int32(RedState<T>& st, const Vec<T, 4> (&x)[kUnroll], const MaskRaw<4, kUnroll>& rv) {
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t m = HAS_V ? mask_get<4, kUnroll>(rv, j) : 15u;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const T v = x[j].e[e];
+            const bool ok = !HAS_V || ((m >> e) & 1u);
+            if (ok) {
+                if constexpr (RedInfo<T>::is_signed) asm("mad.wide.s32 %0, %1, 1, %0;" : "+l"(st.sum) : "r"((int)v));
+                else asm("mad.wide.u32 %0, %1, 1, %0;" : "+l"(st.sum) : "r"((unsigned)v));
+                st.mn = v < st.mn ? v : st.mn;
+                st.mx = v > st.mx ? v : st.mx;
+            }
+        }
+        cnt += HAS_V ? __popc(m) : 4;
+    }
+    return cnt;
+}
+
+// Packed accumulators of the 1- and 2-byte instantiations (folded into the scalar state once per CTA-thread).
+template <typename T>
+struct Packed {
+    static constexpr bool kSigned = RedInfo<T>::is_signed;
+    // 2-byte: mn/mx hold two lanes of T.  1-byte: lanes hold order-preserving UNSIGNED byte keys (value ^ 0x80 for
+    // signed) zero-extended to 16 bits -- [0] even bytes, [1] odd bytes.
+    uint32_t mn[2], mx[2];
+    int acc;   // 32-bit sum of one tile (<= 64 elements of <= 16 bits), flushed into the 64-bit sum per tile
+    __device__ __forceinline__ void init() {
+        if constexpr (sizeof(T) == 2) { mn[0] = mn[1] = kSigned ? 0x7fff7fffu : 0xffffffffu; mx[0] = mx[1] = kSigned ? 0x80008000u : 0u; }
+        else { mn[0] = mn[1] = 0x00ff00ffu; mx[0] = mx[1] = 0u; }
+        acc = 0;
+    }
+    __device__ __forceinline__ void flush(RedState<T>& st) {
+        st.sum += kSigned ? (unsigned long long)(long long)acc : (unsigned long long)(unsigned int)acc;
+        acc = 0;
+    }
+    __device__ __forceinline__ void fold_into(RedState<T>& st) const {
+        if constexpr (sizeof(T) == 2) {
+            const uint32_t a = kSigned ? __vmins2(mn[0], mn[1]) : __vminu2(mn[0], mn[1]);
+            const uint32_t b = kSigned ? __vmaxs2(mx[0], mx[1]) : __vmaxu2(mx[0], mx[1]);
+            const T a0 = (T)(a & 0xffffu), a1 = (T)(a >> 16), b0 = (T)(b & 0xffffu), b1 = (T)(b >> 16);
+            const T lo = a0 < a1 ? a0 : a1, hi = b0 > b1 ? b0 : b1;
+            st.mn = lo < st.mn ? lo : st.mn;
+            st.mx = hi > st.mx ? hi : st.mx;
+        } else {
+            const uint32_t a = __vminu2(mn[0], mn[1]), b = __vmaxu2(mx[0], mx[1]);
+            const uint32_t klo = min(a & 0xffffu, a >> 16), khi = max(b & 0xffffu, b >> 16);
+            // an untouched accumulator holds the identity keys (0xff / 0x00): they map back to T's identities
+            const T lo = (T)(klo ^ (kSigned ? 0x80u : 0u)), hi = (T)(khi ^ (kSigned ? 0x80u : 0u));
+            st.mn = lo < st.mn ? lo : st.mn;
+            st.mx = hi > st.mx ? hi : st.mx;
+        }
+    }
+};
+
+// 2-byte integers: two elements per 32-bit word.
+template <typename T, bool HAS_V>
+__device__ __forceinline__ unsigned int tile_int16(Packed<T>& pk, const Vec<T, 8> (&x)[kUnroll], const MaskRaw<8, kUnroll>& rv) {
+    constexpr bool S = RedInfo<T>::is_signed;
+    constexpr uint32_t ID_MIN = S ? 0x7fff7fffu : 0xffffffffu, ID_MAX = S ? 0x80008000u : 0u;
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t m = HAS_V ? mask_get<8, kUnroll>(rv, j) : 0xffu;
+        const uint32_t w[4] = {x[j].q.x, x[j].q.y, x[j].q.z, x[j].q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t wmin = w[k], wmax = w[k], wsum = w[k];
+            if (HAS_V) {
+                const uint32_t m16 = (((m >> (2 * k)) * 0x8001u) & 0x00010001u) * 0xffffu;   // 2 bits -> two half-word masks
+                wmin = (w[k] & m16) | (~m16 & ID_MIN);
+                wmax = (w[k] & m16) | (~m16 & ID_MAX);
+                wsum = w[k] & m16;
+            }
+            if constexpr (S) {
+                pk.mn[k & 1] = __vmins2(pk.mn[k & 1], wmin); pk.mx[k & 1] = __vmaxs2(pk.mx[k & 1], wmax);
+                pk.acc = __dp2a_lo((int)wsum, 0x0101, pk.acc);
+            } else {
+                pk.mn[k & 1] = __vminu2(pk.mn[k & 1], wmin); pk.mx[k & 1] = __vmaxu2(pk.mx[k & 1], wmax);
+                pk.acc = (int)__dp2a_lo(wsum, 0x0101u, (unsigned)pk.acc);
+            }
+        }
+        cnt += HAS_V ? __popc(m) : 8;
+    }
+    return cnt;
+}
+
+// 1-byte integers: four elements per 32-bit word; min/max on unsigned byte keys split into even / odd 16-bit lanes.
+template <typename T, bool HAS_V>
+__device__ __forceinline__ unsigned int tile_int8(Packed<T>& pk, const Vec<T, 16> (&x)[kUnroll], const MaskRaw<16, kUnroll>& rv) {
+    constexpr bool S = RedInfo<T>::is_signed;
+    constexpr uint32_t FLIP = S ? 0x80808080u : 0u;
+    unsigned int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < kUnroll; j++) {
+        const uint32_t m = HAS_V ? mask_get<16, kUnroll>(rv, j) : 0xffffu;
+        const uint32_t w[4] = {x[j].q.x, x[j].q.y, x[j].q.z, x[j].q.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            uint32_t kmin = w[k] ^ FLIP, kmax = w[k] ^ FLIP, wsum = w[k];
+            if (HAS_V) {
+                const uint32_t m8 = ((((m >> (4 * k)) & 0xfu) * 0x00204081u) & 0x01010101u) * 0xffu;   // 4 bits -> four byte masks
+                kmin = (w[k] ^ FLIP) | ~m8;    // nulls -> 0xff, the identity of min over unsigned keys
+                kmax = (w[k] ^ FLIP) & m8;     // nulls -> 0x00
+                wsum = w[k] & m8;
+            }
+            pk.mn[0] = __vminu2(pk.mn[0], kmin & 0x00ff00ffu);
+            pk.mn[1] = __vminu2(pk.mn[1], __byte_perm(kmin, 0u, 0x4341));   // bytes 1 and 3, zero-extended
+            pk.mx[0] = __vmaxu2(pk.mx[0], kmax & 0x00ff00ffu);
+            pk.mx[1] = __vmaxu2(pk.mx[1], __byte_perm(kmax, 0u, 0x4341));
+            if constexpr (S) pk.acc = __dp4a((int)wsum, 0x01010101, pk.acc);
+            else pk.acc = (int)__dp4a(wsum, 0x01010101u, (unsigned)pk.acc);
+        }
+        cnt += HAS_V ? __popc(m) : 16;
+    }
+    return cnt;
+}
+
 // K consecutive tiles per CTA, not persistent (measured on the read-only f64 stream: 7.2 TB/s for K <= 2,
 // 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  Floats use K = 2; integers
 // K = 4 to amortise the heavier 3-value block reduction.  One partial per CTA in CTA order; launch_finish
 // (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
+// hint (8-byte integers only, else nullptr): {min key, max key} of what earlier CTAs of THIS launch have seen.
 template <typename T, int K>
 __global__ void __launch_bounds__(kThreads)
-k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ cta_partials) {
+k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ cta_partials,
+         unsigned long long* __restrict__ hint) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
+    constexpr bool IS_INT = !RedInfo<T>::is_float;
     using S = RedState<T>;
     __shared__ S s_state[kWarpsPerCta];
     __shared__ unsigned int s_cnt[kWarpsPerCta];
 
     S st; st.init();
+    if constexpr (IS_INT && sizeof(T) == 8) {
+        if (hint) {   // real elements of this column (or the identities): a safe starting point for the filter
+            st.mn = S::from_key(__ldcg(hint));
+            st.mx = S::from_key(__ldcg(hint + 1));
+        }
+    }
+    [[maybe_unused]] Packed<typename std::conditional<(IS_INT && sizeof(T) <= 2), T, int8_t>::type> pk;
+    if constexpr (IS_INT && sizeof(T) <= 2) pk.init();
     unsigned int cnt = 0;
     int c = -1;
     int64_t c_tile0 = 0, c_tile_end = -1, len = 0, off = 0;
@@ -129,22 +303,34 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
             Vec<T, E> x[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
-            if (vi) {
-                MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
-                mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
+            MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+            if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
+            if constexpr (!IS_INT) {
+                if (vi) {
 #pragma unroll
-                for (int j = 0; j < kUnroll; j++) {
-                    const uint32_t m = mask_get<E, kUnroll>(rv, j);
+                    for (int j = 0; j < kUnroll; j++) {
+                        const uint32_t m = mask_get<E, kUnroll>(rv, j);
 #pragma unroll
-                    for (int e = 0; e < E; e++) st.add(x[j].e[e], (m >> e) & 1u);
-                    cnt += __popc(m);
+                        for (int e = 0; e < E; e++) st.add(x[j].e[e], (m >> e) & 1u);
+                        cnt += __popc(m);
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < kUnroll; j++)
+#pragma unroll
+                        for (int e = 0; e < E; e++) st.add_all_valid(x[j].e[e]);
+                    cnt += kUnroll * E;
                 }
+            } else if constexpr (sizeof(T) == 8) {
+                cnt += vi ? tile_int64<T, true>(st, x, rv) : tile_int64<T, false>(st, x, rv);
+            } else if constexpr (sizeof(T) == 4) {
+                cnt += vi ? tile_int32<T, true>(st, x, rv) : tile_int32<T, false>(st, x, rv);
+            } else if constexpr (sizeof(T) == 2) {
+                cnt += vi ? tile_int16<T, true>(pk, x, rv) : tile_int16<T, false>(pk, x, rv);
+                pk.flush(st);
             } else {
-#pragma unroll
-                for (int j = 0; j < kUnroll; j++)
-#pragma unroll
-                    for (int e = 0; e < E; e++) st.add_all_valid(x[j].e[e]);
-                cnt += kUnroll * E;
+                cnt += vi ? tile_int8<T, true>(pk, x, rv) : tile_int8<T, false>(pk, x, rv);
+                pk.flush(st);
             }
         } else {
 #pragma unroll 1
@@ -159,8 +345,8 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
                 cnt += __popc(m);
             }
         }
-        st.end_tile();
     }
+    if constexpr (IS_INT && sizeof(T) <= 2) pk.fold_into(st);
     // fixed xor-shuffle tree inside each warp, then thread 0 folds the warp results in warp order
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { S other = st.shfl_xor(o); st.merge(other); }
@@ -173,8 +359,18 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
 #pragma unroll
         for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_state[w]); total += s_cnt[w]; }
         t.to_dev(&cta_partials[blockIdx.x], total);
+        if constexpr (IS_INT && sizeof(T) == 8) {
+            if (hint && total) {   // publish what this CTA has seen: later CTAs start their filter from it
+                atomicMin(hint, S::key(t.mn));
+                atomicMax(hint + 1, S::key(t.mx));
+            }
+        }
     }
 }
+
+// Resets the min/max hint of the 8-byte integer instantiations (one thread; runs before every such launch so that a
+// hint can never come from another column).
+__global__ void k_reduce_hint_reset(unsigned long long* hint) { hint[0] = ~0ull; hint[1] = 0ull; }
 
 constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 2;
 int64_t reduce_partials(int dtype, int64_t tiles) {
@@ -183,28 +379,31 @@ int64_t reduce_partials(int dtype, int64_t tiles) {
 }
 
 template <typename T>
-static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned long long* hint, cudaStream_t s) {
     constexpr int K = RedInfo<T>::is_float ? kReduceTilesFloat : kReduceTilesInt;
-    k_reduce<T, K><<<(unsigned)((tiles + K - 1) / K), kThreads, 0, s>>>(d, n, tiles, partials);
+    const unsigned grid = (unsigned)((tiles + K - 1) / K);
+    if (sizeof(T) != 8 || RedInfo<T>::is_float || grid < 64) hint = nullptr;   // a hint pays off only across waves of CTAs
+    if (hint) k_reduce_hint_reset<<<1, 1, 0, s>>>(hint);
+    k_reduce<T, K><<<grid, kThreads, 0, s>>>(d, n, tiles, partials, hint);
     return cudaGetLastError();
 }
 
 // Per-tile partials of chunks described by d (k_finish folds them; with tiles == 0 nothing is launched and
-// k_finish produces the identity).
-cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+// k_finish produces the identity).  hint: 16 bytes of device scratch (may be nullptr).
+cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s, unsigned long long* hint) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (dtype) {
-        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, s);
-        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, s);
-        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, s);
-        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, s);
-        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, s);
-        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, s);
-        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, s);
-        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, s);
-        case T_F32: return launch_one<float>(d, n, tiles, partials, s);
-        case T_F64: return launch_one<double>(d, n, tiles, partials, s);
+        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, hint, s);
+        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, hint, s);
+        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, hint, s);
+        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, hint, s);
+        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, hint, s);
+        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, hint, s);
+        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, hint, s);
+        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, hint, s);
+        case T_F32: return launch_one<float>(d, n, tiles, partials, hint, s);
+        case T_F64: return launch_one<double>(d, n, tiles, partials, hint, s);
         default: return cudaErrorInvalidValue;
     }
 }

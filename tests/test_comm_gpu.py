@@ -57,3 +57,40 @@ def test_bench_line_with_the_driver_command_line():
     assert line["n_gpus"] == world and line["value"] > 0 and line["detail"]["collectives_in_timed_region"] >= 20
     assert line["check"]["rows"] == 100_000_000 * world and line["check"]["count"] == 100_000_000 * world
     assert line["other_series"]["scaling"] == "strong" and line["other_series"]["check"]["count"] == 100_000_000
+
+
+@pytest.mark.gpu
+def test_single_rank_communicator(rdf, oracle):
+    """A communicator of ONE rank exercises the whole on-stream combine (pack -> grouped ncclAllReduce/ncclAllGather ->
+    unpack into the pinned slot) on any box: the results must equal the plain single-GPU ones bit for bit."""
+    import numpy as np
+
+    ctx = rdf.Context(0)
+    rng = np.random.default_rng(5)
+    lens = [5000, 0, 1, 70001]
+    ints = [rdf.PrimitiveArray.from_numpy(rng.integers(-2 ** 62, 2 ** 62, n), rng.random(n) > 0.1) for n in lens]
+    flts = [rdf.PrimitiveArray.from_numpy(rng.uniform(-1e3, 1e3, n), rng.random(n) > 0.1) for n in lens]
+    ci, cf = rdf.Column.upload(ints, ctx=ctx), rdf.Column.upload(flts, ctx=ctx)
+    plain = [ci.aggregate_all(), cf.aggregate_all()]
+    plain_many = rdf.Column.aggregate_all_many([ci, cf, ci])
+    col, plain_fused = cf.binary_agg(rdf.native.ADD, cf)
+    col.free()
+    ctx.comm_attach(rdf.Context.comm_unique_id(), 0, 1)
+    info = ctx.comm_info()
+    assert info["world"] == 1 and info["nccl_version"] >= 20000
+    assert [ci.aggregate_all(), cf.aggregate_all()] == plain
+    assert rdf.Column.aggregate_all_many([ci, cf, ci]) == plain_many
+    futs = [cf.binary_agg_async(rdf.native.ADD, cf) for _ in range(4)]
+    for col, fut in futs:
+        assert fut.result() == plain_fused
+        col.free()
+    assert ci.count() == sum(c.length - c.null_count for c in ints)
+    assert ctx.comm_info()["collectives"] >= 8
+    with pytest.raises(rdf.ReferencePanic):
+        ci.max()        # the empty chunk: reference unwrap() panic, reported through the combined flags
+    ctx.comm_barrier()
+    assert float(ctx.comm_all_reduce([2.5], rdf.native.MAX)[0]) == 2.5
+    ctx.comm_detach()
+    assert ci.aggregate_all() == plain[0]
+    ci.free(); cf.free()
+    ctx.close()
