@@ -188,6 +188,7 @@ int main(int argc, char** argv) {
                         rate(t1 - t0), rate(t2 - t1), rate(t3 - t2), rate(t4 - t3));
     }
     { double t0 = now(); memcpy(dst, src, bytes); double t1 = now(); printf("single-thread memcpy %.1f GB/s\n", rate(t1 - t0)); }
+    CK(cudaMemset(dev, 3, bytes));   // the baselines overwrote it; the download checks below expect 3
     struct Cfg { int threads, spt; size_t job; bool nt; int streams; };
     std::vector<Cfg> cfgs;
     for (int t : {4, 8, 12, 16, 24, 32})

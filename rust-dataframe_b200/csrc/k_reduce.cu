@@ -15,17 +15,15 @@
 // instantiations are limited by the ALU pipe (64 lanes/clk/SM: ISETP/SEL/LOP3/VIMNMX), not by memory, unless the
 // per-element instruction count is kept down -- round 1 measured 30 instructions per Int64 element (ALU pipe 79 %
 // busy, DRAM 69 %).  What each width does about it:
-//   8-byte   min/max cost 4 ISETP + 4 SEL per element when done naively.  A thread's running extremes converge after
-//            a few elements, so the tile is first FILTERED (4 ISETP per element: does any valid element beat the running
-//            min or max?) and the update path runs only when a lane of the warp says yes.  CTAs start from a device-wide
-//            hint (the extremes earlier CTAs of the same launch have published -- real elements of the column, so a
-//            CTA whose own elements never beat the hint still reports a correct partial), which makes the update
-//            path rare after the first wave.  The sum is a predicated 64-bit add.
+//   8-byte   4 ISETP + 4 SEL per element for min/max and a 64-bit add, all under the validity predicate; the validity
+//            words of a tile come off one base pointer (common.cuh mask_issue), which removed a third of the
+//            instructions of a nullable tile.
 //   4-byte   predicated VIMNMX for min/max, predicated IMAD.WIDE (FMA pipe) for the 64-bit sum.
 //   1/2-byte SIMD in a register: a 32-bit word holds 4 or 2 elements; validity bits are expanded to byte / half-word
 //            masks with two multiplies, nulls are replaced by the identity with one LOP3 per word, min/max run on
 //            packed 16-bit lanes (VIMNMX.U16x2 / .S16x2 -- bytes are split into even and odd lanes first), the sum
 //            is IDP.4A / IDP.2A against 0x01010101.
+#include <algorithm>
 #include <type_traits>
 
 #include "common.cuh"
@@ -101,33 +99,30 @@ struct RedState<T, true> {
 // x[kUnroll]: the thread's vectors of the tile; HAS_V: rv holds the raw validity words (mask_get(rv, j) = the E bits
 // of vector j).  Returns the number of valid elements.
 
-// 8-byte integers: filter, then (rarely) update.
+// 8-byte integers: everything under the validity predicate (ISETP pairs + SEL for min/max, a 64-bit add for the sum).
+// (A filter-then-update variant with a launch-wide min/max hint was tried in round 2: the filter needs the same four
+// ISETP per element as the update and the first wave of CTAs pays for both -- 0.21 ms instead of 0.147 ms.)
 template <typename T, bool HAS_V>
 __device__ __forceinline__ unsigned int tile_int64(RedState<T>& st, const Vec<T, 2> (&x)[kUnroll], const MaskRaw<2, kUnroll>& rv) {
     unsigned int cnt = 0;
-    bool beat = false;
 #pragma unroll
     for (int j = 0; j < kUnroll; j++) {
         const uint32_t m = HAS_V ? mask_get<2, kUnroll>(rv, j) : 3u;
 #pragma unroll
         for (int e = 0; e < 2; e++) {
             const T v = x[j].e[e];
-            const bool ok = !HAS_V || ((m >> e) & 1u);
-            if (ok) st.sum += (unsigned long long)v;
-            beat = beat | (ok & ((v < st.mn) | (v > st.mx)));   // bitwise on purpose: predicates, no branches
-        }
-        cnt += HAS_V ? __popc(m) : 2;
-    }
-    if (__any_sync(0xffffffffu, beat)) {   // some lane holds a new extreme: rare once the running min/max have converged
-#pragma unroll
-        for (int j = 0; j < kUnroll; j++) {
-            const uint32_t m = HAS_V ? mask_get<2, kUnroll>(rv, j) : 3u;
-#pragma unroll
-            for (int e = 0; e < 2; e++) {
-                const T v = x[j].e[e];
-                if (!HAS_V || ((m >> e) & 1u)) { st.mn = v < st.mn ? v : st.mn; st.mx = v > st.mx ? v : st.mx; }
+            const uint32_t ok = HAS_V ? ((m >> e) & 1u) : 1u;
+            // sum += v * ok as two multiply-adds (IMAD.WIDE + IMAD: the FMA pipe, which this kernel leaves idle; the ALU
+            // pipe is what limits it): low word into the 64-bit sum with carry, high word into its upper half
+            asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(st.sum) : "r"((uint32_t)(unsigned long long)v), "r"(ok));
+            asm("{.reg .b32 l, h;\n mov.b64 {l, h}, %0;\n mad.lo.u32 h, %1, %2, h;\n mov.b64 %0, {l, h};}"
+                : "+l"(st.sum) : "r"((uint32_t)((unsigned long long)v >> 32)), "r"(ok));
+            if (ok) {
+                st.mn = v < st.mn ? v : st.mn;
+                st.mx = v > st.mx ? v : st.mx;
             }
         }
+        cnt += HAS_V ? __popc(m) : 2;
     }
     return cnt;
 }
@@ -254,29 +249,26 @@ __device__ __forceinline__ unsigned int tile_int8(Packed<T>& pk, const Vec<T, 16
     return cnt;
 }
 
-// K consecutive tiles per CTA, not persistent (measured on the read-only f64 stream: 7.2 TB/s for K <= 2,
-// 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  Floats use K = 2; integers
-// K = 4 to amortise the heavier 3-value block reduction.  One partial per CTA in CTA order; launch_finish
-// (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
-// hint (8-byte integers only, else nullptr): {min key, max key} of what earlier CTAs of THIS launch have seen.
-template <typename T, int K>
+// K consecutive tiles per CTA (K = 2 for floats, 4 for integers, more when that would give more than kMaxCtas CTAs),
+// not grid-stride persistent (measured on the read-only f64 stream: 7.2 TB/s for K <= 2, 6.95 TB/s for grid-stride
+// persistent variants, benchmarks/tune_stream.cu).  One partial per CTA in CTA order; the LAST CTA to finish (a ticket)
+// folds all partials with a fixed per-thread assignment and a fixed tree -- the order depends only on the grid size, never
+// on which CTA happens to be last -- and writes the result (device memory or device-mapped host memory).  No second
+// launch: at 1e8 rows the separate k_finish cost 10 us of a 125 us reduction.
+template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ cta_partials,
-         unsigned long long* __restrict__ hint) {
+k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, int K, AggDev* __restrict__ cta_partials,
+         unsigned int* __restrict__ ticket, AggDev* __restrict__ result) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr bool IS_INT = !RedInfo<T>::is_float;
     using S = RedState<T>;
     __shared__ S s_state[kWarpsPerCta];
     __shared__ unsigned int s_cnt[kWarpsPerCta];
+    __shared__ AggDev s_part[kWarpsPerCta];
+    __shared__ bool s_last;
 
     S st; st.init();
-    if constexpr (IS_INT && sizeof(T) == 8) {
-        if (hint) {   // real elements of this column (or the identities): a safe starting point for the filter
-            st.mn = S::from_key(__ldcg(hint));
-            st.mx = S::from_key(__ldcg(hint + 1));
-        }
-    }
     [[maybe_unused]] Packed<typename std::conditional<(IS_INT && sizeof(T) <= 2), T, int8_t>::type> pk;
     if constexpr (IS_INT && sizeof(T) <= 2) pk.init();
     unsigned int cnt = 0;
@@ -359,51 +351,88 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
 #pragma unroll
         for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_state[w]); total += s_cnt[w]; }
         t.to_dev(&cta_partials[blockIdx.x], total);
-        if constexpr (IS_INT && sizeof(T) == 8) {
-            if (hint && total) {   // publish what this CTA has seen: later CTAs start their filter from it
-                atomicMin(hint, S::key(t.mn));
-                atomicMax(hint + 1, S::key(t.mx));
-            }
-        }
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    // ---- the last CTA: fold the gridDim.x partials (thread t takes t, t + 256, ...; fixed tree afterwards) ----
+    __threadfence();
+    auto merge = [](AggDev& a, const AggDev& b) {
+        if constexpr (!IS_INT)
+            a.sum_bits = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a.sum_bits), __longlong_as_double((long long)b.sum_bits)));
+        else a.sum_bits += b.sum_bits;
+        a.min_bits = b.min_bits < a.min_bits ? b.min_bits : a.min_bits;
+        a.max_bits = b.max_bits > a.max_bits ? b.max_bits : a.max_bits;
+        a.count += b.count;
+    };
+    AggDev acc; acc.sum_bits = 0; acc.min_bits = ~0ull; acc.max_bits = 0; acc.count = 0;
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
+        AggDev p;
+        p.sum_bits = __ldcg(&cta_partials[i].sum_bits); p.min_bits = __ldcg(&cta_partials[i].min_bits);
+        p.max_bits = __ldcg(&cta_partials[i].max_bits); p.count = __ldcg(&cta_partials[i].count);
+        merge(acc, p);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        AggDev r;
+        r.sum_bits = __shfl_xor_sync(0xffffffffu, acc.sum_bits, o); r.min_bits = __shfl_xor_sync(0xffffffffu, acc.min_bits, o);
+        r.max_bits = __shfl_xor_sync(0xffffffffu, acc.max_bits, o); r.count = __shfl_xor_sync(0xffffffffu, acc.count, o);
+        merge(acc, r);
+    }
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        AggDev fin = s_part[0];
+        for (int w = 1; w < kWarpsPerCta; w++) merge(fin, s_part[w]);
+        *result = fin;
+        __threadfence_system();   // result may be device-mapped host memory
+        *ticket = 0;              // ready for the next launch on this stream
     }
 }
 
-// Resets the min/max hint of the 8-byte integer instantiations (one thread; runs before every such launch so that a
-// hint can never come from another column).
-__global__ void k_reduce_hint_reset(unsigned long long* hint) { hint[0] = ~0ull; hint[1] = 0ull; }
-
 constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 2;
+constexpr int64_t kMaxCtas = 4096;   // bounds the partials the last CTA folds (16 per thread)
+static int tiles_per_cta(int dtype, int64_t tiles) {
+    const int64_t k = dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt;
+    return (int)std::max<int64_t>(k, (tiles + kMaxCtas - 1) / kMaxCtas);
+}
 int64_t reduce_partials(int dtype, int64_t tiles) {
-    const int k = dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt;
+    const int k = tiles_per_cta(dtype, tiles);
     return (tiles + k - 1) / k;
 }
 
+// The identity aggregate for an empty input (no launch of k_reduce happens then).
+__global__ void k_reduce_empty(AggDev* result) {
+    result->sum_bits = 0; result->min_bits = ~0ull; result->max_bits = 0; result->count = 0;
+    __threadfence_system();
+}
+
 template <typename T>
-static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned long long* hint, cudaStream_t s) {
-    constexpr int K = RedInfo<T>::is_float ? kReduceTilesFloat : kReduceTilesInt;
+static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned int* ticket, AggDev* result, cudaStream_t s) {
+    const int K = tiles_per_cta(RedInfo<T>::is_float ? T_F64 : T_I64, tiles);
     const unsigned grid = (unsigned)((tiles + K - 1) / K);
-    if (sizeof(T) != 8 || RedInfo<T>::is_float || grid < 64) hint = nullptr;   // a hint pays off only across waves of CTAs
-    if (hint) k_reduce_hint_reset<<<1, 1, 0, s>>>(hint);
-    k_reduce<T, K><<<grid, kThreads, 0, s>>>(d, n, tiles, partials, hint);
+    k_reduce<T><<<grid, kThreads, 0, s>>>(d, n, tiles, K, partials, ticket, result);
     return cudaGetLastError();
 }
 
-// Per-tile partials of chunks described by d (k_finish folds them; with tiles == 0 nothing is launched and
-// k_finish produces the identity).  hint: 16 bytes of device scratch (may be nullptr).
-cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s, unsigned long long* hint) {
-    if (tiles <= 0) return cudaSuccess;
+// sum/min/max/count of the chunks described by d into *result (device memory or device-mapped host memory): ONE launch.
+// partials: scratch for reduce_partials(dtype, tiles) records; ticket: a zeroed counter the kernel leaves zeroed.
+cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned int* ticket, AggDev* result,
+                          cudaStream_t s) {
+    if (tiles <= 0) { k_reduce_empty<<<1, 1, 0, s>>>(result); return cudaGetLastError(); }
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (dtype) {
-        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, hint, s);
-        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, hint, s);
-        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, hint, s);
-        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, hint, s);
-        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, hint, s);
-        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, hint, s);
-        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, hint, s);
-        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, hint, s);
-        case T_F32: return launch_one<float>(d, n, tiles, partials, hint, s);
-        case T_F64: return launch_one<double>(d, n, tiles, partials, hint, s);
+        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, ticket, result, s);
+        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, ticket, result, s);
+        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, ticket, result, s);
+        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, ticket, result, s);
+        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, ticket, result, s);
+        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, ticket, result, s);
+        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, ticket, result, s);
+        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, ticket, result, s);
+        case T_F32: return launch_one<float>(d, n, tiles, partials, ticket, result, s);
+        case T_F64: return launch_one<double>(d, n, tiles, partials, ticket, result, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -208,8 +208,7 @@ struct bdf_ctx {
     AggDev* d_partials = nullptr;       // per-tile partials of k_reduce (compute stream only)
     size_t red_part_cap = 0;
     AggDev* d_stage2 = nullptr;         // k_finish staging for the k_reduce path
-    unsigned int* d_ticket = nullptr;   // [0]: k_reduce, [1]: k_finish
-    unsigned long long* d_hint = nullptr;  // k_reduce of 8-byte integers: {min key, max key} seen so far by the launch
+    unsigned int* d_ticket = nullptr;   // [1]: k_finish of the fused aggregates (finish stream), [2]: k_reduce (compute stream)
     AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
     int fut_next = 0;                   // ring cursor over the future half of h_agg
@@ -473,10 +472,8 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
         c->red_part_cap = cap;
     }
     {
-        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // k_reduce + k_finish
-        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->s_compute, c->d_hint));
-        c->launches++;
-        CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, result, c->s_compute));
+        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // one launch: the last CTA folds the partials
+        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->d_ticket + 2, result, c->s_compute));
     }
     return BDF_OK;
 }
@@ -1731,7 +1728,6 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->d_stage2) cudaFree(c->d_stage2);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
-    if (c->d_hint) cudaFree(c->d_hint);
     if (c->flush_buf) cudaFree(c->flush_buf);
     if (c->comm) { comm_destroy(c->comm); c->comm = nullptr; }
     if (c->d_local) cudaFree(c->d_local);
@@ -1777,11 +1773,10 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaHostAlloc((void**)&c->h_flag, sizeof(int), cudaHostAllocDefault));
     CK(cudaMalloc((void**)&c->d_stage2, (size_t)c->sm_count * sizeof(AggDev)));
     CK(cudaMalloc((void**)&c->d_stage, (size_t)c->sm_count * sizeof(AggDev)));
-    CK(cudaMalloc((void**)&c->d_ticket, 2 * sizeof(unsigned int)));
+    CK(cudaMalloc((void**)&c->d_ticket, 4 * sizeof(unsigned int)));
     CK(cudaMalloc((void**)&c->d_flag, sizeof(int)));
-    CK(cudaMalloc((void**)&c->d_hint, 2 * sizeof(unsigned long long)));
     CK(cudaMalloc((void**)&c->d_local, (size_t)kAggSlots * sizeof(AggDev)));
-    CK(cudaMemset(c->d_ticket, 0, 2 * sizeof(unsigned int)));
+    CK(cudaMemset(c->d_ticket, 0, 4 * sizeof(unsigned int)));
     CK(cudaMemset(c->d_flag, 0, sizeof(int)));
     CK(cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev_t0));
