@@ -264,13 +264,11 @@ cudaError_t launch_unary(int op, int dtype, const UnDesc* d_descs, int n_chunks,
                          uint32_t* d_warp_counts, cudaStream_t s);
 cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, int64_t total_tiles,
                         uint32_t* d_warp_counts, cudaStream_t s);
-// K4: sum/min/max/count of the chunks into *result in ONE launch (the last CTA folds the per-CTA partials; integer
-// min/max as unsigned keys: extended value ^ 2^63 for signed types).  partials: scratch for reduce_partials() records;
-// tickets: reduce_tickets() zeroed counters that the kernel leaves zeroed; result: device memory or device-mapped host memory.
+// K4: one AggDev partial per CTA (integer min/max as unsigned keys: extended value ^ 2^63 for signed types);
+// fold with launch_finish.
 cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, AggDev* d_cta_partials,
-                          unsigned int* tickets, AggDev* result, cudaStream_t s);
-int64_t reduce_partials(int dtype, int64_t tiles);
-int64_t reduce_tickets(int dtype, int64_t tiles);  // number of partials launch_reduce writes
+                          cudaStream_t s);
+int64_t reduce_partials(int dtype, int64_t tiles);  // number of partials launch_reduce writes
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
                             const GenDesc* d_descs, int n_chunks, int64_t total_tiles,
                             uint32_t* d_warp_counts, cudaStream_t s);

@@ -250,26 +250,24 @@ __device__ __forceinline__ unsigned int tile_int8(Packed<T>& pk, const Vec<T, 16
 }
 
 // K consecutive tiles per CTA (K = 2 for floats, 4 for integers), not persistent (measured on the read-only f64 stream:
-// 7.2 TB/s for K <= 2, 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu; capping the grid at 4096
-// CTAs -- K = 12 at 1e8 f64 rows -- cost 7 %).  One partial per CTA in CTA order, folded INSIDE the launch in two levels
-// of "last one out": CTAs form groups of kGroup; the last CTA of a group to finish folds the group's partials (thread t
-// takes partial t), and the last group to be folded has its folder fold the group results.  Which CTA does the folding
-// varies from run to run, WHAT it folds and in which order does not (fixed assignment, fixed tree): deterministic, no
-// floating-point atomics, no second launch (the separate k_finish cost 10 us of a 125 us reduction).
-constexpr int kGroup = 64;
-template <typename T>
-__global__ void __launch_bounds__(kThreads)
-k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, int K, AggDev* __restrict__ cta_partials,
-         AggDev* __restrict__ group_partials, unsigned int* __restrict__ tickets /* [0]: groups folded, [1 + g]: CTAs of group g done */,
-         AggDev* __restrict__ result) {
+// 7.2 TB/s for K <= 2, 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  One partial per CTA in
+// CTA order; launch_finish (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
+// Folding inside the launch ("last CTA out" tickets, one or two levels) was tried in round 2 and is slower: the fold code
+// costs 22-24 registers (occupancy 66 % -> 36-48 %) and every CTA waits for a fence + atomic round trip before it retires
+// (f64 sum 0.125 ms -> 0.134 ms with a 4096-CTA grid, 0.181 ms with two-level tickets; profiles/r2_reduce_notes.md).
+// Resident CTAs per SM the register allocator is asked to leave room for: the reductions are latency machines (bytes in
+// flight = resident threads x 64 B), round 1 ran the float instantiation at 7 CTAs/SM (34 registers) and the integer ones at 5.
+template <typename T> struct RedOcc { static constexpr int value = RedInfo<T>::is_float ? 6 : 5; };
+
+template <typename T, int K>
+__global__ void __launch_bounds__(kThreads, RedOcc<T>::value)
+k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, AggDev* __restrict__ cta_partials) {
     constexpr int E = 16 / (int)sizeof(T);
     constexpr int TILE = kThreads * kUnroll * E;
     constexpr bool IS_INT = !RedInfo<T>::is_float;
     using S = RedState<T>;
     __shared__ S s_state[kWarpsPerCta];
     __shared__ unsigned int s_cnt[kWarpsPerCta];
-    __shared__ AggDev s_part[kWarpsPerCta];
-    __shared__ bool s_last;   // thread 0's verdict, read by all after a barrier
 
     S st; st.init();
     [[maybe_unused]] Packed<typename std::conditional<(IS_INT && sizeof(T) <= 2), T, int8_t>::type> pk;
@@ -298,10 +296,10 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, i
             Vec<T, E> x[kUnroll];
 #pragma unroll
             for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
-            MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
-            if (vi) mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
-            if constexpr (!IS_INT) {
-                if (vi) {
+            if (vi) {
+                MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
+                mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
+                if constexpr (!IS_INT) {
 #pragma unroll
                     for (int j = 0; j < kUnroll; j++) {
                         const uint32_t m = mask_get<E, kUnroll>(rv, j);
@@ -309,24 +307,24 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, i
                         for (int e = 0; e < E; e++) st.add(x[j].e[e], (m >> e) & 1u);
                         cnt += __popc(m);
                     }
-                } else {
+                } else if constexpr (sizeof(T) == 8) cnt += tile_int64<T, true>(st, x, rv);
+                else if constexpr (sizeof(T) == 4) cnt += tile_int32<T, true>(st, x, rv);
+                else if constexpr (sizeof(T) == 2) cnt += tile_int16<T, true>(pk, x, rv);
+                else cnt += tile_int8<T, true>(pk, x, rv);
+            } else {
+                MaskRaw<E, kUnroll> none{};   // not read by the HAS_V = false instantiations
+                if constexpr (!IS_INT) {
 #pragma unroll
                     for (int j = 0; j < kUnroll; j++)
 #pragma unroll
                         for (int e = 0; e < E; e++) st.add_all_valid(x[j].e[e]);
                     cnt += kUnroll * E;
-                }
-            } else if constexpr (sizeof(T) == 8) {
-                cnt += vi ? tile_int64<T, true>(st, x, rv) : tile_int64<T, false>(st, x, rv);
-            } else if constexpr (sizeof(T) == 4) {
-                cnt += vi ? tile_int32<T, true>(st, x, rv) : tile_int32<T, false>(st, x, rv);
-            } else if constexpr (sizeof(T) == 2) {
-                cnt += vi ? tile_int16<T, true>(pk, x, rv) : tile_int16<T, false>(pk, x, rv);
-                pk.flush(st);
-            } else {
-                cnt += vi ? tile_int8<T, true>(pk, x, rv) : tile_int8<T, false>(pk, x, rv);
-                pk.flush(st);
+                } else if constexpr (sizeof(T) == 8) cnt += tile_int64<T, false>(st, x, none);
+                else if constexpr (sizeof(T) == 4) cnt += tile_int32<T, false>(st, x, none);
+                else if constexpr (sizeof(T) == 2) cnt += tile_int16<T, false>(pk, x, none);
+                else cnt += tile_int8<T, false>(pk, x, none);
             }
+            if constexpr (IS_INT && sizeof(T) <= 2) pk.flush(st);
         } else {
 #pragma unroll 1
             for (int j = 0; j < kUnroll; j++) {
@@ -354,117 +352,39 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, i
 #pragma unroll
         for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_state[w]); total += s_cnt[w]; }
         t.to_dev(&cta_partials[blockIdx.x], total);
-        __threadfence();
-        const unsigned int g = blockIdx.x / kGroup;
-        const unsigned int in_group = min((unsigned int)kGroup, gridDim.x - g * kGroup);
-        s_last = atomicAdd(&tickets[1 + g], 1u) == in_group - 1;
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // ---- last CTA of its group: fold the group's partials (one per thread, fixed tree) ----
-    __threadfence();
-    auto merge = [](AggDev& a, const AggDev& b) {
-        if constexpr (!IS_INT)
-            a.sum_bits = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a.sum_bits), __longlong_as_double((long long)b.sum_bits)));
-        else a.sum_bits += b.sum_bits;
-        a.min_bits = b.min_bits < a.min_bits ? b.min_bits : a.min_bits;
-        a.max_bits = b.max_bits > a.max_bits ? b.max_bits : a.max_bits;
-        a.count += b.count;
-    };
-    auto load = [](const AggDev* p) {
-        AggDev r;
-        r.sum_bits = __ldcg(&p->sum_bits); r.min_bits = __ldcg(&p->min_bits); r.max_bits = __ldcg(&p->max_bits); r.count = __ldcg(&p->count);
-        return r;
-    };
-    auto block_fold = [&](AggDev acc) {   // every thread's acc -> one record (valid in thread 0)
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            AggDev r;
-            r.sum_bits = __shfl_xor_sync(0xffffffffu, acc.sum_bits, o); r.min_bits = __shfl_xor_sync(0xffffffffu, acc.min_bits, o);
-            r.max_bits = __shfl_xor_sync(0xffffffffu, acc.max_bits, o); r.count = __shfl_xor_sync(0xffffffffu, acc.count, o);
-            merge(acc, r);
-        }
-        __syncthreads();
-        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = acc;
-        __syncthreads();
-        AggDev fin = s_part[0];
-        for (int w = 1; w < kWarpsPerCta; w++) merge(fin, s_part[w]);
-        return fin;
-    };
-    const AggDev ident{0ull, ~0ull, 0ull, 0ull};
-    const unsigned int g = blockIdx.x / kGroup;
-    const unsigned int n_groups = (gridDim.x + kGroup - 1) / kGroup;
-    {
-        const unsigned int i = g * kGroup + threadIdx.x;
-        AggDev acc = (threadIdx.x < kGroup && i < gridDim.x) ? load(&cta_partials[i]) : ident;
-        acc = block_fold(acc);
-        if (threadIdx.x == 0) {
-            group_partials[g] = acc;
-            tickets[1 + g] = 0;   // ready for the next launch on this stream
-            __threadfence();
-            s_last = atomicAdd(&tickets[0], 1u) == n_groups - 1;
-        }
-    }
-    __syncthreads();
-    if (!s_last) return;
-    // ---- the folder of the last group: fold the group results (thread t takes t, t + 256, ...) ----
-    __threadfence();
-    AggDev acc = ident;
-    for (unsigned int i = threadIdx.x; i < n_groups; i += kThreads) merge(acc, load(&group_partials[i]));
-    acc = block_fold(acc);
-    if (threadIdx.x == 0) {
-        *result = acc;
-        __threadfence_system();   // result may be device-mapped host memory
-        tickets[0] = 0;
     }
 }
 
 constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 2;
 static int tiles_per_cta(int dtype) { return dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt; }
-// Scratch records launch_reduce needs for `tiles` tiles: one per CTA plus one per group of CTAs.
-int64_t reduce_partials(int dtype, int64_t tiles) {
+int64_t reduce_partials(int dtype, int64_t tiles) {   // partials launch_reduce writes
     const int k = tiles_per_cta(dtype);
-    const int64_t ctas = (tiles + k - 1) / k;
-    return ctas + (ctas + kGroup - 1) / kGroup;
-}
-int64_t reduce_tickets(int dtype, int64_t tiles) {   // zeroed counters launch_reduce needs (it leaves them zeroed)
-    const int k = tiles_per_cta(dtype);
-    const int64_t ctas = (tiles + k - 1) / k;
-    return 1 + (ctas + kGroup - 1) / kGroup;
-}
-
-// The identity aggregate for an empty input (no launch of k_reduce happens then).
-__global__ void k_reduce_empty(AggDev* result) {
-    result->sum_bits = 0; result->min_bits = ~0ull; result->max_bits = 0; result->count = 0;
-    __threadfence_system();
+    return (tiles + k - 1) / k;
 }
 
 template <typename T>
-static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned int* tickets, AggDev* result, cudaStream_t s) {
-    const int K = tiles_per_cta(RedInfo<T>::is_float ? T_F64 : T_I64);
-    const unsigned grid = (unsigned)((tiles + K - 1) / K);
-    k_reduce<T><<<grid, kThreads, 0, s>>>(d, n, tiles, K, partials, partials + grid, tickets, result);
+static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+    constexpr int K = RedInfo<T>::is_float ? kReduceTilesFloat : kReduceTilesInt;
+    k_reduce<T, K><<<(unsigned)((tiles + K - 1) / K), kThreads, 0, s>>>(d, n, tiles, partials);
     return cudaGetLastError();
 }
 
-// sum/min/max/count of the chunks described by d into *result (device memory or device-mapped host memory): ONE launch.
-// partials: scratch for reduce_partials(dtype, tiles) records; tickets: reduce_tickets(dtype, tiles) zeroed counters that
-// the kernel leaves zeroed.
-cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, unsigned int* tickets, AggDev* result,
-                          cudaStream_t s) {
-    if (tiles <= 0) { k_reduce_empty<<<1, 1, 0, s>>>(result); return cudaGetLastError(); }
+// Per-CTA partials of the chunks described by d (k_finish folds them; with tiles == 0 nothing is launched and
+// k_finish produces the identity).
+cudaError_t launch_reduce(int dtype, const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {
+    if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
     switch (dtype) {
-        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, tickets, result, s);
-        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, tickets, result, s);
-        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, tickets, result, s);
-        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, tickets, result, s);
-        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, tickets, result, s);
-        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, tickets, result, s);
-        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, tickets, result, s);
-        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, tickets, result, s);
-        case T_F32: return launch_one<float>(d, n, tiles, partials, tickets, result, s);
-        case T_F64: return launch_one<double>(d, n, tiles, partials, tickets, result, s);
+        case T_I8: return launch_one<int8_t>(d, n, tiles, partials, s);
+        case T_I16: return launch_one<int16_t>(d, n, tiles, partials, s);
+        case T_I32: return launch_one<int32_t>(d, n, tiles, partials, s);
+        case T_I64: return launch_one<int64_t>(d, n, tiles, partials, s);
+        case T_U8: return launch_one<uint8_t>(d, n, tiles, partials, s);
+        case T_U16: return launch_one<uint16_t>(d, n, tiles, partials, s);
+        case T_U32: return launch_one<uint32_t>(d, n, tiles, partials, s);
+        case T_U64: return launch_one<uint64_t>(d, n, tiles, partials, s);
+        case T_F32: return launch_one<float>(d, n, tiles, partials, s);
+        case T_F64: return launch_one<double>(d, n, tiles, partials, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -205,11 +205,10 @@ struct bdf_ctx {
     unsigned long long* h_sort_agree = nullptr;   // pinned: OR and AND of the sort keys of one criterion
     int64_t last_sort_passes = 0;
     // device scratch
-    AggDev* d_partials = nullptr;       // per-CTA and per-group partials of k_reduce (compute stream only)
-    unsigned int* d_red_tickets = nullptr;  // its "last one out" counters (zeroed; every launch leaves them zeroed)
+    AggDev* d_partials = nullptr;       // per-CTA partials of k_reduce (compute stream only)
     size_t red_part_cap = 0;
     AggDev* d_stage2 = nullptr;         // k_finish staging for the k_reduce path
-    unsigned int* d_ticket = nullptr;   // [1]: k_finish of the fused aggregates (finish stream), [2]: k_reduce (compute stream)
+    unsigned int* d_ticket = nullptr;   // k_finish tickets: [0] reduce path (compute stream), [1] fused aggregates (finish stream)
     AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
     int fut_next = 0;                   // ring cursor over the future half of h_agg
@@ -464,21 +463,19 @@ static int reduce_range(bdf_ctx* c, const bdf_col* col, int64_t begin, int64_t e
     }
     RedDesc* dd = (RedDesc*)dp;
     CK(desc_upload(c, dd, hd, (size_t)n * sizeof(RedDesc)));
-    const size_t need = (size_t)reduce_partials(col->dtype, tiles);
-    if (need > c->red_part_cap) {  // grow the partials / ticket scratch (rare): drain its users first
+    if ((size_t)tiles > c->red_part_cap) {  // grow the per-CTA partials buffer (rare): drain its users first
         CK(cudaStreamSynchronize(c->s_compute));
         if (c->d_partials) CK(cudaFree(c->d_partials));
-        if (c->d_red_tickets) CK(cudaFree(c->d_red_tickets));
-        c->d_partials = nullptr; c->d_red_tickets = nullptr; c->red_part_cap = 0;
-        const size_t cap = std::max<size_t>(need * 2, 65536);
+        c->d_partials = nullptr; c->red_part_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)tiles * 2, 65536);
         CK(cudaMalloc((void**)&c->d_partials, cap * sizeof(AggDev)));
-        CK(cudaMalloc((void**)&c->d_red_tickets, (cap / 32 + 2) * sizeof(unsigned int)));   // >= reduce_tickets() for any launch the scratch fits
-        CK(cudaMemset(c->d_red_tickets, 0, (cap / 32 + 2) * sizeof(unsigned int)));
         c->red_part_cap = cap;
     }
     {
-        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // one launch: the last CTA folds the partials
-        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->d_red_tickets, result, c->s_compute));
+        LaunchTimer t(c, BDF_K_REDUCE, col->dtype, rows, reduce_bytes(col, begin, end));  // k_reduce + k_finish
+        CK(launch_reduce(col->dtype, dd, (int)n, tiles, c->d_partials, c->s_compute));
+        c->launches++;
+        CK(launch_finish(dtype_is_float(col->dtype), c->d_partials, reduce_partials(col->dtype, tiles), c->sm_count, c->d_stage2, c->d_ticket, result, c->s_compute));
     }
     return BDF_OK;
 }
@@ -1730,7 +1727,6 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_sort_agree) cudaFreeHost(c->h_sort_agree);
     if (c->d_partials) cudaFree(c->d_partials);
-    if (c->d_red_tickets) cudaFree(c->d_red_tickets);
     if (c->d_stage2) cudaFree(c->d_stage2);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
