@@ -114,6 +114,15 @@ typedef struct bdf_future bdf_future; /* an aggregate whose kernels are enqueued
 int          bdf_abi_version(void);
 const char*  bdf_last_error(void);
 int          bdf_init(int device, bdf_ctx** out);   /* one context per GPU (one process per GPU) */
+/* ONE context over n_gpus GPUs of the box (0 = all visible; devices == NULL: 0..n-1): what a single Rust process binds.
+ * Every entry below accepts it: the rows of a call are cut into one contiguous range per GPU (the axis the reference's
+ * rayon par_iter parallelises, src/functions/scalar.rs:28-31,99-102 -- cuts inside a chunk fall on 64-row boundaries,
+ * so a piece is a zero-copy Arrow slice), every GPU moves and computes its pieces over its own PCIe link, and aggregates
+ * are combined by the grouped ncclAllReduce (ncclCommInitAll).  Results, chunk structure, null counts and errors are
+ * those of the one-GPU context.  Not offered on a multi-GPU context: sort / take / filter (rows change chunks) and the
+ * IPC readers (BDF_UNSUPPORTED). */
+int          bdf_init_multi(int n_gpus, const int* devices, bdf_ctx** out);
+int          bdf_fleet_size(bdf_ctx* ctx);           /* GPUs behind the context (1 for bdf_init) */
 void         bdf_destroy(bdf_ctx* ctx);
 int          bdf_synchronize(bdf_ctx* ctx);
 int          bdf_device_info(bdf_ctx* ctx, int32_t* sm_count, int32_t* cc_major, int32_t* cc_minor, int64_t* hbm_bytes);

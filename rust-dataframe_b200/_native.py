@@ -95,6 +95,8 @@ def lib() -> C.CDLL:
         "bdf_abi_version": ([], C.c_int),
         "bdf_last_error": ([], C.c_char_p),
         "bdf_init": ([C.c_int, P(vp)], C.c_int),
+        "bdf_init_multi": ([C.c_int, P(C.c_int), P(vp)], C.c_int),
+        "bdf_fleet_size": ([vp], C.c_int),
         "bdf_destroy": ([vp], None),
         "bdf_synchronize": ([vp], C.c_int),
         "bdf_device_info": ([vp, P(i32), P(i32), P(i32), P(i64)], C.c_int),
@@ -176,7 +178,7 @@ def lib() -> C.CDLL:
 
 
 EXPORTED_SYMBOLS = [
-    "bdf_abi_version", "bdf_last_error", "bdf_init", "bdf_destroy", "bdf_synchronize", "bdf_device_info",
+    "bdf_abi_version", "bdf_last_error", "bdf_init", "bdf_init_multi", "bdf_fleet_size", "bdf_destroy", "bdf_synchronize", "bdf_device_info",
     "bdf_comm_unique_id", "bdf_comm_attach", "bdf_comm_detach", "bdf_comm_info", "bdf_comm_collective", "bdf_comm_barrier",
     "bdf_comm_all_reduce_f64", "bdf_aggregate_all_many_dev", "bdf_aggregate_all_many_dev_async", "bdf_future_count",
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
@@ -255,6 +257,22 @@ class Context:
         raise_for_status(lib().bdf_init(int(device), C.byref(h)))
         self.handle = h
         self.device = int(device)
+
+    @classmethod
+    def multi(cls, n_gpus: int = 0, devices: Optional[Sequence[int]] = None) -> "Context":
+        """ONE context over several GPUs of the box (bdf_init_multi; 0 = all visible): the library shards every call by
+        row range, each GPU works over its own PCIe link, aggregates are combined by the grouped ncclAllReduce."""
+        self = cls.__new__(cls)
+        h = C.c_void_p()
+        devs = (C.c_int * len(devices))(*devices) if devices else None
+        raise_for_status(lib().bdf_init_multi(int(n_gpus if not devices else len(devices)), devs, C.byref(h)))
+        self.handle = h
+        self.device = int(devices[0]) if devices else 0
+        return self
+
+    @property
+    def n_gpus(self) -> int:
+        return int(lib().bdf_fleet_size(self.handle))
 
     def close(self):
         if getattr(self, "handle", None):

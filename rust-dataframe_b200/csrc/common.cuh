@@ -137,6 +137,17 @@ __device__ __forceinline__ void mask_issue(MaskRaw<E, U>& r, const uint32_t* __r
         r.hi[j] = two ? __ldg(p + j * stride_words + 1) : 0u;
     }
 }
+// The same with the word pointer and the shift already known (a loop over consecutive tiles advances the pointer by a constant).
+template <int E, int U>
+__device__ __forceinline__ void mask_issue_at(MaskRaw<E, U>& r, const uint32_t* __restrict__ p, int sh, int stride_words) {
+    const bool two = sh + E > 32;
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        r.sh[j] = sh;
+        r.lo[j] = __ldg(p + j * stride_words);
+        r.hi[j] = two ? __ldg(p + j * stride_words + 1) : 0u;
+    }
+}
 template <int E, int U>
 __device__ __forceinline__ uint32_t mask_get(const MaskRaw<E, U>& r, int j) {
     const uint32_t x = __funnelshift_r(r.lo[j], r.hi[j], r.sh[j]);

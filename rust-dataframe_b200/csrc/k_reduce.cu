@@ -249,7 +249,8 @@ __device__ __forceinline__ unsigned int tile_int8(Packed<T>& pk, const Vec<T, 16
     return cnt;
 }
 
-// K consecutive tiles per CTA (K = 2 for floats, 4 for integers), not persistent (measured on the read-only f64 stream:
+// K consecutive tiles per CTA (K = 2 for floats; 8 for integers, whose three-value block reduction costs ~200
+// instructions per thread and has to be amortised), not persistent (measured on the read-only f64 stream:
 // 7.2 TB/s for K <= 2, 6.95 TB/s for grid-stride persistent variants, benchmarks/tune_stream.cu).  One partial per CTA in
 // CTA order; launch_finish (k_finish, k_binary.cu) folds the partials with a fixed grid and assignment => deterministic.
 // Folding inside the launch ("last CTA out" tickets, one or two levels) was tried in round 2 and is slower: the fold code
@@ -273,32 +274,33 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
     [[maybe_unused]] Packed<typename std::conditional<(IS_INT && sizeof(T) <= 2), T, int8_t>::type> pk;
     if constexpr (IS_INT && sizeof(T) <= 2) pk.init();
     unsigned int cnt = 0;
-    int c = -1;
-    int64_t c_tile0 = 0, c_tile_end = -1, len = 0, off = 0;
-    const T* __restrict__ pi = nullptr;
-    const uint32_t* __restrict__ vi = nullptr;
 
+    // This CTA's tiles [tile, tile_end) are walked chunk by chunk; inside a chunk the full tiles are a pointer-bumping loop
+    // (no 64-bit index arithmetic, no chunk lookup per tile -- that overhead was a fifth of the instructions of the
+    // integer instantiations), then at most one partial tile at the end of the chunk.
+    int64_t tile = (int64_t)blockIdx.x * K;
+    const int64_t tile_end = min(tile + K, total_tiles);
 #pragma unroll 1
-    for (int kk = 0; kk < K; kk++) {
-        const int64_t tile = (int64_t)blockIdx.x * K + kk;
-        if (tile >= total_tiles) break;
-        if (tile >= c_tile_end) {  // first tile, or moved into the next chunk
-            c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
-            pi = (const T*)descs[c].in;
-            vi = descs[c].vin;
-            len = descs[c].len;
-            off = descs[c].off;
-            c_tile0 = descs[c].tile0;
-            c_tile_end = c_tile0 + (len + TILE - 1) / TILE;
-        }
-        const int64_t base = (tile - c_tile0) * TILE;
-        if (base + TILE <= len) {
+    while (tile < tile_end) {
+        const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+        const T* __restrict__ pi = (const T*)descs[c].in;
+        const uint32_t* __restrict__ vi = descs[c].vin;
+        const int64_t len = descs[c].len, off = descs[c].off, c_tile0 = descs[c].tile0;
+        const int64_t run_end = min(tile_end, c_tile0 + (len + TILE - 1) / TILE);   // this CTA's tiles inside chunk c
+        const int n_full = (int)max((int64_t)0, min(run_end, c_tile0 + len / TILE) - tile);
+        const int64_t base0 = (tile - c_tile0) * TILE;
+        const T* __restrict__ p = pi + base0 + (int64_t)threadIdx.x * E;
+        const int64_t bit0 = off + base0 + (int64_t)threadIdx.x * E;
+        const uint32_t* __restrict__ vp = vi ? vi + (bit0 >> 5) : nullptr;
+        const int sh = (int)(bit0 & 31);   // TILE is a multiple of 32 bits: the shift is the same for every tile of the run
+#pragma unroll 1
+        for (int t = 0; t < n_full; t++) {
             Vec<T, E> x[kUnroll];
 #pragma unroll
-            for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
+            for (int j = 0; j < kUnroll; j++) x[j].load(p + (int64_t)j * kThreads * E);
             if (vi) {
                 MaskRaw<E, kUnroll> rv;  // validity words of all steps in one batch (see common.cuh)
-                mask_issue<E, kUnroll>(rv, vi, off + base + (int64_t)threadIdx.x * E, (int64_t)kThreads * E);
+                mask_issue_at<E, kUnroll>(rv, vp, sh, kThreads * E / 32);
                 if constexpr (!IS_INT) {
 #pragma unroll
                     for (int j = 0; j < kUnroll; j++) {
@@ -311,6 +313,7 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
                 else if constexpr (sizeof(T) == 4) cnt += tile_int32<T, true>(st, x, rv);
                 else if constexpr (sizeof(T) == 2) cnt += tile_int16<T, true>(pk, x, rv);
                 else cnt += tile_int8<T, true>(pk, x, rv);
+                vp += TILE / 32;
             } else {
                 MaskRaw<E, kUnroll> none{};   // not read by the HAS_V = false instantiations
                 if constexpr (!IS_INT) {
@@ -325,7 +328,11 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
                 else cnt += tile_int8<T, false>(pk, x, none);
             }
             if constexpr (IS_INT && sizeof(T) <= 2) pk.flush(st);
-        } else {
+            p += TILE;
+        }
+        tile += n_full;
+        if (tile < run_end) {   // the partial last tile of the chunk
+            const int64_t base = (tile - c_tile0) * TILE;
 #pragma unroll 1
             for (int j = 0; j < kUnroll; j++) {
                 const int64_t e0 = base + (int64_t)(j * kThreads + threadIdx.x) * E;
@@ -337,6 +344,7 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
                     if ((in_range >> e) & 1u) st.add(pi[e0 + e], (m >> e) & 1u);
                 cnt += __popc(m);
             }
+            tile++;
         }
     }
     if constexpr (IS_INT && sizeof(T) <= 2) pk.fold_into(st);
@@ -355,7 +363,7 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
     }
 }
 
-constexpr int kReduceTilesInt = 4, kReduceTilesFloat = 2;
+constexpr int kReduceTilesInt = 8, kReduceTilesFloat = 2;
 static int tiles_per_cta(int dtype) { return dtype_is_float(dtype) ? kReduceTilesFloat : kReduceTilesInt; }
 int64_t reduce_partials(int dtype, int64_t tiles) {   // partials launch_reduce writes
     const int k = tiles_per_cta(dtype);
