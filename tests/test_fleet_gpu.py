@@ -150,7 +150,8 @@ def test_device_resident_chain_and_fused_entries(rdf, oracle, fleet):
     assert wa["count"] == sum(c.length - c.null_count for c in og)
     m = ca.gt(cb)
     _, om = oracle.compare(oracle.GT, fa[0], fb[0])
-    assert m.download()[0].to_pylist() == om.to_pylist()
+    gm = m.download()[0]
+    assert np.array_equal(gm.valid_mask(), om.valid_mask()) and np.array_equal(gm.value_bits()[om.valid_mask()], om.value_bits()[om.valid_mask()])
     with pytest.raises(rdf.UnsupportedType):
         ca.filter(m)
     assert int(ci.sum()) == int(many[0]["sum"]) and ci.count() == many[0]["count"]
