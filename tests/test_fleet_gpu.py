@@ -146,7 +146,7 @@ def test_device_resident_chain_and_fused_entries(rdf, oracle, fleet):
     assert int(r[0]["sum"]) == int(many[0]["sum"]) and int(r[1]["min"]) == int(many[2]["min"])
     w, wa = rdf.eval_expr_agg([ca, cb], [(rdf.native.ADD, 0, 1), (rdf.native.MUL, 2, 0)])
     for i, (x, y) in enumerate(zip(w.download(), og)):
-        assert_same_array(x, y, what=f"fused expression chunk {i}")
+        assert_same_array(x, y, what=f"fused expression chunk {i}", check_payload=False)   # null slots of a fused chain carry payload 0
     assert wa["count"] == sum(c.length - c.null_count for c in og)
     m = ca.gt(cb)
     _, om = oracle.compare(oracle.GT, fa[0], fb[0])
