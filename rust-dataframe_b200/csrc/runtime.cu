@@ -18,6 +18,7 @@
 #include <deque>
 #include <functional>
 #include <sched.h>
+#include <sys/mman.h>
 #include <string>
 #include <thread>
 #include <vector>
@@ -153,10 +154,21 @@ class CopyPool {
         for (auto& t : th_) t.join();
     }
     int workers() const { return (int)th_.size(); }
-    void copy(char* dst, const char* src, size_t n) {
+    // populate: the destination may be memory nobody has touched yet (a fresh Arrow MutableBuffer): every job first asks
+    // the kernel for its pages in ONE call (MADV_POPULATE_WRITE) instead of taking a fault per 4 KiB page inside the
+    // copy -- 18 -> 31 GB/s into fresh memory with 8 threads (benchmarks/staging_probe2.cu); a no-op for resident pages.
+    static void job_copy(char* dst, const char* src, size_t n, bool populate) {
+        if (populate) {
+            const uintptr_t a = ((uintptr_t)dst + 4095) & ~(uintptr_t)4095, b = ((uintptr_t)dst + n) & ~(uintptr_t)4095;
+            if (b > a) madvise((void*)a, b - a, 23 /* MADV_POPULATE_WRITE (Linux 5.14+); an error only means: fault as usual */);
+        }
+        memcpy(dst, src, n);
+    }
+    void copy(char* dst, const char* src, size_t n, bool populate = false) {
         constexpr size_t kJob = (size_t)512 << 10;
-        if (th_.empty() || n < 2 * kJob) { memcpy(dst, src, n); return; }
+        if (th_.empty() || n < 2 * kJob) { job_copy(dst, src, n, populate); return; }
         std::unique_lock<std::mutex> lk(m_);
+        populate_ = populate;
         dst_ = dst; src_ = src; n_ = n; next_ = 0; jobs_ = (n + kJob - 1) / kJob; done_ = 0;
         lk.unlock();
         cv_work_.notify_all();
@@ -164,7 +176,7 @@ class CopyPool {
         while (next_ < jobs_) {   // the caller works too
             const size_t j = next_++;
             lk.unlock();
-            memcpy(dst + j * kJob, src + j * kJob, std::min(kJob, n - j * kJob));
+            job_copy(dst + j * kJob, src + j * kJob, std::min(kJob, n - j * kJob), populate);
             lk.lock();
             done_++;
         }
@@ -181,8 +193,9 @@ class CopyPool {
             if (stop_) return;
             const size_t j = next_++;
             char* d = dst_; const char* s = src_; const size_t n = n_;
+            const bool pop = populate_;
             lk.unlock();
-            memcpy(d + j * kJob, s + j * kJob, std::min(kJob, n - j * kJob));
+            job_copy(d + j * kJob, s + j * kJob, std::min(kJob, n - j * kJob), pop);
             lk.lock();
             if (++done_ == jobs_) cv_done_.notify_all();
         }
@@ -192,7 +205,7 @@ class CopyPool {
     std::vector<std::thread> th_;
     char* dst_ = nullptr; const char* src_ = nullptr;
     size_t n_ = 0, next_ = 0, jobs_ = 0, done_ = 0;
-    bool stop_ = false;
+    bool stop_ = false, populate_ = false;
 };
 
 struct bdf_ctx {
@@ -577,7 +590,7 @@ static cudaError_t d2h_staged(bdf_ctx* c, const std::vector<bdf_col::StagedCopy>
         Pending p = pending.front();
         pending.pop_front();
         cudaError_t e = cudaEventSynchronize(p.sl->ev);
-        if (e == cudaSuccess) c->pool->copy(p.dst, p.sl->p, p.n);
+        if (e == cudaSuccess) c->pool->copy(p.dst, p.sl->p, p.n, true);
         p.sl->busy = false;
         return e;
     };
