@@ -16,6 +16,7 @@
 #include <mutex>
 #include <new>
 #include <deque>
+#include <limits>
 #include <functional>
 #include <sched.h>
 #include <sys/mman.h>
@@ -1192,6 +1193,10 @@ static int avg_dev(bdf_ctx* c, bdf_col* col, double* out, int32_t* is_some) {
             else if (dtype_is_signed_int(dtype)) s = (double)(int64_t)a.sum_bits;
             else s = (double)a.sum_bits;
             const double mch = len ? s / (double)len : 0.0;
+            // A rank of a communicator sees only SOME chunks of the column: an empty local chunk contributes nothing there
+            // (the reference's 0/0 = NaN when the column's FIRST chunk has no valid slot is a statement about the whole
+            // column's chunk order; the one-GPU context and the multi-GPU context reproduce it, see fleet_avg_dev).
+            if (len == 0 && is_global(c)) continue;
             count += len;
             mean = mean + ((mch - mean) * (double)len) / (double)count;
         }
@@ -2108,6 +2113,8 @@ static int fleet_aggregate_all_blocking(bdf_ctx* c, int32_t n_cols, const bdf_co
     return BDF_OK;
 }
 
+static int fleet_chunk_info(bdf_ctx* c, const bdf_col* col, int64_t chunk, int64_t* len, int64_t* null_count, int32_t* has_validity);
+
 static int fleet_avg_dev(bdf_ctx* c, const bdf_col* col, double* out, int32_t* is_some) {
     Fleet* f = c->fleet;
     if (!is_fleet_col(col)) return fail(BDF_INVALID, "a column of a one-GPU context was passed to a multi-GPU context");
@@ -2115,6 +2122,12 @@ static int fleet_avg_dev(bdf_ctx* c, const bdf_col* col, double* out, int32_t* i
     std::vector<int32_t> some(f->kids.size(), 0);
     TRY(fleet_run(f, [&](int k) { return bdf_avg_dev(f->kids[k], col->fparts[k], &v[k], &some[k]); }));
     *out = v[0]; *is_some = some[0];
+    // aggregate.rs:57-60: `mean + (m - mean) * len / count` is 0/0 when the first chunk has no valid slot, and NaN sticks
+    if (!col->fmap.empty()) {
+        int64_t len = 0, nulls = 0; int32_t hv = 0;
+        TRY(fleet_chunk_info(c, col, 0, &len, &nulls, &hv));
+        if (len - (hv ? nulls : 0) == 0) *out = std::numeric_limits<double>::quiet_NaN();
+    }
     return BDF_OK;
 }
 
