@@ -310,22 +310,37 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
 
     # cost of the combine alone: a blocking 4-in-1 aggregate of a tiny column with the collective on and off
     combine_us = None
+    primary_mode = ctx.comm_get_combine() if world > 1 else None
     if world > 1:
         tiny = rdf.Column.generate(rdf.I64, [1024], 3, seed=SEED, col_id=9, row0=rank * 1024, ctx=ctx)
         reps = 200
-        t = {}
-        for mode in (True, False):
-            ctx.comm_collective(mode)
+
+        def blocking_us(collective: bool):
+            ctx.comm_collective(collective)
             for _ in range(20):
                 tiny.aggregate_all_async().result()
-            ctx.comm_barrier() if mode else ctx.synchronize()
+            ctx.comm_barrier() if collective else ctx.synchronize()
             t0 = time.perf_counter()
             for _ in range(reps):
                 tiny.aggregate_all_async().result()
-            t[mode] = (time.perf_counter() - t0) / reps * 1e6
+            return (time.perf_counter() - t0) / reps * 1e6
+
+        local_us = blocking_us(False)
+        combine_us = {"blocking_aggregate_local_us": local_us}
+        modes = [primary_mode]
+        try:   # the other transport, if the box offers it
+            ctx.comm_set_combine(primary_mode != "peer-memory")
+            modes.append(ctx.comm_get_combine())
+            ctx.comm_set_combine(primary_mode == "peer-memory")
+        except rdf.ArrowError:
+            pass
+        for m in modes:
+            ctx.comm_set_combine(m == "peer-memory")
+            us = blocking_us(True)
+            combine_us[m] = {"blocking_aggregate_collective_us": us, "combine_us": us - local_us}
+        ctx.comm_set_combine(primary_mode == "peer-memory")
         ctx.comm_collective(True)
         tiny.free()
-        combine_us = {"blocking_aggregate_collective_us": t[True], "blocking_aggregate_local_us": t[False], "combine_us": t[True] - t[False]}
 
     sampler = ClockSampler(local)
     sampler.start()
@@ -354,6 +369,18 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
     sampler.join(timeout=1)
     clocks = sampler.summary(t_wall0, t_wall2)
     clocks["window"] = f"timed region + {extra} untimed steps of the same load"
+
+    # ---- the same series with the other transport of the combine (N > 1) ----
+    other_transport = None
+    if world > 1 and combine_us is not None and len(combine_us) > 2:
+        alt = [m for m in combine_us if m not in ("blocking_aggregate_local_us", primary_mode)][0]
+        ctx.comm_set_combine(alt == "peer-memory")
+        for _ in range(3):
+            loop.step()
+        loop.drain()
+        ms_alt = timed_loop(ctx, loop, args.steps, world)
+        ctx.comm_set_combine(primary_mode == "peer-memory")
+        other_transport = {"combine": alt, "value": rows_global * args.steps / (ms_alt * 1e-3), "ms_per_step": ms_alt / args.steps}
 
     # ---- the other scaling series (N > 1): same loop over the other sharding ----
     other = None
@@ -409,8 +436,9 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
                    "l2": "inputs (2.4 GB working set per step at 1e8 rows) are larger than the 126 MB L2; no flush needed",
                    "fused": "sum(c) is computed by the add kernel while c is written (c is still materialised): 24 B/row",
                    "host_pipelining": f"{depth} step(s) in flight: step i's scalar is read after step i+{depth} is enqueued",
-                   "collective": "none" if world == 1 else "ONE grouped ncclAllReduce of the partial (sum,count,rows,min,max) per step, enqueued by libb200df on the stream that produced it; no collective is issued by bench.py inside the timed loop",
-                   "collectives_in_timed_region": int(collectives), "nccl_version": ctx.comm_info()["nccl_version"], "combine": combine_us},
+                   "collective": "none" if world == 1 else "ONE combine of the partial (sum,count,rows,min,max) per step, enqueued by libb200df on the stream that produced it -- NVLink peer-memory mailboxes (k_p2p_combine) or the grouped ncclAllReduce, see combine_transport; no collective is issued by bench.py inside the timed loop",
+                   "collectives_in_timed_region": int(collectives), "nccl_version": ctx.comm_info()["nccl_version"],
+                   "combine_transport": primary_mode, "combine": combine_us, "same_series_other_transport": other_transport},
         "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         "check": {"sum": last[0], "count": last[1], "rows": last[2]},
     }

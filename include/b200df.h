@@ -146,6 +146,12 @@ int  bdf_comm_attach(bdf_ctx* ctx, const uint8_t* id, int rank, int world);
 int  bdf_comm_detach(bdf_ctx* ctx);
 int  bdf_comm_info(bdf_ctx* ctx, int32_t* rank, int32_t* world, int32_t* nccl_version, int64_t* collectives_enqueued);
 int  bdf_comm_collective(bdf_ctx* ctx, int on);
+/* How the partial aggregates travel: 0 = the grouped ncclAllReduce, 1 = NVLink peer-memory mailboxes (one small kernel of
+ * the library stores every rank's record into every peer and folds in rank order; needs peer access between all GPUs).
+ * Default: 1 where available, unless the environment says BDF_COMBINE=nccl.  Results are identical (integers: order
+ * independent; float sums: rank-order fold in both).  Collective: every rank switches at the same point. */
+int  bdf_comm_set_combine(bdf_ctx* ctx, int mode);
+int  bdf_comm_get_combine(bdf_ctx* ctx);
 int  bdf_comm_barrier(bdf_ctx* ctx);    /* drains this context's streams, then returns once every rank has arrived */
 int  bdf_comm_all_reduce_f64(bdf_ctx* ctx, int op /* BDF_SUM | BDF_MIN | BDF_MAX */, int64_t n, double* inout); /* blocking */
 

@@ -106,6 +106,8 @@ def lib() -> C.CDLL:
         "bdf_comm_info": ([vp, P(i32), P(i32), P(i32), P(i64)], C.c_int),
         "bdf_comm_collective": ([vp, C.c_int], C.c_int),
         "bdf_comm_barrier": ([vp], C.c_int),
+        "bdf_comm_set_combine": ([vp, C.c_int], C.c_int),
+        "bdf_comm_get_combine": ([vp], C.c_int),
         "bdf_comm_all_reduce_f64": ([vp, C.c_int, i64, P(C.c_double)], C.c_int),
         "bdf_aggregate_all_many_dev": ([vp, i32, P(vp), P(Agg4)], C.c_int),
         "bdf_aggregate_all_many_dev_async": ([vp, i32, P(vp), P(vp)], C.c_int),
@@ -179,7 +181,7 @@ def lib() -> C.CDLL:
 
 EXPORTED_SYMBOLS = [
     "bdf_abi_version", "bdf_last_error", "bdf_init", "bdf_init_multi", "bdf_fleet_size", "bdf_destroy", "bdf_synchronize", "bdf_device_info",
-    "bdf_comm_unique_id", "bdf_comm_attach", "bdf_comm_detach", "bdf_comm_info", "bdf_comm_collective", "bdf_comm_barrier",
+    "bdf_comm_unique_id", "bdf_comm_attach", "bdf_comm_detach", "bdf_comm_info", "bdf_comm_collective", "bdf_comm_barrier", "bdf_comm_set_combine", "bdf_comm_get_combine",
     "bdf_comm_all_reduce_f64", "bdf_aggregate_all_many_dev", "bdf_aggregate_all_many_dev_async", "bdf_future_count",
     "bdf_host_alloc", "bdf_host_free", "bdf_host_register", "bdf_host_unregister", "bdf_binary", "bdf_unary", "bdf_cast",
     "bdf_aggregate", "bdf_aggregate_all", "bdf_avg", "bdf_upload", "bdf_upload_many", "bdf_col_wait", "bdf_col_describe",
@@ -323,6 +325,13 @@ class Context:
 
     def comm_barrier(self):
         raise_for_status(lib().bdf_comm_barrier(self.handle))
+
+    def comm_set_combine(self, peer_memory: bool):
+        """True: NVLink peer-memory mailboxes (one kernel of the library); False: the grouped ncclAllReduce."""
+        raise_for_status(lib().bdf_comm_set_combine(self.handle, 1 if peer_memory else 0))
+
+    def comm_get_combine(self) -> str:
+        return "peer-memory" if lib().bdf_comm_get_combine(self.handle) else "nccl"
 
     def comm_all_reduce(self, values, op: int = SUM):
         """Blocking all-reduce of a few float64 values (timing max-over-ranks and the like)."""

@@ -46,6 +46,15 @@ cudaError_t comm_combine(Comm* c, unsigned long long float_mask, int n, const Ag
                          const unsigned int* local_panics, const unsigned int* local_chunks, AggDev* result, cudaStream_t s,
                          std::string* err);
 
+// The same combine over NVLink peer memory instead of NCCL (k_p2p_combine in comm.cu): every rank stores its record into
+// every peer's mailbox and folds what it received in rank order -- one small launch, no library call.  Needs peer access
+// between all GPUs of the communicator (NVSwitch boxes have it).  comm_enable_p2p is collective (every rank calls it).
+int comm_enable_p2p(Comm* c, std::string* err);               // process per GPU: CUDA IPC handles travel through the communicator
+int comm_enable_p2p_all(int n, Comm** comms, std::string* err);   // one process: direct peer pointers
+bool comm_has_p2p(const Comm* c);
+bool comm_uses_p2p(const Comm* c);
+int comm_set_p2p(Comm* c, bool on);   // non-zero if the mailboxes are not set up
+
 // In-place all-reduce of device memory on `s` (the DivideByZero flag: every rank must take the same exit).
 cudaError_t comm_allreduce_max_i32(Comm* c, int* d_inout, int n, cudaStream_t s, std::string* err);
 // Blocking host-side helpers (bench timing, avg merge): stage through device scratch on `s`, synchronise.

@@ -280,6 +280,14 @@ cudaError_t launch_cast(int from, int to, const UnDesc* d_descs, int n_chunks, i
 cudaError_t launch_reduce(int dtype, const RedDesc* d_descs, int n_chunks, int64_t total_tiles, AggDev* d_cta_partials,
                           cudaStream_t s);
 int64_t reduce_partials(int dtype, int64_t tiles);  // number of partials launch_reduce writes
+// Several columns of ONE dtype can share a launch: concatenate their chunk descriptors and start every column's tile
+// numbering on a multiple of reduce_tiles_per_cta(dtype) -- a CTA then never mixes columns, and column k's partials are the
+// CTA range [tile0_k / K, ceil(tile_end_k / K)).
+int reduce_tiles_per_cta(int dtype);
+// Fold up to kFinishMany partial ranges in ONE launch (grid.y = range); stage: n x sm_count records, tickets: n zeroed counters.
+constexpr int kFinishMany = 64;
+struct FinishJob { const AggDev* parts; long long n_parts; AggDev* result; int is_float; int pad; };
+cudaError_t launch_finish_many(int n, const FinishJob* jobs, int sm_count, AggDev* stage, unsigned int* tickets, cudaStream_t s);
 cudaError_t launch_generate(int dtype, int kind, double lo, double hi, uint64_t seed, uint64_t col, uint32_t null_mod,
                             const GenDesc* d_descs, int n_chunks, int64_t total_tiles,
                             uint32_t* d_warp_counts, cudaStream_t s);

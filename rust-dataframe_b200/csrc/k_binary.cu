@@ -254,6 +254,83 @@ cudaError_t launch_finish(bool is_float, const AggDev* parts, int64_t n_parts, i
     return cudaGetLastError();
 }
 
+// The same fold for several partial ranges at once (blockIdx.y = range): multi-column aggregates pay one launch, not one per column.
+struct FinishJobs { FinishJob j[kFinishMany]; };
+__global__ void __launch_bounds__(kThreads)
+k_finish_many(const FinishJobs jobs, AggDev* __restrict__ stage_all, unsigned int* __restrict__ tickets) {
+    __shared__ AggDev s_part[kThreads / 32];
+    __shared__ bool s_last;
+    const FinishJob& job = jobs.j[blockIdx.y];
+    const AggDev* __restrict__ parts = job.parts;
+    const long long n_parts = job.n_parts;
+    const bool is_float = job.is_float != 0;
+    AggDev* __restrict__ stage = stage_all + (size_t)blockIdx.y * gridDim.x;
+    unsigned int* __restrict__ ticket = tickets + blockIdx.y;
+    auto ident = [] { AggDev a; a.sum_bits = 0; a.min_bits = ~0ull; a.max_bits = 0; a.count = 0; return a; };
+    auto merge = [is_float](AggDev& a, const AggDev& b) {
+        if (is_float)
+            a.sum_bits = (unsigned long long)__double_as_longlong(__dadd_rn(__longlong_as_double((long long)a.sum_bits), __longlong_as_double((long long)b.sum_bits)));
+        else a.sum_bits += b.sum_bits;
+        a.min_bits = b.min_bits < a.min_bits ? b.min_bits : a.min_bits;
+        a.max_bits = b.max_bits > a.max_bits ? b.max_bits : a.max_bits;
+        a.count += b.count;
+    };
+    auto shfl = [](const AggDev& a, int o) {
+        AggDev r;
+        r.sum_bits = __shfl_xor_sync(0xffffffffu, a.sum_bits, o); r.min_bits = __shfl_xor_sync(0xffffffffu, a.min_bits, o);
+        r.max_bits = __shfl_xor_sync(0xffffffffu, a.max_bits, o); r.count = __shfl_xor_sync(0xffffffffu, a.count, o);
+        return r;
+    };
+    auto block_fold = [&](AggDev v) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { AggDev t = shfl(v, o); merge(v, t); }
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+        __syncthreads();
+        AggDev r = s_part[0];
+        for (int w = 1; w < kThreads / 32; w++) merge(r, s_part[w]);
+        return r;
+    };
+    AggDev acc = ident();
+    for (long long i = (long long)blockIdx.x * kThreads + threadIdx.x; i < n_parts; i += (long long)gridDim.x * kThreads) {
+        AggDev p;
+        p.sum_bits = __ldcg(&parts[i].sum_bits); p.min_bits = __ldcg(&parts[i].min_bits);
+        p.max_bits = __ldcg(&parts[i].max_bits); p.count = __ldcg(&parts[i].count);
+        merge(acc, p);
+    }
+    acc = block_fold(acc);
+    if (threadIdx.x == 0) {
+        stage[blockIdx.x] = acc;
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    AggDev fin = ident();
+    for (unsigned int i = threadIdx.x; i < gridDim.x; i += kThreads) {
+        AggDev p;
+        p.sum_bits = __ldcg(&stage[i].sum_bits); p.min_bits = __ldcg(&stage[i].min_bits);
+        p.max_bits = __ldcg(&stage[i].max_bits); p.count = __ldcg(&stage[i].count);
+        merge(fin, p);
+    }
+    fin = block_fold(fin);
+    if (threadIdx.x == 0) { *job.result = fin; __threadfence_system(); *ticket = 0; }
+}
+
+cudaError_t launch_finish_many(int n, const FinishJob* jobs, int sm_count, AggDev* stage, unsigned int* tickets, cudaStream_t s) {
+    if (n < 1 || n > kFinishMany) return cudaErrorInvalidValue;
+    FinishJobs jj;
+    long long most = 1;
+    for (int i = 0; i < n; i++) { jj.j[i] = jobs[i]; most = jobs[i].n_parts > most ? jobs[i].n_parts : most; }
+    int64_t gx = (most + 4 * kThreads - 1) / (4 * kThreads);
+    const int64_t cap = sm_count / (n < 4 ? 1 : 4) > 1 ? sm_count / (n < 4 ? 1 : 4) : 1;   // n ranges share the SMs
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    k_finish_many<<<dim3((unsigned)gx, (unsigned)n), kThreads, 0, s>>>(jj, stage, tickets);
+    return cudaGetLastError();
+}
+
 int elems_per_tile(int dtype) { return kTileBytes / dtype_width(dtype); }
 
 // Compute-heavy binaries (divide and the libm ones) keep fewer vectors in registers per thread: the extra

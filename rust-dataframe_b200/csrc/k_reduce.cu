@@ -286,7 +286,9 @@ k_reduce(const RedDesc* __restrict__ descs, int n_chunks, int64_t total_tiles, A
         const T* __restrict__ pi = (const T*)descs[c].in;
         const uint32_t* __restrict__ vi = descs[c].vin;
         const int64_t len = descs[c].len, off = descs[c].off, c_tile0 = descs[c].tile0;
-        const int64_t run_end = min(tile_end, c_tile0 + (len + TILE - 1) / TILE);   // this CTA's tiles inside chunk c
+        const int64_t chunk_end = c_tile0 + (len + TILE - 1) / TILE;
+        if (tile >= chunk_end) break;   // padding between the columns of a batched launch (columns start on CTA boundaries)
+        const int64_t run_end = min(tile_end, chunk_end);   // this CTA's tiles inside chunk c
         const int n_full = (int)max((int64_t)0, min(run_end, c_tile0 + len / TILE) - tile);
         const int64_t base0 = (tile - c_tile0) * TILE;
         const T* __restrict__ p = pi + base0 + (int64_t)threadIdx.x * E;
@@ -369,6 +371,7 @@ int64_t reduce_partials(int dtype, int64_t tiles) {   // partials launch_reduce 
     const int k = tiles_per_cta(dtype);
     return (tiles + k - 1) / k;
 }
+int reduce_tiles_per_cta(int dtype) { return tiles_per_cta(dtype); }
 
 template <typename T>
 static cudaError_t launch_one(const RedDesc* d, int n, int64_t tiles, AggDev* partials, cudaStream_t s) {

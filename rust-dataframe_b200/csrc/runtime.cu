@@ -231,6 +231,8 @@ struct bdf_ctx {
     AggDev* d_partials = nullptr;       // per-CTA partials of k_reduce (compute stream only)
     size_t red_part_cap = 0;
     AggDev* d_stage2 = nullptr;         // k_finish staging for the k_reduce path
+    AggDev* d_stage_many = nullptr;     // k_finish_many staging (kFinishMany x sm_count) and tickets, allocated on first use
+    unsigned int* d_tickets_many = nullptr;
     unsigned int* d_ticket = nullptr;   // k_finish tickets: [0] reduce path (compute stream), [1] fused aggregates (finish stream)
     AggDev* d_stage = nullptr;          // k_finish per-CTA staging, sm_count entries
     int* d_flag = nullptr;
@@ -1056,6 +1058,74 @@ static void convert_agg(int dtype, int fused, const AggDev& a, int64_t rows, bdf
     out->any_valid = a.count > 0;
 }
 
+// sum/min/max/count of several columns with as few launches as possible: the columns of one dtype share ONE k_reduce launch
+// (their chunk descriptors are concatenated, every column starting on a CTA boundary), and ONE k_finish_many folds every
+// column's partials.  BASELINE config 3 (8 x Int64) is 2 launches instead of 16 -- what matters once the rows are split
+// over 8 GPUs and a column's reduction takes 17 us.
+static int reduce_columns(bdf_ctx* c, int n_cols, bdf_col* const* cols, bdf_future* f) {
+    struct Range { int64_t cta0, ctas; };
+    std::vector<Range> range((size_t)n_cols);
+    int64_t total_ctas = 0, total_chunks = 0;
+    for (int k = 0; k < n_cols; k++) total_chunks += (int64_t)cols[k]->chunks.size();
+    void *hp = nullptr, *dp = nullptr;
+    TRY(ring_alloc(c, (size_t)total_chunks * sizeof(RedDesc), &hp, &dp));
+    RedDesc* hd = (RedDesc*)hp;
+    RedDesc* dd = (RedDesc*)dp;
+    struct Launch { int dtype; int64_t desc0, n_desc, tiles, cta0; int64_t rows, bytes; };
+    std::vector<Launch> launches;
+    std::vector<char> done((size_t)n_cols, 0);
+    int64_t di = 0;
+    for (int k0 = 0; k0 < n_cols; k0++) {
+        if (done[k0]) continue;
+        const int dtype = cols[k0]->dtype;
+        const int K = reduce_tiles_per_cta(dtype), tile = elems_per_tile(dtype);
+        Launch L{dtype, di, 0, 0, total_ctas, 0, 0};
+        int64_t tiles = 0;
+        for (int k = k0; k < n_cols; k++) {
+            if (done[k] || cols[k]->dtype != dtype) continue;
+            done[k] = 1;
+            tiles = (tiles + K - 1) / K * K;   // the column starts on a CTA boundary
+            const int64_t col_tile0 = tiles;
+            for (const DevChunk& ch : cols[k]->chunks) {
+                hd[di] = RedDesc{ch.values, ch.validity, ch.len, tiles, ch.bit_off, 0};
+                di++;
+                tiles += (ch.len + tile - 1) / tile;
+                L.rows += ch.len;
+            }
+            L.bytes += reduce_bytes(cols[k], 0, (int64_t)cols[k]->chunks.size());
+            range[k] = Range{L.cta0 + col_tile0 / K, (tiles - col_tile0 + K - 1) / K};
+        }
+        L.n_desc = di - L.desc0;
+        L.tiles = tiles;
+        total_ctas += (tiles + K - 1) / K;
+        launches.push_back(L);
+    }
+    CK(desc_upload(c, dd, hd, (size_t)total_chunks * sizeof(RedDesc)));
+    if ((size_t)total_ctas > c->red_part_cap) {
+        CK(cudaStreamSynchronize(c->s_compute));
+        if (c->d_partials) CK(cudaFree(c->d_partials));
+        c->d_partials = nullptr; c->red_part_cap = 0;
+        const size_t cap = std::max<size_t>((size_t)total_ctas * 2, 65536);
+        CK(cudaMalloc((void**)&c->d_partials, cap * sizeof(AggDev)));
+        c->red_part_cap = cap;
+    }
+    if (!c->d_stage_many) {
+        CK(cudaMalloc((void**)&c->d_stage_many, (size_t)kFinishMany * c->sm_count * sizeof(AggDev)));
+        CK(cudaMalloc((void**)&c->d_tickets_many, kFinishMany * sizeof(unsigned int)));
+        CK(cudaMemset(c->d_tickets_many, 0, kFinishMany * sizeof(unsigned int)));
+    }
+    for (const Launch& L : launches) {
+        LaunchTimer t(c, BDF_K_REDUCE, L.dtype, L.rows, L.bytes);
+        CK(launch_reduce(L.dtype, dd + L.desc0, (int)L.n_desc, L.tiles, c->d_partials + L.cta0, c->s_compute));
+    }
+    FinishJob jobs[kFinishMany];
+    for (int k = 0; k < n_cols; k++)
+        jobs[k] = FinishJob{c->d_partials + range[k].cta0, (long long)range[k].ctas, future_target(c, f, k), dtype_is_float(cols[k]->dtype) ? 1 : 0, 0};
+    c->launches++;
+    CK(launch_finish_many(n_cols, jobs, c->sm_count, c->d_stage_many, c->d_tickets_many, c->s_compute));
+    return BDF_OK;
+}
+
 // Chunks of the column that are empty or all-null: the reference's max/min .unwrap() a None there (aggregate.rs:19,29).
 static int count_panic_chunks(bdf_ctx* c, bdf_col* col, uint32_t* out) {
     TRY(ensure_null_counts(c, col));
@@ -1081,13 +1151,14 @@ static int aggregate_many_dev_async(bdf_ctx* c, int n_cols, bdf_col* const* cols
     bdf_future* f = nullptr;
     TRY(future_new(c, cols[0]->dtype, 2, 0, &f, n_cols));
     int st = BDF_OK;
-    for (int k = 0; k < n_cols && st == BDF_OK; k++) {
+    for (int k = 0; k < n_cols; k++) {
         bdf_col* col = cols[k];
         const int64_t n = (int64_t)col->chunks.size();
         f->dtypes[k] = col->dtype; f->rows[k] = col->total_len; f->panics[k] = panics[k]; f->chunks[k] = (uint32_t)n;
         wait_groups(c->s_compute, col, 0, n);
-        st = reduce_range(c, col, 0, n, future_target(c, f, k));
     }
+    if (n_cols == 1) st = reduce_range(c, cols[0], 0, (int64_t)cols[0]->chunks.size(), future_target(c, f, 0));
+    else st = reduce_columns(c, n_cols, cols, f);
     cudaError_t e = cudaSuccess;
     if (st == BDF_OK) e = future_combine(c, f, c->s_compute);
     if (st == BDF_OK && e == cudaSuccess) e = cudaEventRecord(f->ev, c->s_compute);
@@ -2334,6 +2405,8 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->h_sort_agree) cudaFreeHost(c->h_sort_agree);
     if (c->d_partials) cudaFree(c->d_partials);
     if (c->d_stage2) cudaFree(c->d_stage2);
+    if (c->d_stage_many) cudaFree(c->d_stage_many);
+    if (c->d_tickets_many) cudaFree(c->d_tickets_many);
     if (c->d_ticket) cudaFree(c->d_ticket);
     if (c->d_flag) cudaFree(c->d_flag);
     if (c->flush_buf) cudaFree(c->flush_buf);
@@ -2439,7 +2512,15 @@ int bdf_init_multi(int n_gpus, const int* devices, bdf_ctx** out) {
         std::vector<Comm*> comms((size_t)n_gpus, nullptr);
         std::string err;
         if (comm_create_all(n_gpus, devs.data(), comms.data(), &err) != 0) st = fail(BDF_NCCL, "%s", err.c_str());
-        else for (int i = 0; i < n_gpus; i++) ctx_attach_comm(f->kids[i], comms[i]);
+        else {
+            for (int i = 0; i < n_gpus; i++) ctx_attach_comm(f->kids[i], comms[i]);
+            const char* mode = getenv("BDF_COMBINE");
+            if (!(mode && strcmp(mode, "nccl") == 0)) {
+                std::string perr;
+                if (comm_enable_p2p_all(n_gpus, comms.data(), &perr) == 0) for (Comm* cm : comms) comm_set_p2p(cm, true);
+                else if (mode && strcmp(mode, "p2p") == 0) st = fail(BDF_NCCL, "BDF_COMBINE=p2p: %s", perr.c_str());
+            }
+        }
     }
     if (st == BDF_OK)
         for (int i = 0; i < n_gpus; i++) {
@@ -2527,7 +2608,30 @@ int bdf_comm_attach(bdf_ctx* c, const uint8_t* id, int rank, int world) {
     c->comm = cm;
     c->collective = true;
     c->collectives = 0;
+    // The combine itself can run over NVLink peer memory instead of NCCL (comm.cuh); every rank reads the same environment.
+    const char* mode = getenv("BDF_COMBINE");
+    if (world > 1 && !(mode && strcmp(mode, "nccl") == 0)) {
+        std::string perr;
+        if (comm_enable_p2p(cm, &perr) == 0) comm_set_p2p(cm, true);
+        else if (mode && strcmp(mode, "p2p") == 0) { comm_destroy(cm); c->comm = nullptr; return fail(BDF_NCCL, "BDF_COMBINE=p2p: %s", perr.c_str()); }
+    }
     return BDF_OK;
+}
+
+int bdf_comm_set_combine(bdf_ctx* c, int mode) {
+    if (c && c->fleet) { for (bdf_ctx* k : c->fleet->kids) TRY(bdf_comm_set_combine(k, mode)); return BDF_OK; }
+    ENTER(c);
+    if (mode != 0 && mode != 1) return fail(BDF_INVALID, "combine mode is 0 (NCCL) or 1 (peer memory)");
+    if (!c->comm) return mode == 0 ? BDF_OK : fail(BDF_UNSUPPORTED, "the context is not a rank of a communicator");
+    CK(cudaStreamSynchronize(c->s_compute));
+    CK(cudaStreamSynchronize(c->s_fin));
+    if (comm_set_p2p(c->comm, mode == 1) != 0) return fail(BDF_UNSUPPORTED, "peer-memory mailboxes are not available on this communicator");
+    return BDF_OK;
+}
+
+int bdf_comm_get_combine(bdf_ctx* c) {
+    if (c && c->fleet) return bdf_comm_get_combine(c->fleet->kids[0]);
+    return c && c->comm && comm_uses_p2p(c->comm) ? 1 : 0;
 }
 
 int bdf_comm_detach(bdf_ctx* c) {

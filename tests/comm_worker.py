@@ -199,11 +199,40 @@ def main():
                     assert int(orc.aggregate(op, orc.I64, o)[1]) == want[k][key], (k, key)
     checks += 1
 
+    # ---- 7. many collectives back to back on both streams (fused futures: finish stream; plain aggregates: compute stream),
+    #         then the other transport of the combine: same answers
+    ref_many = rdf.Column.aggregate_all_many([cia, cib])
+    futs = []
+    for i in range(40):
+        futs.append(ca.binary_agg_async(N.ADD, cb))
+        if i % 3 == 0:
+            got = rdf.Column.aggregate_all_many([cia, cib])
+            assert [int(g["sum"]) for g in got] == [int(g["sum"]) for g in ref_many]
+    sums = set()
+    for col, fut in futs:
+        sums.add(np.float64(fut.result()["sum"]).view(np.uint64).item())
+        col.free()
+    assert len(sums) == 1
+    before = ctx.comm_get_combine()
+    try:
+        ctx.comm_set_combine(before != "peer-memory")
+        switched = True
+    except rdf.ArrowError:
+        switched = False   # no peer access on this box: only NCCL
+    if switched:
+        got = rdf.Column.aggregate_all_many([cia, cib])
+        assert [int(g[k]) for g in got for k in ("sum", "min", "max", "count")] == [int(g[k]) for g in ref_many for k in ("sum", "min", "max", "count")]
+        col, r = ca.binary_agg(N.ADD, cb)
+        assert np.float64(r["sum"]).view(np.uint64).item() in sums   # rank-order fold in both transports: bit-identical
+        col.free()
+        ctx.comm_set_combine(before == "peer-memory")
+    checks += 1
+
     ctx.comm_barrier()
     ok = ctx.comm_all_reduce([1.0], N.SUM)[0]
     assert ok == world
     if rank == 0:
-        print("COMM-OK " + json.dumps({"world": world, "checks": checks, "nccl": info["nccl_version"], "collectives": ctx.comm_info()["collectives"],
+        print("COMM-OK " + json.dumps({"world": world, "checks": checks, "nccl": info["nccl_version"], "collectives": ctx.comm_info()["collectives"], "combine": ctx.comm_get_combine(),
                                        "config3_sum_col0": want[0]["sum"] if want else None}), flush=True)
     ctx.comm_detach()
 

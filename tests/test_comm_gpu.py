@@ -26,21 +26,24 @@ def _free_port() -> int:
         return s.getsockname()[1]
 
 
-def _launch(world: int, script: str, *extra: str, timeout: int = 900) -> str:
+def _launch(world: int, script: str, *extra: str, timeout: int = 900, env=None) -> str:
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(_free_port()), os.path.join(ROOT, script), *extra]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT)
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout, cwd=ROOT, env=dict(os.environ, **(env or {})))
     assert r.returncode == 0, f"rc={r.returncode}\n{r.stdout[-4000:]}\n{r.stderr[-6000:]}"
     return r.stdout
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("combine", ["nccl", "p2p"])
 @pytest.mark.parametrize("world", [2, 4, 8])
-def test_sharded_aggregates_match_the_oracle(world):
+def test_sharded_aggregates_match_the_oracle(world, combine):
+    """Both transports of the combine: the grouped ncclAllReduce and the NVLink peer-memory mailboxes (k_p2p_combine)."""
     if _gpu_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    out = _launch(world, "tests/comm_worker.py")
+    out = _launch(world, "tests/comm_worker.py", env={"BDF_COMBINE": combine})
     assert "COMM-OK" in out, out[-2000:]
+    assert ('"combine": "peer-memory"' in out) == (combine == "p2p"), out[-500:]
 
 
 @pytest.mark.gpu
