@@ -87,6 +87,12 @@ def main():
     report("tan f64", "cfg2", timed(ctx, lambda: g.tan()), "unary")
     report("abs f64", "cfg2", timed(ctx, lambda: g.abs()), "unary")
     g.free()
+    # config 2, second run: |g| up to 1e12 -- beyond the fast path of the trig argument reduction
+    big = G(rdf.F64, lens, 0, -1e12, 1e12, col_id=14)
+    report("sin f64, |x| up to 1e12 (slow-path reduction)", "cfg2-slow", timed(ctx, lambda: big.sin()), "unary")
+    report("cos f64, |x| up to 1e12", "cfg2-slow", timed(ctx, lambda: big.cos()), "unary")
+    report("tan f64, |x| up to 1e12", "cfg2-slow", timed(ctx, lambda: big.tan()), "unary")
+    big.free()
     bn = G(rdf.F64, lens, 0, -1e3, 1e3, col_id=4, null_mod=10)
     dn = G(rdf.F64, lens, 1, col_id=5, null_mod=10)
     report("add f64, 10% nulls on one input", "cfg2-nulls", timed(ctx, lambda: a.add(bn)), "binary")

@@ -252,6 +252,7 @@ struct bdf_ctx {
     size_t pipeline_bytes = (size_t)32 << 20;
     bool profiling = false;
     std::vector<ProfEntry> prof;
+    std::vector<cudaEvent_t> prof_pool;   // recycled timing events
     int64_t launches = 0;
     // multi-GPU: the communicator this context is a rank of (nullptr = a lone GPU) -- comm.cuh
     Comm* comm = nullptr;
@@ -321,7 +322,12 @@ struct LaunchTimer {  // brackets one launch with events when profiling is on
         c->launches++;
         if (!on) return;
         e.rec.kernel = kernel; e.rec.dtype = dtype; e.rec.rows = rows; e.rec.bytes = bytes; e.rec.ms = 0.f;
-        cudaEventCreate(&e.e0); cudaEventCreate(&e.e1);
+        // timing events come from a pool (bdf_profile_read returns them): creating two events per launch cost more host time
+        // than the launch itself and showed up as a few percent of the headline step at 8 GPUs
+        auto take = [&](cudaEvent_t* ev) {
+            if (!c->prof_pool.empty()) { *ev = c->prof_pool.back(); c->prof_pool.pop_back(); } else cudaEventCreate(ev);
+        };
+        take(&e.e0); take(&e.e1);
         cudaEventRecord(e.e0, c->s_compute);
     }
     ~LaunchTimer() {
@@ -2393,6 +2399,7 @@ void bdf_destroy(bdf_ctx* c) {
     if (c->s_desc) cudaStreamSynchronize(c->s_desc);
     if (c->s_fin) cudaStreamSynchronize(c->s_fin);
     for (auto& p : c->prof) { cudaEventDestroy(p.e0); cudaEventDestroy(p.e1); }
+    for (auto ev : c->prof_pool) cudaEventDestroy(ev);
     for (auto ev : c->ev_pool) cudaEventDestroy(ev);
     c->pool.reset();
     for (auto& sl : c->stage) { if (sl.p) cudaFreeHost(sl.p); if (sl.ev) cudaEventDestroy(sl.ev); }
@@ -2612,7 +2619,11 @@ int bdf_comm_attach(bdf_ctx* c, const uint8_t* id, int rank, int world) {
     const char* mode = getenv("BDF_COMBINE");
     if (world > 1 && !(mode && strcmp(mode, "nccl") == 0)) {
         std::string perr;
-        if (comm_enable_p2p(cm, &perr) == 0) comm_set_p2p(cm, true);
+        // Default transport: the mailboxes up to 4 ranks, NCCL above unless asked for.  Measured on NVSwitch B200 boxes
+        // (profiles/r2_*): a blocking combine costs 10 / 13 / 13 us over the mailboxes and 17 / 23 / 31 us over NCCL at
+        // 2 / 4 / 8 GPUs and the strong series gains 10 % at 8, but the pipelined weak series at 8 GPUs ran 8 % slower with
+        // the mailboxes in the one 8-GPU comparison this round could afford (0.400 vs 0.369-0.379 ms per step).
+        if (comm_enable_p2p(cm, &perr) == 0) comm_set_p2p(cm, world <= 4 || (mode && strcmp(mode, "p2p") == 0));
         else if (mode && strcmp(mode, "p2p") == 0) { comm_destroy(cm); c->comm = nullptr; return fail(BDF_NCCL, "BDF_COMBINE=p2p: %s", perr.c_str()); }
     }
     return BDF_OK;
@@ -3154,7 +3165,7 @@ int bdf_profile_read(bdf_ctx* c, bdf_launch_record* buf, int64_t cap, int64_t* n
         cudaEventElapsedTime(&ms, p.e0, p.e1);
         p.rec.ms = ms;
         if (buf && k < cap) buf[k++] = p.rec;
-        cudaEventDestroy(p.e0); cudaEventDestroy(p.e1);
+        c->prof_pool.push_back(p.e0); c->prof_pool.push_back(p.e1);
     }
     c->prof.clear();
     if (n) *n = k;
