@@ -137,6 +137,19 @@ __device__ __forceinline__ void mask_issue(MaskRaw<E, U>& r, const uint32_t* __r
         r.hi[j] = two ? __ldg(p + j * stride_words + 1) : 0u;
     }
 }
+// The general form (a word index per step).  k_filter.cu keeps it: with three bitmaps in flight the base-pointer form above
+// costs it registers (filter scatter 0.226 -> 0.279 ms at 1e8 f64 rows when it was switched over in round 2).
+template <int E, int U>
+__device__ __forceinline__ void mask_issue_general(MaskRaw<E, U>& r, const uint32_t* __restrict__ v, int64_t bit0, int64_t stride_bits) {
+#pragma unroll
+    for (int j = 0; j < U; j++) {
+        const int64_t bit = bit0 + (int64_t)j * stride_bits;
+        const int64_t w = bit >> 5;
+        r.sh[j] = (int)(bit & 31);
+        r.lo[j] = __ldg(v + w);
+        r.hi[j] = (r.sh[j] + E > 32) ? __ldg(v + w + 1) : 0u;
+    }
+}
 // The same with the word pointer and the shift already known (a loop over consecutive tiles advances the pointer by a constant).
 template <int E, int U>
 __device__ __forceinline__ void mask_issue_at(MaskRaw<E, U>& r, const uint32_t* __restrict__ p, int sh, int stride_words) {

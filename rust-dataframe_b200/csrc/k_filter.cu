@@ -117,8 +117,8 @@ k_compare(const BinDesc* __restrict__ descs, int n_chunks, int ta, int tb, doubl
         raw_issue<kUnroll>(ta, pa, e_first, (int64_t)kThreads * E, qa);
         if constexpr (!SCALAR) raw_issue<kUnroll>(tb, pb, e_first, (int64_t)kThreads * E, qb);
         MaskRaw<E, kUnroll> ra, rb;
-        if (va) mask_issue<E, kUnroll>(ra, va, offa + e_first, (int64_t)kThreads * E);
-        if (vb) mask_issue<E, kUnroll>(rb, vb, offb + e_first, (int64_t)kThreads * E);
+        if (va) mask_issue_general<E, kUnroll>(ra, va, offa + e_first, (int64_t)kThreads * E);
+        if (vb) mask_issue_general<E, kUnroll>(rb, vb, offb + e_first, (int64_t)kThreads * E);
         raw_convert<kUnroll>(ta, qa, a);
         if constexpr (!SCALAR) raw_convert<kUnroll>(tb, qb, b);
 #pragma unroll
@@ -309,9 +309,9 @@ k_filter_scatter(const FilterDesc* __restrict__ descs, int n_chunks, const long 
         for (int j = 0; j < kUnroll; j++) x[j].load(pi + base + (int64_t)(j * kThreads + threadIdx.x) * E);
         MaskRaw<E, kUnroll> rm, rmv, rv;
         const int64_t e_first = base + (int64_t)threadIdx.x * E;
-        mask_issue<E, kUnroll>(rm, mval, moff + e_first, (int64_t)kThreads * E);
-        if (mvalid) mask_issue<E, kUnroll>(rmv, mvalid, mvoff + e_first, (int64_t)kThreads * E);
-        if (vi) mask_issue<E, kUnroll>(rv, vi, off + e_first, (int64_t)kThreads * E);
+        mask_issue_general<E, kUnroll>(rm, mval, moff + e_first, (int64_t)kThreads * E);
+        if (mvalid) mask_issue_general<E, kUnroll>(rmv, mvalid, mvoff + e_first, (int64_t)kThreads * E);
+        if (vi) mask_issue_general<E, kUnroll>(rv, vi, off + e_first, (int64_t)kThreads * E);
 #pragma unroll
         for (int j = 0; j < kUnroll; j++) {
             sel[j] = mask_get<E, kUnroll>(rm, j);

@@ -2469,6 +2469,8 @@ static int init_impl(bdf_ctx* c, int device) {
     CK(cudaEventCreateWithFlags(&c->ev_tmp, cudaEventDisableTiming));
     CK(cudaEventCreate(&c->ev_t0));
     CK(cudaEventCreate(&c->ev_t1));
+    // experiment knob: L2 fetch granularity hint (32 / 64 / 128 bytes) -- random gathers (take) fetch whole 128-byte lines by default
+    if (const char* fg = getenv("BDF_L2_FETCH")) { if (atoi(fg) > 0) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(fg)); cudaGetLastError(); }
     const char* pb = getenv("BDF_PIPELINE_BYTES");
     if (pb && atoll(pb) > 0) c->pipeline_bytes = (size_t)atoll(pb);
     return BDF_OK;
