@@ -35,6 +35,11 @@ pub const BDF_EXPR_UNARY: i32 = 100;
 pub struct BdfSortKey { pub column: *const BdfCol, pub descending: i32 }
 pub const BDF_ASYNC: c_int = 1;
 
+/// All four aggregates of one pass (include/b200df.h `bdf_agg4`, ABI version 2: `n_chunks` added).
+#[repr(C)]
+pub struct BdfAgg4 { pub sum: u64, pub min: u64, pub max: u64, pub count: i64, pub rows: i64, pub any_valid: i32, pub would_panic: i32, pub n_chunks: i64 }
+pub enum BdfFuture {}
+
 pub const BDF_OK: c_int = 0;
 pub const BDF_LENGTH_MISMATCH: c_int = 1;
 pub const BDF_DIVIDE_BY_ZERO: c_int = 2;
@@ -42,6 +47,19 @@ pub const BDF_WOULD_PANIC: c_int = 7;
 
 extern "C" {
     pub fn bdf_init(device: c_int, out: *mut *mut BdfCtx) -> c_int;
+    /// ONE context over `n_gpus` GPUs of the box (0 = all visible): the library shards every call by row range, each GPU
+    /// moves its pieces over its own PCIe link, aggregates are combined over NVLink (grouped ncclAllReduce / peer-memory
+    /// mailboxes).  What a single Rust process binds; every entry below accepts it.
+    pub fn bdf_init_multi(n_gpus: c_int, devices: *const c_int, out: *mut *mut BdfCtx) -> c_int;
+    pub fn bdf_fleet_size(ctx: *mut BdfCtx) -> c_int;
+    /// Process per GPU (MPI-style launchers): rank 0 makes the id, ships the 128 bytes, every rank attaches its one-GPU context.
+    pub fn bdf_comm_unique_id(id: *mut u8) -> c_int;
+    pub fn bdf_comm_attach(ctx: *mut BdfCtx, id: *const u8, rank: c_int, world: c_int) -> c_int;
+    pub fn bdf_aggregate_all(ctx: *mut BdfCtx, dtype: c_int, n: i64, input: *const BdfView, out: *mut BdfAgg4) -> c_int;
+    pub fn bdf_aggregate_all_many_dev(ctx: *mut BdfCtx, n_cols: i32, cols: *const *const BdfCol, out: *mut BdfAgg4) -> c_int;
+    pub fn bdf_binary_agg_dev_async(ctx: *mut BdfCtx, op: c_int, left: *const BdfCol, right: *const BdfCol, out: *mut *mut BdfCol,
+                                    fut: *mut *mut BdfFuture) -> c_int;
+    pub fn bdf_future_wait(ctx: *mut BdfCtx, fut: *mut BdfFuture, out: *mut BdfAgg4) -> c_int;
     pub fn bdf_last_error() -> *const c_char;
     pub fn bdf_host_register(ctx: *mut BdfCtx, p: *mut c_void, bytes: usize) -> c_int;
     pub fn bdf_host_unregister(ctx: *mut BdfCtx, p: *mut c_void) -> c_int;
@@ -76,21 +94,56 @@ extern "C" {
     pub fn bdf_ipc_write(ctx: *mut BdfCtx, path: *const c_char, n_cols: i32, names: *const *const c_char, cols: *const *const BdfCol) -> c_int;
 }
 
-/// Process-wide context: one GPU per process, LOCAL_RANK selects the device under a multi-process launcher.
+/// Process-wide context.  A plain process gets ONE context over every GPU of the box (`bdf_init_multi(0, ..)`: the library
+/// shards each call over the GPUs -- the role rayon's par_iter plays in the reference, src/functions/scalar.rs:28-31).  Under a
+/// process-per-GPU launcher (RANK / WORLD_SIZE / LOCAL_RANK set) each process takes its LOCAL_RANK's GPU and the launcher's
+/// side channel carries the communicator id: see `attach` below.  Set BDF_ONE_GPU=1 to pin a plain process to GPU 0.
 pub fn ctx() -> *mut BdfCtx {
     use std::sync::Once;
     static INIT: Once = Once::new();
     static mut CTX: *mut BdfCtx = std::ptr::null_mut();
     unsafe {
         INIT.call_once(|| {
-            let dev = std::env::var("LOCAL_RANK").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
             let mut c = std::ptr::null_mut();
-            let st = bdf_init(dev, &mut c);
+            let launcher = std::env::var("WORLD_SIZE").ok().and_then(|s| s.parse::<i32>().ok()).map_or(false, |w| w > 1);
+            let st = if launcher || std::env::var("BDF_ONE_GPU").is_ok() {
+                let dev = std::env::var("LOCAL_RANK").ok().and_then(|s| s.parse().ok()).unwrap_or(0);
+                bdf_init(dev, &mut c)
+            } else {
+                bdf_init_multi(0, std::ptr::null(), &mut c)
+            };
+            assert_eq!(st, BDF_OK, "libb200df initialisation failed: {}", last_error());
+            CTX = c;
+        });
+        CTX
+    }
+}
+
+/// A one-GPU context for the entries a multi-GPU context does not offer (sort / take / filter move rows between chunks; the IPC
+/// readers map one file): GPU LOCAL_RANK (0 in a plain process).  The same object as `ctx()` under a process-per-GPU launcher.
+pub fn ctx_one_gpu() -> *mut BdfCtx {
+    use std::sync::Once;
+    static INIT: Once = Once::new();
+    static mut CTX: *mut BdfCtx = std::ptr::null_mut();
+    unsafe {
+        INIT.call_once(|| {
+            let all = ctx();
+            if bdf_fleet_size(all) <= 1 { CTX = all; return; }
+            let mut c = std::ptr::null_mut();
+            let st = bdf_init(0, &mut c);
             assert_eq!(st, BDF_OK, "bdf_init failed: {}", last_error());
             CTX = c;
         });
         CTX
     }
+}
+
+/// Process per GPU: make this process's context a rank of the job's communicator.  `id` = the 128 bytes rank 0 obtained from
+/// `bdf_comm_unique_id` and the launcher distributed (an MPI broadcast, a file, a TCP store ...).  Afterwards every aggregate
+/// entry returns the aggregate of the whole sharded column on every rank.
+pub fn attach(id: &[u8; 128], rank: i32, world: i32) -> Result<(), ArrowError> {
+    let st = unsafe { bdf_comm_attach(ctx(), id.as_ptr(), rank, world) };
+    if st == BDF_OK { Ok(()) } else { Err(to_arrow_error(st)) }
 }
 
 pub fn last_error() -> String {

@@ -15,10 +15,13 @@ pub struct DeviceColumns {
 impl Drop for DeviceColumns {
     fn drop(&mut self) {
         for c in &self.cols {
-            unsafe { bdf_col_free(ctx(), *c) };
+            if !c.is_null() { unsafe { bdf_col_free(dev(), *c) }; }
         }
     }
 }
+
+/// The frames of this module live on ONE GPU: sort, take and the IPC readers are one-GPU entries (include/b200df.h).
+fn dev() -> *mut BdfCtx { ctx_one_gpu() }
 
 /// DataFrame::from_arrow (src/dataframe.rs:391-407) for the columns on the path: the file is mapped and its body buffers
 /// go straight to the device.  Columns reported with dtype -1 (Utf8, List, ...) keep coming from arrow's FileReader.
@@ -26,22 +29,27 @@ pub fn from_arrow_device(path: &str) -> Result<DeviceColumns, String> {
     let cpath = CString::new(path).unwrap();
     let mut f: *mut BdfIpc = std::ptr::null_mut();
     check(unsafe { bdf_ipc_open(cpath.as_ptr(), &mut f) })?;
+    // the file handle is closed on every path out of this function
+    struct Close(*mut BdfIpc);
+    impl Drop for Close { fn drop(&mut self) { unsafe { bdf_ipc_close(self.0) } } }
+    let _close = Close(f);
     let (mut n_cols, mut n_batches, mut n_rows) = (0i32, 0i64, 0i64);
-    unsafe { bdf_ipc_describe(f, &mut n_cols, &mut n_batches, &mut n_rows) };
+    check(unsafe { bdf_ipc_describe(f, &mut n_cols, &mut n_batches, &mut n_rows) })?;
     let mut wanted = vec![];
     let mut names = vec![];
     for c in 0..n_cols {
         let (mut name, mut dtype, mut nullable): (*const c_char, i32, i32) = (std::ptr::null(), -1, 0);
-        unsafe { bdf_ipc_column(f, c, &mut name, &mut dtype, &mut nullable) };
+        check(unsafe { bdf_ipc_column(f, c, &mut name, &mut dtype, &mut nullable) })?;
         if dtype >= 0 {
             wanted.push(c);
             names.push(unsafe { CStr::from_ptr(name) }.to_string_lossy().into_owned());
         }
     }
+    if wanted.is_empty() {
+        return Ok(DeviceColumns { names, cols: vec![] });   // no numeric/boolean column: nothing for the device (bdf_ipc_read rejects n_cols == 0)
+    }
     let mut cols = vec![std::ptr::null_mut(); wanted.len()];
-    let st = unsafe { bdf_ipc_read(ctx(), f, wanted.len() as i32, wanted.as_ptr(), 0, cols.as_mut_ptr()) };
-    unsafe { bdf_ipc_close(f) };   // synchronous read: the copies are done
-    check(st)?;
+    check(unsafe { bdf_ipc_read(dev(), f, wanted.len() as i32, wanted.as_ptr(), 0, cols.as_mut_ptr()) })?;   // synchronous: the copies are done
     Ok(DeviceColumns { names, cols })
 }
 
@@ -51,7 +59,7 @@ pub fn to_arrow_device(frame: &DeviceColumns, path: &str) -> Result<(), String> 
     let cnames: Vec<CString> = frame.names.iter().map(|s| CString::new(s.as_str()).unwrap()).collect();
     let name_ptrs: Vec<*const c_char> = cnames.iter().map(|s| s.as_ptr()).collect();
     let col_ptrs: Vec<*const BdfCol> = frame.cols.iter().map(|c| *c as *const BdfCol).collect();
-    check(unsafe { bdf_ipc_write(ctx(), cpath.as_ptr(), col_ptrs.len() as i32, name_ptrs.as_ptr(), col_ptrs.as_ptr()) })
+    check(unsafe { bdf_ipc_write(dev(), cpath.as_ptr(), col_ptrs.len() as i32, name_ptrs.as_ptr(), col_ptrs.as_ptr()) })
 }
 
 /// DataFrame::sort (src/dataframe.rs:194-222): criteria = (column index, descending); nulls last like the reference.
@@ -61,19 +69,16 @@ pub fn sort_device(frame: &DeviceColumns, criteria: &[(usize, bool)]) -> Result<
     }
     let keys: Vec<BdfSortKey> = criteria.iter().map(|(c, d)| BdfSortKey { column: frame.cols[*c], descending: *d as i32 }).collect();
     let mut indices: *mut BdfCol = std::ptr::null_mut();
-    check(unsafe { bdf_sort_indices_dev(ctx(), keys.len() as i32, keys.as_ptr(), &mut indices) })?;   // lexsort_to_indices
-    let mut out = vec![];
+    check(unsafe { bdf_sort_indices_dev(dev(), keys.len() as i32, keys.as_ptr(), &mut indices) })?;   // lexsort_to_indices
+    // both the index column and the columns taken so far are owned by guards: an error half-way frees them (raw pointers have no Drop)
+    let idx = DeviceColumns { names: vec![], cols: vec![indices] };
+    let mut out = DeviceColumns { names: frame.names.clone(), cols: Vec::with_capacity(frame.cols.len()) };
     for c in &frame.cols {
         let mut taken: *mut BdfCol = std::ptr::null_mut();
-        let st = unsafe { bdf_take_dev(ctx(), *c, indices, &mut taken) };                               // sort_by_indices -> Column::take
-        if st != BDF_OK {
-            unsafe { bdf_col_free(ctx(), indices) };
-            return check(st).map(|_| unreachable!());
-        }
-        out.push(taken);
+        check(unsafe { bdf_take_dev(dev(), *c, idx.cols[0], &mut taken) })?;                            // sort_by_indices -> Column::take
+        out.cols.push(taken);
     }
-    unsafe { bdf_col_free(ctx(), indices) };
-    Ok(DeviceColumns { names: frame.names.clone(), cols: out })
+    Ok(out)
 }
 
 /// A run of Float64 Calculations whose intermediates are not kept (config 2: h = sin(((a+b)*c)/d)) as one pass.
@@ -81,7 +86,7 @@ pub fn sort_device(frame: &DeviceColumns, criteria: &[(usize, bool)]) -> Result<
 pub fn fused_chain(frame: &DeviceColumns, inputs: &[usize], nodes: &[BdfExprNode]) -> Result<*mut BdfCol, String> {
     let cols: Vec<*const BdfCol> = inputs.iter().map(|i| frame.cols[*i] as *const BdfCol).collect();
     let mut out: *mut BdfCol = std::ptr::null_mut();
-    check(unsafe { bdf_eval_expr_dev(ctx(), cols.len() as i32, cols.as_ptr(), nodes.len() as i32, nodes.as_ptr(), &mut out) })?;
+    check(unsafe { bdf_eval_expr_dev(dev(), cols.len() as i32, cols.as_ptr(), nodes.len() as i32, nodes.as_ptr(), &mut out) })?;
     Ok(out)
 }
 

@@ -36,7 +36,10 @@ pub fn gpu_unary<T: ArrowNumericType>(op: c_int, array: Vec<&PrimitiveArray<T>>)
 
 fn alloc_outputs<T: ArrowNumericType>(lens: &[usize]) -> (Vec<MutableBuffer>, Vec<MutableBuffer>, Vec<BdfOut>) {
     let width = std::mem::size_of::<T::Native>();
-    let mut vals: Vec<MutableBuffer> = lens.iter().map(|&n| MutableBuffer::new(n * width)).collect();
+    // Both buffers get their FINAL length before the call (zero-filled once, as arrow's own kernels do with `with_bitset`): the
+    // library then writes into initialised memory of the right size and nothing has to be resized afterwards -- on arrow
+    // versions where `MutableBuffer::resize` zero-fills the grown range, resizing AFTER the call would wipe the results.
+    let mut vals: Vec<MutableBuffer> = lens.iter().map(|&n| MutableBuffer::new(n * width).with_bitset(n * width, false)).collect();
     let mut bits: Vec<MutableBuffer> = lens.iter().map(|&n| MutableBuffer::new((n + 7) / 8).with_bitset((n + 7) / 8, false)).collect();
     let outs = (0..lens.len()).map(|i| BdfOut {
         values: vals[i].raw_data_mut() as *mut c_void, validity: bits[i].raw_data_mut(), len: lens[i] as i64, null_count: 0, has_validity: 0,
@@ -45,11 +48,8 @@ fn alloc_outputs<T: ArrowNumericType>(lens: &[usize]) -> (Vec<MutableBuffer>, Ve
 }
 
 fn finish<T: ArrowNumericType>(vals: Vec<MutableBuffer>, bits: Vec<MutableBuffer>, outs: &[BdfOut]) -> Vec<PrimitiveArray<T>> {
-    let width = std::mem::size_of::<T::Native>();
-    outs.iter().zip(vals.into_iter().zip(bits.into_iter())).map(|(o, (mut v, mut b))| {
-        let len = o.len as usize;
-        v.resize(len * width).unwrap();
-        b.resize((len + 7) / 8).unwrap();
+    outs.iter().zip(vals.into_iter().zip(bits.into_iter())).map(|(o, (v, b))| {
+        let len = o.len as usize;   // == the length the buffers were created with (bdf_out.len is checked by the library)
         let nulls = if o.has_validity != 0 { Some(b.freeze()) } else { None };
         let data = ArrayData::new(T::get_data_type(), len, Some(o.null_count as usize), nulls, 0, vec![v.freeze()], vec![]);
         PrimitiveArray::<T>::from(Arc::new(data))
