@@ -265,6 +265,18 @@ typedef struct { const bdf_col* column; int32_t descending; } bdf_sort_key;
 int  bdf_sort_indices_dev(bdf_ctx* ctx, int32_t n_keys, const bdf_sort_key* keys, bdf_col** indices);
 int  bdf_take_dev(bdf_ctx* ctx, const bdf_col* values, const bdf_col* indices, bdf_col** out);
 
+/* ---- group-by aggregate (the tail of SURVEY 8(f) N4: `Transformation::GroupAggregate`, a panic! in the reference,
+ * src/evaluation.rs:73; its intended shape is src/expression.rs:114-221) ---------------------------------------------------
+ * Rows are grouped by ONE numeric key column; every value column is folded per group with the aggregates of
+ * AggregateFunctions (sum: wrapping for integers, double accumulation for floats; count of valid slots; min / max for integers).
+ * Groups come out in ascending key order, the null key (one group) last -- the order of DataFrame::sort; NaN keys form one
+ * group after every number, -0.0 and 0.0 are one group.  Results: one chunk per column, n_groups rows; sum (dtype of the value
+ * column, never null: an all-null group sums to 0 like AggregateFunctions::sum), count (Int64), min / max (NULL for a group
+ * without a valid value; not produced for float columns -- T::Native: Ord -- the pointers are NULL then). */
+typedef struct { bdf_col *sum, *count, *min, *max; } bdf_group_out;
+int  bdf_group_aggregate_dev(bdf_ctx* ctx, const bdf_col* key, int32_t n_values, const bdf_col* const* values, bdf_col** out_keys,
+                             bdf_group_out* out /* n_values */, int64_t* n_groups);
+
 /* ---- N4: Arrow IPC files either side of the path ---------------------------------------------------------------
  * DataFrame::from_arrow (src/dataframe.rs:391-407: arrow::ipc::reader::FileReader, every RecordBatch -> one chunk per
  * column) and DataFrame::to_arrow (:515-525: arrow::ipc::writer::FileWriter).  The file is mapped and its footer, schema
@@ -301,7 +313,7 @@ typedef struct {
     int64_t bytes;    /* algorithmic bytes of the launch (SURVEY 8(d) per-row figure x rows) */
     float   ms;       /* device time between the bracketing events */
 } bdf_launch_record;
-typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER, BDF_K_EXPR, BDF_K_SORT, BDF_K_TAKE } bdf_kernel_id;
+typedef enum { BDF_K_BINARY = 0, BDF_K_UNARY, BDF_K_CAST, BDF_K_REDUCE, BDF_K_GENERATE, BDF_K_AVG, BDF_K_COMPARE, BDF_K_FILTER, BDF_K_EXPR, BDF_K_SORT, BDF_K_TAKE, BDF_K_GROUP } bdf_kernel_id;
 int     bdf_profile_enable(bdf_ctx* ctx, int on);
 int     bdf_profile_read(bdf_ctx* ctx, bdf_launch_record* buf, int64_t cap, int64_t* n); /* syncs; drains */
 int64_t bdf_launch_count(bdf_ctx* ctx);           /* kernels launched since bdf_init */

@@ -303,3 +303,52 @@ def generate(dtype: int, kind: int, lo: float, hi: float, seed: int, col: int, r
     lib().orc_generate(dtype, kind, lo, hi, seed, col, row0, length, null_mod, v.ctypes.data if length else 0,
                        b.ctypes.data if (b is not None and b.size) else None, C.byref(nc))
     return OracleArray(dtype, v, b, int(nc.value))
+
+
+# ---------------------------------------------------------------------------------------------------------
+# group-by aggregate (numpy restatement; the reference's GroupAggregate is a panic!, src/evaluation.rs:73 -- the operator is
+# DEFINED by include/b200df.h bdf_group_aggregate_dev: one numeric key, groups in ascending key order with the null key last
+# (DataFrame::sort's order), NaN keys one group after every number, -0.0 == 0.0; per group the aggregates of
+# AggregateFunctions (aggregate.rs:12-93): wrapping integer sum, valid count, min / max over valid slots (None if there is none)).
+# Parity unpinned: no reference test exists for this operator; cross-checked against pyarrow's group_by in tests/test_group_gpu.py.
+
+def group_aggregate(key_chunks, value_chunks):
+    """key_chunks / value_chunks: lists of chunks (same lengths).  Returns
+    (keys ndarray, key_valid bool ndarray, {"sum": ndarray, "count": int64 ndarray, "min"/"max": (ndarray, valid) or None,
+    "exact": longdouble sums and sums of magnitudes for float columns})."""
+    kv = np.concatenate([np.asarray(c.values)[c.offset:c.offset + c.length] for c in key_chunks]) if key_chunks else np.zeros(0)
+    km = np.concatenate([c.valid_mask() for c in key_chunks]) if key_chunks else np.zeros(0, bool)
+    vv = np.concatenate([np.asarray(c.values)[c.offset:c.offset + c.length] for c in value_chunks])
+    vm = np.concatenate([c.valid_mask() for c in value_chunks])
+    n = kv.shape[0]
+    if kv.dtype.kind == "f":
+        isnan = np.isnan(kv)
+        ck = np.where(isnan, 0.0, kv) + 0.0          # -0.0 + 0.0 = +0.0: one group for both zeros
+    else:
+        isnan = np.zeros(n, bool)
+        ck = kv
+    ck = np.where(km, ck, 0)                         # payload under a null key does not matter
+    isnan = isnan & km
+    order = np.lexsort((ck, isnan, ~km))             # stable: nulls last, NaN after every number, then the value
+    sk, sn, sm = ck[order], isnan[order], km[order]
+    head = np.ones(n, bool)
+    if n > 1:
+        same = (sm[1:] == sm[:-1]) & (~sm[1:] | ((sn[1:] == sn[:-1]) & (sn[1:] | (sk[1:] == sk[:-1]))))
+        head[1:] = ~same
+    starts = np.nonzero(head)[0]
+    keys = kv[order][starts] if n else kv[:0]
+    key_valid = km[order][starts] if n else km[:0]
+    sv, svm = vv[order], vm[order]
+    counts = np.add.reduceat(svm.astype(np.int64), starts) if n else np.zeros(0, np.int64)
+    out = {"count": counts, "min": None, "max": None, "exact": None}
+    if vv.dtype.kind == "f":
+        ld = np.where(svm, sv, 0).astype(np.longdouble)
+        out["sum"] = np.add.reduceat(np.where(svm, sv, 0).astype(np.float64), starts).astype(vv.dtype) if n else vv[:0]
+        out["exact"] = (np.add.reduceat(ld, starts), np.add.reduceat(np.abs(ld), starts)) if n else (ld[:0], ld[:0])
+    else:
+        u = np.dtype(f"u{vv.dtype.itemsize}")
+        out["sum"] = np.add.reduceat(np.where(svm, sv, 0).astype(vv.dtype).view(u), starts).view(vv.dtype) if n else vv[:0]   # wraps in T's width
+        info = np.iinfo(vv.dtype)
+        out["min"] = (np.minimum.reduceat(np.where(svm, sv, info.max), starts), counts > 0) if n else (vv[:0], counts > 0)
+        out["max"] = (np.maximum.reduceat(np.where(svm, sv, info.min), starts), counts > 0) if n else (vv[:0], counts > 0)
+    return keys, key_valid, out

@@ -1799,6 +1799,109 @@ static int take_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* indices, b
 }
 
 // ---------------------------------------------------------------------------------------------------
+// group-by aggregate (k_group.cu): sort the key, gather, mark group heads, compact keys and group starts, one warp per group
+
+namespace bdf {
+cudaError_t launch_group_heads(int dtype, const void* key, const uint32_t* kvalid, long long n, uint32_t* words, cudaStream_t s);
+cudaError_t launch_group_reduce(int dtype, const void* val, const uint32_t* vvalid, const uint32_t* starts, long long n_groups, long long n_rows,
+                                void* sum, long long* count, void* mn, void* mx, uint32_t* mm_valid, cudaStream_t s);
+}  // namespace bdf
+
+static int group_aggregate_dev(bdf_ctx* c, const bdf_col* key, int n_values, const bdf_col* const* values, bdf_col** out_keys,
+                               bdf_group_out* outs, int64_t* n_groups_out) {
+    if (key->dtype < 0 || key->dtype >= BDF_NTYPES) return fail(BDF_UNSUPPORTED, "the group key must be a numeric column");
+    if (n_values < 0 || n_values > 64) return fail(BDF_INVALID, "0..64 value columns");
+    for (int j = 0; j < n_values; j++) {
+        if (!values[j]) return fail(BDF_INVALID, "null value column");
+        if (values[j]->dtype < 0 || values[j]->dtype >= BDF_NTYPES) return fail(BDF_UNSUPPORTED, "aggregated columns must be numeric");
+        if (values[j]->total_len != key->total_len) return fail(BDF_LENGTH_MISMATCH, "key and value columns have different lengths");
+    }
+    const int64_t n = key->total_len;
+    std::vector<bdf_col*> tmp;   // everything made on the way; released at the end whatever happens
+    std::vector<bdf_col*> made;  // the results (released only on failure)
+    auto cleanup = [&](bool fail_too) {
+        for (bdf_col* t : tmp) col_release(c, t);
+        if (fail_too) for (bdf_col* t : made) col_release(c, t);
+    };
+    int st = BDF_OK;
+    cudaError_t e = cudaSuccess;
+    bdf_col *idx = nullptr, *skey = nullptr, *head = nullptr, *iota = nullptr, *starts = nullptr, *ukeys = nullptr;
+    const bdf_sort_key sk{key, 0};
+    st = sort_indices_dev(c, 1, &sk, &idx);
+    if (st == BDF_OK) { tmp.push_back(idx); st = take_dev(c, key, idx, &skey); }
+    if (st == BDF_OK) { tmp.push_back(skey); st = col_alloc(c, kBool, {ChunkPlan{n, false}}, nullptr, 0, &head); }
+    if (st == BDF_OK) {
+        tmp.push_back(head);
+        wait_groups(c->s_compute, skey, 0, 1);
+        c->launches++;
+        e = launch_group_heads(skey->dtype, skey->chunks[0].values, skey->chunks[0].validity, n, (uint32_t*)head->chunks[0].values, c->s_compute);
+        if (e == cudaSuccess) e = finish_single_group(c, head);
+        if (e != cudaSuccess) st = fail_cuda(e, "group heads");
+    }
+    if (st == BDF_OK) st = filter_dev(c, skey, head, &ukeys);                       // the distinct keys, ascending, null key last
+    if (st == BDF_OK) { made.push_back(ukeys); st = col_alloc(c, BDF_U32, {ChunkPlan{n, false}}, nullptr, 0, &iota); }
+    if (st == BDF_OK) {
+        tmp.push_back(iota);
+        c->launches++;
+        e = n > 0 ? launch_iota((uint32_t*)iota->chunks[0].values, n, c->sm_count, c->s_compute) : cudaSuccess;
+        if (e == cudaSuccess) e = finish_single_group(c, iota);
+        if (e != cudaSuccess) st = fail_cuda(e, "group iota");
+    }
+    if (st == BDF_OK) st = filter_dev(c, iota, head, &starts);                     // first sorted row of every group
+    int64_t n_groups = 0;
+    if (st == BDF_OK) { tmp.push_back(starts); n_groups = starts->chunks.empty() ? 0 : starts->chunks[0].len; }
+    for (int j = 0; j < n_values && st == BDF_OK; j++) {
+        const int dt = values[j]->dtype;
+        const bool is_float = dtype_is_float(dt);
+        bdf_col* sval = nullptr;
+        st = take_dev(c, values[j], idx, &sval);
+        if (st != BDF_OK) break;
+        tmp.push_back(sval);
+        bdf_col *csum = nullptr, *ccnt = nullptr, *cmin = nullptr, *cmax = nullptr;
+        st = col_alloc(c, dt, {ChunkPlan{n_groups, false}}, nullptr, 0, &csum);
+        if (st == BDF_OK) { made.push_back(csum); st = col_alloc(c, BDF_I64, {ChunkPlan{n_groups, false}}, nullptr, 0, &ccnt); }
+        if (st == BDF_OK) made.push_back(ccnt);
+        if (st == BDF_OK && !is_float) {
+            st = col_alloc(c, dt, {ChunkPlan{n_groups, true}}, nullptr, 0, &cmin);
+            if (st == BDF_OK) { made.push_back(cmin); st = col_alloc(c, dt, {ChunkPlan{n_groups, true}}, nullptr, 0, &cmax); }
+            if (st == BDF_OK) made.push_back(cmax);
+        }
+        if (st != BDF_OK) break;
+        wait_groups(c->s_compute, sval, 0, 1);
+        wait_groups(c->s_compute, starts, 0, 1);
+        {
+            const int w = dtype_width(dt);
+            LaunchTimer t(c, BDF_K_GROUP, dt, n, n * w + (sval->chunks[0].validity ? bitmap_bytes(n) : 0) + n_groups * (4 + (is_float ? 1 : 3) * w + 8));
+            e = launch_group_reduce(dt, sval->chunks[0].values, sval->chunks[0].validity, (const uint32_t*)starts->chunks[0].values, n_groups, n,
+                                    csum->chunks[0].values, (long long*)ccnt->chunks[0].values, cmin ? cmin->chunks[0].values : nullptr,
+                                    cmax ? cmax->chunks[0].values : nullptr, cmin ? cmin->chunks[0].validity : nullptr, c->s_compute);
+        }
+        // max shares min's validity pattern: copy the bitmap rather than set it twice with atomics
+        if (e == cudaSuccess && cmin && n_groups)
+            e = cudaMemcpyAsync(cmax->chunks[0].validity, cmin->chunks[0].validity, (size_t)bitmap_bytes(n_groups), cudaMemcpyDeviceToDevice, c->s_compute);
+        for (bdf_col* r : {csum, ccnt, cmin, cmax})
+            if (r && e == cudaSuccess) {
+                e = finish_single_group(c, r);
+                if (r == cmin || r == cmax) r->null_counts[0] = -1;   // learnt on demand (ensure_null_counts)
+            }
+        if (e != cudaSuccess) { st = fail_cuda(e, "group aggregate"); break; }
+        outs[j].sum = csum; outs[j].count = ccnt; outs[j].min = cmin; outs[j].max = cmax;
+    }
+    if (st != BDF_OK) {
+        const std::string keep = g_err;
+        cudaGetLastError();
+        cleanup(true);
+        for (int j = 0; j < n_values; j++) outs[j] = bdf_group_out{nullptr, nullptr, nullptr, nullptr};
+        g_err = keep;
+        return st;
+    }
+    cleanup(false);
+    *out_keys = ukeys;
+    if (n_groups_out) *n_groups_out = n_groups;
+    return BDF_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Multi-GPU context (bdf_init_multi): ONE process, every GPU of the box.  The library owns the sharding that the
 // reference leaves to rayon (par_iter over chunks, src/functions/scalar.rs:28-31,99-102): the rows of a call are cut into
 // one contiguous range per GPU (cuts on 64-row boundaries inside a chunk, so a piece is a zero-copy Arrow slice whose
@@ -2967,6 +3070,14 @@ int bdf_sort_indices_dev(bdf_ctx* c, int32_t n_keys, const bdf_sort_key* keys, b
     ENTER(c);
     if (!keys || !indices) return fail(BDF_INVALID, "null argument");
     return sort_indices_dev(c, n_keys, keys, indices);
+}
+
+int bdf_group_aggregate_dev(bdf_ctx* c, const bdf_col* key, int32_t n_values, const bdf_col* const* values, bdf_col** out_keys, bdf_group_out* out,
+                            int64_t* n_groups) {
+    if (c && c->fleet) return fail(BDF_UNSUPPORTED, "group-by moves rows between chunks: use a one-GPU context (bdf_init) for it");
+    ENTER(c);
+    if (!key || !out_keys || (n_values && (!values || !out))) return fail(BDF_INVALID, "null argument");
+    return group_aggregate_dev(c, key, n_values, values, out_keys, out, n_groups);
 }
 
 int bdf_take_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* indices, bdf_col** out) {

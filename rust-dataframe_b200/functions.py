@@ -477,6 +477,20 @@ def sort_columns(criteria: Sequence[tuple], columns: Sequence["Column"]) -> List
     return [c.take(idx) for c in columns]
 
 
+def group_aggregate(key: "Column", values: Sequence["Column"]):
+    """Group-by aggregate (`GroupAggregate`, unimplemented in the reference: src/evaluation.rs:73): returns
+    ``(keys Column, [ {"sum": Column, "count": Column, "min": Column | None, "max": Column | None} per value column ])``.
+    Groups in ascending key order, the null key last; see include/b200df.h bdf_group_aggregate_dev."""
+    ctx = key.ctx
+    k = len(values)
+    cols = (C.c_void_p * max(k, 1))(*[v.handle for v in values])
+    outs = (N.GroupOut * max(k, 1))()
+    hk, ng = C.c_void_p(), C.c_int64(0)
+    N.raise_for_status(N.lib().bdf_group_aggregate_dev(ctx.handle, key.handle, k, cols, C.byref(hk), outs, C.byref(ng)))
+    wrap = lambda p: Column(ctx, C.c_void_p(p)) if p else None
+    return Column(ctx, hk), [{"sum": wrap(outs[j].sum), "count": wrap(outs[j].count), "min": wrap(outs[j].min), "max": wrap(outs[j].max)} for j in range(k)]
+
+
 def _expr_nodes(nodes: Sequence[tuple]):
     arr = (N.ExprNode * len(nodes))()
     for k, nd in enumerate(nodes):

@@ -1,0 +1,138 @@
+"""Group-by aggregate (bdf_group_aggregate_dev): the operator the reference leaves as a panic! (src/evaluation.rs:73).  Checked
+against the numpy restatement in oracle/pyoracle.py (itself cross-checked against pyarrow's hash aggregate below)."""
+import numpy as np
+import pytest
+
+
+def _chunks(rdf, values, mask, lens):
+    out, row = [], 0
+    for n in lens:
+        out.append(rdf.PrimitiveArray.from_numpy(values[row:row + n], None if mask is None else mask[row:row + n]))
+        row += n
+    return out
+
+
+def _col_values(col):
+    """One-chunk result column -> (values, valid mask, array)."""
+    arrs = col.download()
+    assert len(arrs) == 1
+    return arrs[0].value_slice(), arrs[0].valid_mask(), arrs[0]
+
+
+def test_oracle_group_aggregate_matches_pyarrow(oracle):
+    import pyarrow as pa
+
+    rng = np.random.default_rng(3)
+    n = 20_000
+    k = rng.integers(-50, 50, n).astype(np.int32)
+    km = rng.random(n) > 0.05
+    v = rng.integers(-1000, 1000, n).astype(np.int64)
+    vm = rng.random(n) > 0.2
+
+    class Ch:
+        def __init__(self, values, mask):
+            self.values, self.offset, self.length, self._m = values, 0, len(values), mask
+
+        def valid_mask(self):
+            return self._m
+
+    keys, kvalid, out = oracle.group_aggregate([Ch(k, km)], [Ch(v, vm)])
+    t = pa.table({"k": pa.array(k, mask=~km), "v": pa.array(v, mask=~vm)})
+    g = t.group_by("k").aggregate([("v", "sum"), ("v", "count"), ("v", "min"), ("v", "max")]).to_pydict()
+    want = {kk: (s, c, mn, mx) for kk, s, c, mn, mx in zip(g["k"], g["v_sum"], g["v_count"], g["v_min"], g["v_max"])}
+    assert len(want) == len(keys)
+    for i in range(len(keys)):
+        kk = int(keys[i]) if kvalid[i] else None
+        s, c, mn, mx = want[kk]
+        assert out["count"][i] == c and int(out["sum"][i]) == (s or 0)
+        assert (bool(out["min"][1][i]), bool(out["max"][1][i])) == (mn is not None, mx is not None)
+        if mn is not None:
+            assert int(out["min"][0][i]) == mn and int(out["max"][0][i]) == mx
+    assert list(keys[kvalid]) == sorted(keys[kvalid]) and (not kvalid.all()) and not kvalid[-1]   # ascending, the null key last
+
+
+CASES = [("int32", "int64", 200, 0.05, 0.1), ("float64", "float64", 50, 0.0, 0.2), ("int8", "int16", 300, 0.1, 0.0),
+         ("uint64", "uint32", 7, 0.0, 0.5), ("float32", "int8", 1000, 0.02, 0.05), ("int64", "float32", 3, 0.3, 0.0)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kname,vname,cardinality,knull,vnull", CASES)
+def test_group_aggregate_matches_the_oracle(rdf, ctx, oracle, kname, vname, cardinality, knull, vnull):
+    rng = np.random.default_rng(sum(map(ord, kname + vname)))
+    lens = [50_000, 1, 0, 123_457, 64]
+    n = sum(lens)
+    kd, vd = np.dtype(kname), np.dtype(vname)
+    if kd.kind == "f":
+        k = rng.integers(-cardinality // 2, cardinality // 2, n).astype(kd) * kd.type(0.5)
+        k[rng.random(n) < 0.01] = np.nan            # NaN keys: one group after every number
+        k[rng.random(n) < 0.01] = -0.0              # -0.0 and 0.0 are one group
+    elif kd.kind == "u":
+        k = (rng.integers(0, cardinality, n).astype(np.uint64) * np.uint64(2 ** 60 // max(cardinality, 1))).astype(kd)
+    else:
+        info = np.iinfo(kd)
+        k = rng.integers(max(info.min, -cardinality // 2), min(info.max, cardinality // 2), n, endpoint=True).astype(kd)
+    if vd.kind == "f":
+        v = rng.uniform(-1e3, 1e3, n).astype(vd)
+    else:
+        info = np.iinfo(vd)
+        v = rng.integers(info.min, info.max, n, dtype=vd, endpoint=True)   # full range: sums wrap
+    km = rng.random(n) >= knull if knull else None
+    vm = rng.random(n) >= vnull if vnull else None
+    kch, vch = _chunks(rdf, k, km, lens), _chunks(rdf, v, vm, lens)
+    ck, cv = rdf.Column.upload(kch, ctx=ctx), rdf.Column.upload(vch, ctx=ctx)
+    keys, res = rdf.group_aggregate(ck, [cv])
+    okeys, okvalid, want = oracle.group_aggregate(kch, vch)
+    gk, gkv, _ = _col_values(keys)
+    assert len(gk) == len(okeys) and np.array_equal(gkv, okvalid)
+    if kd.kind == "f":
+        both_nan = np.isnan(gk) & np.isnan(okeys)
+        assert np.array_equal(np.where(both_nan | ~gkv, 0, gk) + 0.0, np.where(both_nan | ~okvalid, 0, okeys) + 0.0)
+    else:
+        assert np.array_equal(gk[gkv], okeys[okvalid])
+    r = res[0]
+    gcount, _, _ = _col_values(r["count"])
+    assert np.array_equal(gcount, want["count"])
+    gsum, gsv, sum_arr = _col_values(r["sum"])
+    assert gsv.all() and sum_arr.validity is None          # an all-null group sums to 0, never NULL
+    if vd.kind == "f":
+        exact, mag = want["exact"]
+        eps = 2.0 ** -53 if vd.itemsize == 8 else 2.0 ** -24
+        ng = np.maximum(want["count"], 2)
+        assert np.all(np.abs(gsum.astype(np.longdouble) - exact) <= 16 * np.log2(ng) * eps * mag + 1e-300)
+        assert r["min"] is None and r["max"] is None       # T::Native: Ord
+    else:
+        assert np.array_equal(gsum, want["sum"])
+        for key in ("min", "max"):
+            g, gv, arr = _col_values(r[key])
+            wv, wm = want[key]
+            assert np.array_equal(gv, wm) and np.array_equal(g[gv], wv[wm])
+            assert arr.null_count == int((~wm).sum())
+    for col in (ck, cv, keys, r["sum"], r["count"], r["min"], r["max"]):
+        if col is not None:
+            col.free()
+
+
+@pytest.mark.gpu
+def test_group_aggregate_shapes(rdf, ctx, oracle):
+    """Edge shapes: empty input, one group, every row its own group, several value columns at once, determinism."""
+    empty = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.zeros(0, np.int64))], ctx=ctx)
+    keys, res = rdf.group_aggregate(empty, [empty])
+    assert len(keys) == 0 and len(res[0]["sum"]) == 0
+    n = 300_000
+    rng = np.random.default_rng(1)
+    one = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(np.full(n, 7, np.int16))], ctx=ctx)
+    vals = rng.integers(-10 ** 6, 10 ** 6, n)
+    v = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(vals)], ctx=ctx)
+    f = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(rng.uniform(-1, 1, n))], ctx=ctx)
+    keys, res = rdf.group_aggregate(one, [v, f])
+    assert len(keys) == 1 and int(res[0]["sum"].download()[0].value_slice()[0]) == int(vals.sum()) and int(res[0]["count"].download()[0].value_slice()[0]) == n
+    first = res[1]["sum"].download()[0].value_slice()[0]
+    keys2, res2 = rdf.group_aggregate(one, [v, f])
+    assert np.float64(res2[1]["sum"].download()[0].value_slice()[0]).view(np.uint64) == np.float64(first).view(np.uint64)   # deterministic
+    uniq = rdf.Column.upload([rdf.PrimitiveArray.from_numpy(rng.permutation(n).astype(np.int64))], ctx=ctx)
+    keys3, res3 = rdf.group_aggregate(uniq, [v])
+    assert len(keys3) == n and np.array_equal(keys3.download()[0].value_slice(), np.arange(n))
+    perm_keys = uniq.download()[0].value_slice()
+    assert np.array_equal(res3[0]["sum"].download()[0].value_slice()[perm_keys], vals)   # group of key k holds the row whose key is k
+    with pytest.raises(rdf.ComputeError):
+        rdf.group_aggregate(one, [empty])   # different lengths
