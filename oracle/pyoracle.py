@@ -347,7 +347,8 @@ def group_aggregate(key_chunks, value_chunks):
         out["exact"] = (np.add.reduceat(ld, starts), np.add.reduceat(np.abs(ld), starts)) if n else (ld[:0], ld[:0])
     else:
         u = np.dtype(f"u{vv.dtype.itemsize}")
-        out["sum"] = np.add.reduceat(np.where(svm, sv, 0).astype(vv.dtype).view(u), starts).view(vv.dtype) if n else vv[:0]   # wraps in T's width
+        # dtype=u: numpy would otherwise accumulate small integers in the platform word; the reference wraps in T's width
+        out["sum"] = np.add.reduceat(np.where(svm, sv, 0).astype(vv.dtype).view(u), starts, dtype=u).view(vv.dtype) if n else vv[:0]
         info = np.iinfo(vv.dtype)
         out["min"] = (np.minimum.reduceat(np.where(svm, sv, info.max), starts), counts > 0) if n else (vv[:0], counts > 0)
         out["max"] = (np.maximum.reduceat(np.where(svm, sv, info.min), starts), counts > 0) if n else (vv[:0], counts > 0)

@@ -49,6 +49,13 @@ def test_oracle_group_aggregate_matches_pyarrow(oracle):
         if mn is not None:
             assert int(out["min"][0][i]) == mn and int(out["max"][0][i]) == mx
     assert list(keys[kvalid]) == sorted(keys[kvalid]) and (not kvalid.all()) and not kvalid[-1]   # ascending, the null key last
+    # narrow values: sums wrap in T's width (AggregateFunctions::sum adds T::Native), whatever numpy's default accumulator is
+    v16 = rng.integers(-32768, 32767, n).astype(np.int16)
+    _, _, out16 = oracle.group_aggregate([Ch(k, km)], [Ch(v16, np.ones(n, bool))])
+    assert out16["sum"].dtype == np.int16 and len(out16["sum"]) == len(keys)
+    order = np.lexsort((np.where(km, k, 0), ~km))
+    first = np.nonzero(np.where(km, k, 0)[order] == np.where(km, k, 0)[order][0])[0]
+    assert int(out16["sum"][0]) == int(np.sum(v16[order][first[first < np.searchsorted(~km[order], True)]].astype(np.int64)).astype(np.int16))
 
 
 CASES = [("int32", "int64", 200, 0.05, 0.1), ("float64", "float64", 50, 0.0, 0.2), ("int8", "int16", 300, 0.1, 0.0),
