@@ -302,6 +302,31 @@ class DeviceFrame:
         idx = sort_indices([(self.column(c), d) for c, d in criteria])
         return DeviceFrame(OrderedDict((n, c.take(idx)) for n, c in self.columns.items()))
 
+    def group_aggregate(self, key: str, aggregates: Sequence[Tuple[str, str]]) -> "DeviceFrame":
+        """What `Transformation::GroupAggregate` is meant to do (the reference's evaluator panics on it, src/evaluation.rs:73, and
+        `evaluate` below mirrors that): group by ONE key column, fold `(column, "sum" | "count" | "min" | "max")` per group.
+        Result frame: the key column, then one column per aggregate named `<fn>_<column>`; groups in ascending key order,
+        the null key last (bdf_group_aggregate_dev)."""
+        from .functions import group_aggregate
+
+        names = list(OrderedDict.fromkeys(c for c, _ in aggregates))
+        keys, res = group_aggregate(self.column(key), [self.column(c) for c in names])
+        out: "OrderedDict[str, Column]" = OrderedDict([(key, keys)])
+        used = set()
+        for cname, fn in aggregates:
+            r = res[names.index(cname)]
+            if fn not in ("sum", "count", "min", "max"):
+                raise N.UnsupportedType(f"aggregate {fn!r} is not on the path")
+            if r[fn] is None:
+                raise N.UnsupportedType("min/max need T::Native: Ord (integers only)")
+            out[f"{fn}_{cname}"] = r[fn]
+            used.add(id(r[fn]))
+        for r in res:   # aggregates nobody asked for
+            for c in r.values():
+                if c is not None and id(c) not in used:
+                    c.free()
+        return DeviceFrame(out)
+
     def limit(self, count: int) -> "DeviceFrame":
         if not self.columns:
             return self

@@ -143,3 +143,26 @@ def test_group_aggregate_shapes(rdf, ctx, oracle):
     assert np.array_equal(res3[0]["sum"].download()[0].value_slice()[perm_keys], vals)   # group of key k holds the row whose key is k
     with pytest.raises(rdf.ComputeError):
         rdf.group_aggregate(one, [empty])   # different lengths
+
+
+@pytest.mark.gpu
+def test_device_frame_group_aggregate(rdf, ctx):
+    """DeviceFrame.group_aggregate against pandas' groupby on the same columns (and the evaluator still mirrors the reference's panic)."""
+    import pandas as pd
+
+    rng = np.random.default_rng(9)
+    n = 100_000
+    k = rng.integers(0, 40, n).astype(np.int64)
+    x = rng.integers(-1000, 1000, n).astype(np.int32)
+    y = rng.uniform(-1, 1, n)
+    frame = rdf.DeviceFrame.from_host({"k": [rdf.PrimitiveArray.from_numpy(k)], "x": [rdf.PrimitiveArray.from_numpy(x)],
+                                       "y": [rdf.PrimitiveArray.from_numpy(y)]}, ctx=ctx)
+    g = frame.group_aggregate("k", [("x", "sum"), ("x", "max"), ("y", "sum"), ("y", "count")]).to_host()
+    want = pd.DataFrame({"k": k, "x": x, "y": y}).groupby("k").agg(sum_x=("x", "sum"), max_x=("x", "max"), sum_y=("y", "sum"), count_y=("y", "count"))
+    assert np.array_equal(g["k"][0].value_slice(), want.index.to_numpy())
+    assert np.array_equal(g["sum_x"][0].value_slice(), want["sum_x"].to_numpy().astype(np.int32))
+    assert np.array_equal(g["max_x"][0].value_slice(), want["max_x"].to_numpy())
+    assert np.allclose(g["sum_y"][0].value_slice(), want["sum_y"].to_numpy(), rtol=0, atol=1e-9)
+    assert np.array_equal(g["count_y"][0].value_slice(), want["count_y"].to_numpy())
+    with pytest.raises(rdf.ReferencePanic):
+        frame.evaluate([("group_aggregate", None)])
