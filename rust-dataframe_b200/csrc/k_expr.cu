@@ -13,6 +13,7 @@
 // register accumulator; the input tiles and up to two temporaries staged in shared memory (see k_expr).
 #include "common.cuh"
 
+#include <cstdlib>
 #include <vector>
 
 namespace bdf {
@@ -364,6 +365,248 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
     if (divzero) atomicOr(flags, 1);
 }
 
+// ---- the all-Float64 chain with bulk asynchronous copies (1-D TMA) and two stages per CTA ------------------------------------
+// k_expr above loads a tile, waits, computes: loads and math of ONE CTA never overlap, only the 3 CTAs of an SM overlap each
+// other (ncu round 2: arithmetic chain DRAM 67 %, occupancy 36 %).  Here a CTA walks its tiles in HALF tiles (1024 rows = 8 KiB per
+// input) through two shared-memory stages: while the warps interpret the program over stage s, ONE thread has already asked the
+// copy engine for the next half tile into stage s ^ 1 (`cp.async.bulk.shared.global`, UBLKCP in SASS, completion counted in
+// bytes on an mbarrier), so no lane spends issue slots on 16-byte LDGSTS and the next tile is always in flight.  The layout of a
+// stage is the one k_expr uses ([slot][j][thread] 16-byte pairs == the half tile's rows in order), so a bulk copy of
+// U * 256 * 16 bytes per input drops in.  Partial half tiles at the end of a chunk are filled by the threads themselves.
+constexpr int kBulkU = 2;   // half tile = 256 threads x 2 vectors x 2 rows = 1024 rows
+
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+    const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+    unsigned done = 0;
+    while (!done) {
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                     : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    }
+}
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gsrc, unsigned bytes, unsigned long long* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+
+template <bool AGG>
+__global__ void __launch_bounds__(kThreads, 2)
+k_expr_bulk(const ExprDesc* __restrict__ descs, int n_chunks, long long total_tiles, const ExprProg prog, uint32_t* __restrict__ warp_counts,
+            int* __restrict__ flags, AggDev* __restrict__ tile_partials) {
+    constexpr int U = kBulkU, E = 2;
+    constexpr int HALF = kThreads * U * E;             // rows per half tile
+    constexpr int TILE = kThreads * kExprUnroll * E;   // rows per tile, as the host numbers them
+    constexpr int SLOT = U * kThreads;                 // 16-byte pairs per slot
+    constexpr uint32_t ALL = (1u << (U * E)) - 1u;
+    extern __shared__ __align__(128) unsigned char expr_smem[];
+    const int ni = prog.n_inputs, nt = prog.n_slots - ni;
+    const int tid = threadIdx.x;
+    Vec<double, 2>* stage[2];
+    stage[0] = reinterpret_cast<Vec<double, 2>*>(expr_smem);
+    stage[1] = stage[0] + (size_t)ni * SLOT;
+    Vec<double, 2>* temps = stage[1] + (size_t)ni * SLOT;
+    uint32_t* sm = reinterpret_cast<uint32_t*>(temps + (size_t)nt * SLOT);   // [slot][thread] validity bits of the current half tile
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(sm + (size_t)prog.n_slots * kThreads);
+    int* s_full = reinterpret_cast<int*>(bar + 2);                           // was stage s filled by the copy engine?
+    __shared__ unsigned int s_cnt[kWarpsPerCta];
+    __shared__ FusedAgg<double> s_agg[kWarpsPerCta];
+
+    if (tid == 0) {
+        mbar_init(&bar[0], 1); mbar_init(&bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const long long my_tiles = (total_tiles - (long long)blockIdx.x + (long long)gridDim.x - 1) / (long long)gridDim.x;   // blockIdx.x < total_tiles
+    const long long n_half = my_tiles * 2;
+    auto tile_of = [&](long long q) { return (long long)blockIdx.x + (q >> 1) * (long long)gridDim.x; };
+    // thread 0: start the copies of half tile q into stage s (or note that the threads must fill it themselves)
+    auto issue = [&](long long q, int s) {
+        const long long tile = tile_of(q);
+        const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+        const ExprDesc& d = descs[c];
+        const long long base = (tile - d.tile0) * TILE + (q & 1) * HALF;
+        const bool full = base + HALF <= d.len;
+        s_full[s] = full ? 1 : 0;
+        if (full) {
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // the stage was read through the generic proxy a moment ago
+            mbar_expect_tx(&bar[s], (unsigned)(ni * SLOT * 16));
+            for (int i = 0; i < ni; i++) bulk_g2s(stage[s] + (size_t)i * SLOT, (const char*)d.in[i] + base * 8, SLOT * 16, &bar[s]);
+        }
+    };
+    if (tid == 0 && n_half > 0) issue(0, 0);
+    __syncthreads();
+
+    unsigned phase[2] = {0u, 0u};
+    unsigned int nvalid = 0;
+    FusedAgg<double> agg;
+    if constexpr (AGG) agg.init();
+    bool divzero = false;
+#pragma unroll 1
+    for (long long q = 0; q < n_half; q++) {
+        const int s = (int)(q & 1);
+        if (tid == 0 && q + 1 < n_half) issue(q + 1, s ^ 1);   // stage s ^ 1 was released by the barrier that ended iteration q - 1
+        const long long tile = tile_of(q);
+        const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+        const ExprDesc& d = descs[c];
+        const long long len = d.len;
+        const long long base = (tile - d.tile0) * TILE + (q & 1) * HALF;
+        const long long e_first = base + (long long)tid * E;
+        double* __restrict__ po = d.out;
+        uint32_t* __restrict__ vo = d.vout;
+        const bool full = s_full[s] != 0;
+        Vec<double, 2>* in_stage = stage[s];
+        auto slot_ptr = [&](int slot) { return slot < ni ? in_stage + (size_t)slot * SLOT : temps + (size_t)(slot - ni) * SLOT; };
+        if (full) {
+            // validity words first (they are in flight while the thread waits for the copy engine)
+            for (int i = 0; i < ni; i++) {
+                uint32_t m = ALL;
+                const uint32_t* vin = d.vin[i];
+                if (vin) {
+                    MaskRaw<E, U> r;
+                    mask_issue<E, U>(r, vin, d.off[i] + e_first, (int64_t)kThreads * E);
+                    m = 0;
+#pragma unroll
+                    for (int j = 0; j < U; j++) m |= mask_get<E, U>(r, j) << (j * E);
+                }
+                sm[i * kThreads + tid] = m;
+            }
+            mbar_wait(&bar[s], phase[s]);
+            phase[s] ^= 1u;
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < ni; i++) {
+                uint32_t m = 0;
+#pragma unroll
+                for (int j = 0; j < U; j++) {
+                    const long long e0 = e_first + (long long)j * kThreads * E;
+                    uint32_t in_range = tail_mask<E>(e0, len);
+                    Vec<double, 2> x;
+                    x.e[0] = 0.0; x.e[1] = 0.0;
+                    if (in_range) {
+#pragma unroll
+                        for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) x.e[e] = ((const double*)d.in[i])[e0 + e];
+                        if (d.vin[i]) in_range &= load_bits<E>(d.vin[i], d.off[i] + e0);
+                    }
+                    in_stage[(i * U + j) * kThreads + tid] = x;
+                    m |= in_range << (j * E);
+                }
+                sm[i * kThreads + tid] = m;
+            }
+        }
+
+        Vec<double, 2> acc[U];
+        uint32_t am = 0;
+#pragma unroll
+        for (int j = 0; j < U; j++) { acc[j].e[0] = 0.0; acc[j].e[1] = 0.0; }
+#pragma unroll 1
+        for (int k = 0; k < prog.n_ins; k++) {
+            const int op = prog.op[k], src = prog.src[k];
+            if (op >= XI_UN) {
+                expr_dispatch_unary<U>(op - XI_UN, acc, am);
+            } else if (op == XI_STORE) {
+                Vec<double, 2>* t = slot_ptr(src);
+#pragma unroll
+                for (int j = 0; j < U; j++) t[j * kThreads + tid] = acc[j];
+                sm[src * kThreads + tid] = am;
+            } else {
+                Vec<double, 2> o[U];
+                uint32_t om = am;
+                if (src == kOperandAcc) {
+#pragma unroll
+                    for (int j = 0; j < U; j++) o[j] = acc[j];
+                } else {
+                    const Vec<double, 2>* t = slot_ptr(src);
+#pragma unroll
+                    for (int j = 0; j < U; j++) o[j] = t[j * kThreads + tid];
+                    om = sm[src * kThreads + tid];
+                }
+                if (op == XI_LOAD) {
+#pragma unroll
+                    for (int j = 0; j < U; j++) acc[j] = o[j];
+                    am = om;
+                } else {
+                    const uint32_t ok = am & om;
+                    if (op >= XI_RBIN) expr_dispatch<U>(op - XI_RBIN, acc, o, acc, ok, divzero);
+                    else expr_dispatch<U>(op, acc, acc, o, ok, divzero);
+                    am = ok;
+                }
+            }
+        }
+
+#pragma unroll
+        for (int j = 0; j < U; j++) {
+            const long long e0 = e_first + (long long)j * kThreads * E;
+            const uint32_t in_range = full ? 3u : tail_mask<E>(e0, len);
+            const uint32_t okbits = (am >> (j * E)) & in_range;
+            Vec<double, E> r;
+#pragma unroll
+            for (int e = 0; e < E; e++) {
+                r.e[e] = ((okbits >> e) & 1u) ? acc[j].e[e] : 0.0;
+                if constexpr (AGG) agg.add(r.e[e], (okbits >> e) & 1u, 0ull);
+            }
+            if (po) {
+                if (full) r.store(po + e0);
+                else {
+#pragma unroll
+                    for (int e = 0; e < E; e++) if ((in_range >> e) & 1u) po[e0 + e] = r.e[e];
+                }
+            }
+            if (vo) store_bits<E>(vo, e0, okbits, in_range != 0);
+            if (vo || AGG) nvalid += __popc(okbits);
+        }
+        __syncthreads();   // every warp is done with stage s (and with the temporaries): thread 0 may refill it next iteration
+
+        if (q & 1) {       // second half: the host's tile is complete -> its per-warp valid counts and its aggregate partial
+            if (vo || AGG) {
+                const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+                if ((tid & 31) == 0 && vo) warp_counts[tile * kWarpsPerCta + (tid >> 5)] = wvalid;
+                if constexpr (AGG) {
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) agg.merge_shfl(o);
+                    if ((tid & 31) == 0) { s_cnt[tid >> 5] = wvalid; s_agg[tid >> 5] = agg; }
+                    __syncthreads();
+                    if (tid == 0) {
+                        FusedAgg<double> t = s_agg[0];
+                        unsigned long long total = s_cnt[0];
+#pragma unroll
+                        for (int w = 1; w < kWarpsPerCta; w++) { t.merge(s_agg[w]); total += s_cnt[w]; }
+                        t.store(&tile_partials[tile], total);
+                    }
+                    agg.init();
+                }
+            }
+            nvalid = 0;
+        }
+    }
+    if (divzero) atomicOr(flags, 1);
+}
+
+static size_t expr_bulk_smem(const ExprProg& p) {
+    const size_t slot = (size_t)kBulkU * kThreads * 16;
+    return (size_t)(2 * p.n_inputs + (p.n_slots - p.n_inputs)) * slot + (size_t)p.n_slots * kThreads * 4 + 2 * 8 + 2 * 4 + 16;
+}
+
+template <bool AGG>
+static cudaError_t launch_expr_bulk(const ExprDesc* dd, int n_chunks, int64_t tiles, const ExprProg& pp, uint32_t* warp_counts, int* flags,
+                                    AggDev* tile_partials, int sm_count, cudaStream_t s) {
+    constexpr int kMaxSmem = (2 * kExprMaxInputs + kExprMaxTemps) * kBulkU * kThreads * 16 + (kExprMaxInputs + kExprMaxTemps) * kThreads * 4 + 64;
+    static const cudaError_t attr = cudaFuncSetAttribute(k_expr_bulk<AGG>, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem);
+    if (attr != cudaSuccess) return attr;
+    const size_t smem = expr_bulk_smem(pp);
+    int per_sm = (int)((size_t)(227 * 1024) / (smem + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);   // 96-104 registers: two CTAs per SM
+    int64_t grid = (int64_t)sm_count * per_sm;
+    if (grid > tiles) grid = tiles;
+    k_expr_bulk<AGG><<<(unsigned)grid, kThreads, smem, s>>>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials);
+    return cudaGetLastError();
+}
+
 int expr_tile_elems() { return kThreads * kExprUnroll * 2; }
 int expr_max_inputs() { return kExprMaxInputs; }
 int expr_max_nodes() { return kExprMaxNodes; }
@@ -473,6 +716,13 @@ cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const vo
     const ExprProg& pp = *(const ExprProg*)prog;
     bool typed = false;
     for (int i = 0; i < pp.n_inputs; i++) typed = typed || pp.in_dtype[i] != T_F64;
+    static const bool use_bulk = [] { const char* e = getenv("BDF_EXPR_BULK"); return !(e && e[0] == '0'); }();
+    if (!typed && use_bulk) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (tile_partials) return launch_expr_bulk<true>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, sms, s);
+        return launch_expr_bulk<false>(dd, n_chunks, tiles, pp, warp_counts, flags, nullptr, sms, s);
+    }
     if (tile_partials) {
         if (typed) return launch_expr_u<kExprUnroll, kExprMinCtas, true, true>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
         return launch_expr_u<kExprUnroll, kExprMinCtas, true, false>(dd, n_chunks, tiles, pp, warp_counts, flags, tile_partials, s);
