@@ -365,7 +365,7 @@ k_expr(const ExprDesc* __restrict__ descs, int n_chunks, const ExprProg prog, ui
     if (divzero) atomicOr(flags, 1);
 }
 
-// ---- the all-Float64 chain with bulk asynchronous copies (1-D TMA) and two stages per CTA ------------------------------------
+// ---- EXPERIMENT (not the default, see launch_expr): the all-Float64 chain with bulk asynchronous copies (1-D TMA) -------------
 // k_expr above loads a tile, waits, computes: loads and math of ONE CTA never overlap, only the 3 CTAs of an SM overlap each
 // other (ncu round 2: arithmetic chain DRAM 67 %, occupancy 36 %).  Here a CTA walks its tiles in HALF tiles (1024 rows = 8 KiB per
 // input) through two shared-memory stages: while the warps interpret the program over stage s, ONE thread has already asked the
@@ -716,7 +716,11 @@ cudaError_t launch_expr(const void* descs, int n_chunks, int64_t tiles, const vo
     const ExprProg& pp = *(const ExprProg*)prog;
     bool typed = false;
     for (int i = 0; i < pp.n_inputs; i++) typed = typed || pp.in_dtype[i] != T_F64;
-    static const bool use_bulk = [] { const char* e = getenv("BDF_EXPR_BULK"); return !(e && e[0] == '0'); }();
+    // Off by default: measured slower than k_expr on B200 (round 2, profiles/r2_expr_bulk_probe.log: arithmetic chain 0.913 vs
+    // 0.710 ms, sin chain 1.166 vs 0.860, a + b 0.62 vs 0.42 at 1e8 rows) -- two CTAs of 96-104 registers per SM, one block barrier
+    // per half tile and a single stage of look-ahead (32-64 KiB in flight per SM) lose to three independent cp.async CTAs.  Kept
+    // for the next iteration (deeper pipeline / warp-specialised producer); BDF_EXPR_BULK=1 selects it, results are identical.
+    static const bool use_bulk = [] { const char* e = getenv("BDF_EXPR_BULK"); return e && e[0] == '1'; }();
     if (!typed && use_bulk) {
         int dev = 0, sms = 148;
         if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
