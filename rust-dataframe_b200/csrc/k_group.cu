@@ -11,8 +11,10 @@
 //   k_group_reduce  one warp per group: lane l folds rows start + l, start + l + 32, ... in order, then a fixed xor-shuffle
 //                   tree: deterministic (no atomics on values), integers wrap like AggregateFunctions::sum, floats are
 //                   accumulated in double like K4.  sum / count always exist; min / max (integers: T::Native: Ord) are
-//                   NULL for a group without a valid value.  A group of tens of millions of rows is one warp's work --
-//                   correct, slow; splitting giant groups over warps is the obvious next step and is not done.
+//                   NULL for a group without a valid value.  A group of more than kBigGroup rows is not folded by its warp:
+//                   the warp registers it in a work list and k_group_big folds it one CTA per 64 Ki-row segment (thread-strided
+//                   fold + fixed block tree), k_group_big_finish then folds a group's segment partials in segment order --
+//                   still deterministic, and a single hot key is spread over the whole GPU instead of one warp.
 #include "common.cuh"
 
 namespace bdf {
@@ -41,15 +43,104 @@ k_group_heads(const T* __restrict__ key, const uint32_t* __restrict__ kvalid, lo
     if ((threadIdx.x & 31) == 0 && i < n) head_words[i >> 5] = w;
 }
 
+// Hot keys.  The work list lives in device memory: {counters, list[]} then the segment partials.
+constexpr long long kBigGroup = 65536;   // rows a single warp still folds itself; also the segment length of k_group_big
+struct BigGroup { unsigned long long g, begin, end; unsigned int seg0, n_seg; };
+struct BigWork { unsigned int n_groups, n_segments; BigGroup list[1]; };   // list[capacity] follows
+
+template <typename T>
+__device__ __forceinline__ void group_write(const FusedAgg<T>& a, unsigned long long cnt, long long g, T* out_sum, long long* out_count, T* out_min,
+                                            T* out_max, uint32_t* mm_valid, unsigned long long flip) {
+    out_count[g] = (long long)cnt;
+    if constexpr (IsFloat<T>::value) {
+        out_sum[g] = (T)a.sum;
+    } else {
+        using U = typename UnsignedOf<T>::type;
+        out_sum[g] = (T)(U)a.sum;   // wrapping
+        if (out_min) {
+            out_min[g] = cnt ? (T)(U)(a.kmin ^ flip) : (T)0;
+            out_max[g] = cnt ? (T)(U)(a.kmax ^ flip) : (T)0;
+            if (cnt) atomicOr(&mm_valid[g >> 5], 1u << (g & 31));
+        }
+    }
+}
+
+template <typename T> struct GroupFlip {
+    static constexpr unsigned long long value = IsFloat<T>::value ? 0ull : (((T)-1 < (T)0) ? (1ull << (8 * sizeof(T) - 1)) : 0ull);
+};
+
+// One CTA per (hot group, segment): thread t folds rows begin + t, begin + t + 256, ... of the segment, then warp trees, then the
+// warps in order -> partial[seg0 + segment].  The grid is fixed; CTAs walk the work items (the counters are only known on the device).
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_group_big(const T* __restrict__ val, const uint32_t* __restrict__ vvalid, const BigWork* __restrict__ big, FusedAgg<T>* __restrict__ part,
+            unsigned long long* __restrict__ part_cnt) {
+    __shared__ FusedAgg<T> s_a[kWarpsPerCta];
+    __shared__ unsigned long long s_c[kWarpsPerCta];
+    const unsigned int n_big = big->n_groups, n_seg = big->n_segments;
+    for (unsigned int w = blockIdx.x; w < n_seg; w += gridDim.x) {
+        unsigned int gi = 0;
+        while (gi < n_big && !(big->list[gi].seg0 <= w && w < big->list[gi].seg0 + big->list[gi].n_seg)) gi++;   // a handful of hot groups
+        if (gi == n_big) continue;
+        const BigGroup bg = big->list[gi];
+        const long long b = (long long)bg.begin + (long long)(w - bg.seg0) * kBigGroup;
+        const long long e = min((long long)bg.end, b + kBigGroup);
+        FusedAgg<T> a;
+        a.init();
+        unsigned long long cnt = 0;
+        for (long long i = b + threadIdx.x; i < e; i += kThreads) {
+            const bool ok = vvalid ? ((vvalid[i >> 5] >> (i & 31)) & 1u) : true;
+            a.add(val[i], ok, GroupFlip<T>::value);
+            cnt += ok ? 1ull : 0ull;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { a.merge_shfl(o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+        __syncthreads();   // the previous work item's readers are done with the shared arrays
+        if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_c[threadIdx.x >> 5] = cnt; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            FusedAgg<T> t = s_a[0];
+            unsigned long long total = s_c[0];
+#pragma unroll
+            for (int k = 1; k < kWarpsPerCta; k++) { t.merge(s_a[k]); total += s_c[k]; }
+            part[w] = t;
+            part_cnt[w] = total;
+        }
+    }
+}
+
+// One thread per hot group: its segment partials in segment order.
+template <typename T>
+__global__ void k_group_big_finish(const BigWork* __restrict__ big, const FusedAgg<T>* __restrict__ part, const unsigned long long* __restrict__ part_cnt,
+                                   T* __restrict__ out_sum, long long* __restrict__ out_count, T* __restrict__ out_min, T* __restrict__ out_max,
+                                   uint32_t* __restrict__ mm_valid) {
+    const unsigned int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (gi >= big->n_groups) return;
+    const BigGroup bg = big->list[gi];
+    FusedAgg<T> a = part[bg.seg0];
+    unsigned long long cnt = part_cnt[bg.seg0];
+    for (unsigned int k = 1; k < bg.n_seg; k++) { a.merge(part[bg.seg0 + k]); cnt += part_cnt[bg.seg0 + k]; }
+    group_write<T>(a, cnt, (long long)bg.g, out_sum, out_count, out_min, out_max, mm_valid, GroupFlip<T>::value);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
 k_group_reduce(const T* __restrict__ val, const uint32_t* __restrict__ vvalid, const uint32_t* __restrict__ starts, long long n_groups,
                long long n_rows, T* __restrict__ out_sum, long long* __restrict__ out_count, T* __restrict__ out_min, T* __restrict__ out_max,
-               uint32_t* __restrict__ mm_valid) {
+               uint32_t* __restrict__ mm_valid, BigWork* __restrict__ big) {
     const long long g = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
     if (g >= n_groups) return;
     const int lane = threadIdx.x & 31;
     const long long b = starts[g], e = g + 1 < n_groups ? (long long)starts[g + 1] : n_rows;
+    if (big && e - b > kBigGroup) {   // a hot key: leave it to k_group_big (one CTA per segment)
+        if (lane == 0) {
+            const unsigned int nseg = (unsigned int)((e - b + kBigGroup - 1) / kBigGroup);
+            const unsigned int slot = atomicAdd(&big->n_groups, 1u);
+            const unsigned int base = atomicAdd(&big->n_segments, nseg);
+            big->list[slot] = BigGroup{(unsigned long long)g, (unsigned long long)b, (unsigned long long)e, base, nseg};
+        }
+        return;
+    }
     FusedAgg<T> a;
     a.init();
     unsigned long long cnt = 0;
@@ -61,20 +152,7 @@ k_group_reduce(const T* __restrict__ val, const uint32_t* __restrict__ vvalid, c
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { a.merge_shfl(o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) {
-        out_count[g] = (long long)cnt;
-        if constexpr (IsFloat<T>::value) {
-            out_sum[g] = (T)a.sum;
-        } else {
-            using U = typename UnsignedOf<T>::type;
-            out_sum[g] = (T)(U)a.sum;   // wrapping
-            if (out_min) {
-                out_min[g] = cnt ? (T)(U)(a.kmin ^ flip) : (T)0;
-                out_max[g] = cnt ? (T)(U)(a.kmax ^ flip) : (T)0;
-                if (cnt) atomicOr(&mm_valid[g >> 5], 1u << (g & 31));
-            }
-        }
-    }
+    if (lane == 0) group_write<T>(a, cnt, g, out_sum, out_count, out_min, out_max, mm_valid, flip);
 }
 
 template <typename T>
@@ -97,29 +175,47 @@ cudaError_t launch_group_heads(int dtype, const void* key, const uint32_t* kvali
     }
 }
 
+size_t group_big_scratch_bytes(long long n_rows) {   // work list + segment partials for any distribution of n_rows rows
+    const size_t max_groups = (size_t)(n_rows / kBigGroup) + 2, max_segs = 2 * max_groups + 2;
+    return 64 + max_groups * sizeof(BigGroup) + max_segs * (sizeof(FusedAgg<long long>) + 8) + 256;
+}
+
 template <typename T>
 static cudaError_t reduce_one(const void* val, const uint32_t* vvalid, const uint32_t* starts, long long n_groups, long long n_rows, void* sum,
-                              long long* count, void* mn, void* mx, uint32_t* mm_valid, cudaStream_t s) {
+                              long long* count, void* mn, void* mx, uint32_t* mm_valid, void* scratch, int sm_count, cudaStream_t s) {
+    BigWork* big = (BigWork*)scratch;
+    cudaError_t e = cudaMemsetAsync(big, 0, 8, s);   // the two counters
+    if (e != cudaSuccess) return e;
     k_group_reduce<T><<<(unsigned)((n_groups + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, 0, s>>>((const T*)val, vvalid, starts, n_groups, n_rows, (T*)sum,
-                                                                                                    count, (T*)mn, (T*)mx, mm_valid);
+                                                                                                    count, (T*)mn, (T*)mx, mm_valid, big);
+    if (n_rows > kBigGroup) {   // hot keys are possible: the two follow-up kernels find nothing to do when there are none
+        const size_t max_groups = (size_t)(n_rows / kBigGroup) + 2, max_segs = 2 * max_groups + 2;
+        char* p = (char*)scratch + 64 + max_groups * sizeof(BigGroup);
+        p = (char*)(((uintptr_t)p + 15) & ~(uintptr_t)15);
+        FusedAgg<T>* part = (FusedAgg<T>*)p;
+        unsigned long long* part_cnt = (unsigned long long*)(p + max_segs * sizeof(FusedAgg<long long>));
+        k_group_big<T><<<(unsigned)(sm_count * 4), kThreads, 0, s>>>((const T*)val, vvalid, big, part, part_cnt);
+        k_group_big_finish<T><<<(unsigned)((max_groups + 127) / 128), 128, 0, s>>>(big, part, part_cnt, (T*)sum, count, (T*)mn, (T*)mx, mm_valid);
+    }
     return cudaGetLastError();
 }
 
+// scratch: group_big_scratch_bytes(n_rows) of device memory.
 cudaError_t launch_group_reduce(int dtype, const void* val, const uint32_t* vvalid, const uint32_t* starts, long long n_groups, long long n_rows,
-                                void* sum, long long* count, void* mn, void* mx, uint32_t* mm_valid, cudaStream_t s) {
+                                void* sum, long long* count, void* mn, void* mx, uint32_t* mm_valid, void* scratch, int sm_count, cudaStream_t s) {
     if (n_groups <= 0) return cudaSuccess;
     if (n_groups > 0x7fffffffLL * kWarpsPerCta) return cudaErrorInvalidConfiguration;
     switch (dtype) {
-        case T_I8: return reduce_one<int8_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_I16: return reduce_one<int16_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_I32: return reduce_one<int32_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_I64: return reduce_one<int64_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_U8: return reduce_one<uint8_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_U16: return reduce_one<uint16_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_U32: return reduce_one<uint32_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_U64: return reduce_one<uint64_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_F32: return reduce_one<float>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
-        case T_F64: return reduce_one<double>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, s);
+        case T_I8: return reduce_one<int8_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_I16: return reduce_one<int16_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_I32: return reduce_one<int32_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_I64: return reduce_one<int64_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_U8: return reduce_one<uint8_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_U16: return reduce_one<uint16_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_U32: return reduce_one<uint32_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_U64: return reduce_one<uint64_t>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_F32: return reduce_one<float>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
+        case T_F64: return reduce_one<double>(val, vvalid, starts, n_groups, n_rows, sum, count, mn, mx, mm_valid, scratch, sm_count, s);
         default: return cudaErrorInvalidValue;
     }
 }

@@ -1804,7 +1804,8 @@ static int take_dev(bdf_ctx* c, const bdf_col* values, const bdf_col* indices, b
 namespace bdf {
 cudaError_t launch_group_heads(int dtype, const void* key, const uint32_t* kvalid, long long n, uint32_t* words, cudaStream_t s);
 cudaError_t launch_group_reduce(int dtype, const void* val, const uint32_t* vvalid, const uint32_t* starts, long long n_groups, long long n_rows,
-                                void* sum, long long* count, void* mn, void* mx, uint32_t* mm_valid, cudaStream_t s);
+                                void* sum, long long* count, void* mn, void* mx, uint32_t* mm_valid, void* scratch, int sm_count, cudaStream_t s);
+size_t group_big_scratch_bytes(long long n_rows);
 }  // namespace bdf
 
 static int group_aggregate_dev(bdf_ctx* c, const bdf_col* key, int n_values, const bdf_col* const* values, bdf_col** out_keys,
@@ -1872,9 +1873,14 @@ static int group_aggregate_dev(bdf_ctx* c, const bdf_col* key, int n_values, con
         {
             const int w = dtype_width(dt);
             LaunchTimer t(c, BDF_K_GROUP, dt, n, n * w + (sval->chunks[0].validity ? bitmap_bytes(n) : 0) + n_groups * (4 + (is_float ? 1 : 3) * w + 8));
-            e = launch_group_reduce(dt, sval->chunks[0].values, sval->chunks[0].validity, (const uint32_t*)starts->chunks[0].values, n_groups, n,
-                                    csum->chunks[0].values, (long long*)ccnt->chunks[0].values, cmin ? cmin->chunks[0].values : nullptr,
-                                    cmax ? cmax->chunks[0].values : nullptr, cmin ? cmin->chunks[0].validity : nullptr, c->s_compute);
+            void* scratch = nullptr;
+            e = cudaMallocAsync(&scratch, group_big_scratch_bytes(n), c->s_compute);
+            c->launches += 2;   // hot keys: k_group_big + k_group_big_finish
+            if (e == cudaSuccess)
+                e = launch_group_reduce(dt, sval->chunks[0].values, sval->chunks[0].validity, (const uint32_t*)starts->chunks[0].values, n_groups, n,
+                                        csum->chunks[0].values, (long long*)ccnt->chunks[0].values, cmin ? cmin->chunks[0].values : nullptr,
+                                        cmax ? cmax->chunks[0].values : nullptr, cmin ? cmin->chunks[0].validity : nullptr, scratch, c->sm_count, c->s_compute);
+            if (scratch) cudaFreeAsync(scratch, c->s_compute);
         }
         // max shares min's validity pattern: copy the bitmap rather than set it twice with atomics
         if (e == cudaSuccess && cmin && n_groups)

@@ -166,3 +166,38 @@ def test_device_frame_group_aggregate(rdf, ctx):
     assert np.array_equal(g["count_y"][0].value_slice(), want["count_y"].to_numpy())
     with pytest.raises(rdf.ReferencePanic):
         frame.evaluate([("group_aggregate", None)])
+
+
+@pytest.mark.gpu
+def test_group_aggregate_hot_keys(rdf, ctx, oracle):
+    """Skew: two hot keys (hundreds of thousands of rows each: folded by k_group_big, one CTA per 64 Ki-row segment) among many
+    small groups, nullable values and keys; integers exact, floats within the sum tolerance and bit-reproducible."""
+    rng = np.random.default_rng(21)
+    n = 1_500_000
+    k = rng.integers(0, 5000, n).astype(np.int64)
+    hot = rng.random(n)
+    k[hot < 0.45] = 17
+    k[(hot >= 0.45) & (hot < 0.6)] = -3
+    km = rng.random(n) >= 0.02
+    vi = rng.integers(np.iinfo(np.int64).min, np.iinfo(np.int64).max, n, dtype=np.int64, endpoint=True)
+    vf = rng.uniform(-1e3, 1e3, n)
+    vm = rng.random(n) >= 0.1
+    lens = [700_000, 800_000]
+    kch, ich, fch = _chunks(rdf, k, km, lens), _chunks(rdf, vi, vm, lens), _chunks(rdf, vf, None, lens)
+    ck, ci, cf = rdf.Column.upload(kch, ctx=ctx), rdf.Column.upload(ich, ctx=ctx), rdf.Column.upload(fch, ctx=ctx)
+    keys, res = rdf.group_aggregate(ck, [ci, cf])
+    okeys, okvalid, wi = oracle.group_aggregate(kch, ich)
+    _, _, wf = oracle.group_aggregate(kch, fch)
+    gk, gkv, _ = _col_values(keys)
+    assert np.array_equal(gkv, okvalid) and np.array_equal(gk[gkv], okeys[okvalid])
+    assert wi["count"].max() > 400_000                                   # the hot key really is hot
+    assert np.array_equal(_col_values(res[0]["count"])[0], wi["count"])
+    assert np.array_equal(_col_values(res[0]["sum"])[0], wi["sum"])
+    for key in ("min", "max"):
+        g, gv, _ = _col_values(res[0][key])
+        assert np.array_equal(gv, wi[key][1]) and np.array_equal(g[gv], wi[key][0][wi[key][1]])
+    fs = _col_values(res[1]["sum"])[0]
+    exact, mag = wf["exact"]
+    assert np.all(np.abs(fs.astype(np.longdouble) - exact) <= 16 * np.log2(np.maximum(wf["count"], 2)) * 2.0 ** -53 * mag + 1e-300)
+    keys2, res2 = rdf.group_aggregate(ck, [cf])
+    assert np.array_equal(_col_values(res2[0]["sum"])[0].view(np.uint64), fs.view(np.uint64))   # same bits every run
