@@ -13,6 +13,9 @@
 //      (each lane compacts its E bits, the 32/E lanes of a word OR them together) and OR-ed into the output
 //      bitmap with at most two atomics per 32 input slots.
 // Roofline: HBM, w x (1 + selectivity) + bitmaps bytes/row for the scatter; 16 B/row for a compare.
+#include <cmath>
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace bdf {
@@ -395,12 +398,121 @@ static cudaError_t cmp_one(const BinDesc* d, int n, int64_t tiles, int ta, int t
     return cudaGetLastError();
 }
 
+// ---- compare an integer column of at most 32 bits with a SCALAR: no Float64 arithmetic at all --------------------------------
+// `cast(x, Float64) OP s` with x an integer is a statement about integers: x > s <=> x >= floor(s) + 1, x >= s <=> x >= ceil(s),
+// x < s <=> x <= ceil(s) - 1, x <= s <=> x <= floor(s), x == s <=> s is integral and x == s (a NaN scalar compares false, != true).
+// The host turns (op, s) into a closed range [lo, hi] of T (possibly empty) and a negate flag; the kernel is then a range test on
+// 8 elements per lane (one or two 16-byte loads), against 2 elements per lane, an I2F.F64 and a DSETP per element in k_compare --
+// the generic kernel ran an Int32 column at 0.33 of the roofline (conversion-issue bound).  Null slots compare as 0, the cast's payload.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+k_compare_int(const BinDesc* __restrict__ descs, int n_chunks, long long lo64, long long hi64, int negate, uint32_t* __restrict__ warp_counts) {
+    constexpr int E = 8;
+    constexpr int TILE = kThreads * E;   // == compare_tile_elems(): the host's tile numbering and count layout stay as they are
+    using C = typename std::conditional<((T)-1 < (T)0), int, unsigned int>::type;
+    const C lo = (C)lo64, hi = (C)hi64;
+    const int64_t tile = blockIdx.x;
+    const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
+    const T* __restrict__ pa = (const T*)descs[c].a;
+    uint32_t* __restrict__ po = (uint32_t*)descs[c].out;
+    const uint32_t* __restrict__ va = descs[c].va;
+    uint32_t* __restrict__ vo = descs[c].vout;
+    const int64_t len = descs[c].len, offa = descs[c].offa;
+    const int64_t base = (tile - descs[c].tile0) * TILE;
+    const int64_t e0 = base + (int64_t)threadIdx.x * E;
+    const uint32_t in_range = tail_mask<E>(e0, len);
+    uint32_t m = in_range;
+    T v[E];
+    if (in_range == 0xffu) {
+        if constexpr (sizeof(T) == 4) {
+            const uint4 q0 = ld_stream16(pa + e0), q1 = ld_stream16(pa + e0 + 4);
+            v[0] = (T)q0.x; v[1] = (T)q0.y; v[2] = (T)q0.z; v[3] = (T)q0.w; v[4] = (T)q1.x; v[5] = (T)q1.y; v[6] = (T)q1.z; v[7] = (T)q1.w;
+        } else if constexpr (sizeof(T) == 2) {
+            const uint4 q = ld_stream16(pa + e0);
+            v[0] = (T)(q.x & 0xffffu); v[1] = (T)(q.x >> 16); v[2] = (T)(q.y & 0xffffu); v[3] = (T)(q.y >> 16);
+            v[4] = (T)(q.z & 0xffffu); v[5] = (T)(q.z >> 16); v[6] = (T)(q.w & 0xffffu); v[7] = (T)(q.w >> 16);
+        } else {
+            const uint2 q = ld_stream8(pa + e0);
+#pragma unroll
+            for (int e = 0; e < 4; e++) { v[e] = (T)((q.x >> (8 * e)) & 0xffu); v[4 + e] = (T)((q.y >> (8 * e)) & 0xffu); }
+        }
+    } else {
+#pragma unroll
+        for (int e = 0; e < E; e++) v[e] = ((in_range >> e) & 1u) ? pa[e0 + e] : (T)0;
+    }
+    if (va && in_range) m &= load_bits<E>(va, offa + e0);
+    uint32_t bits = 0;
+#pragma unroll
+    for (int e = 0; e < E; e++) {
+        const C x = (C)(((m >> e) & 1u) || !va ? v[e] : (T)0);   // a null slot compares as the cast's payload, 0
+        const bool in = (x >= lo) & (x <= hi);
+        bits |= ((in ? 1u : 0u) ^ (unsigned)negate) << e;
+    }
+    bits &= in_range;
+    store_bits<E>(po, e0, bits, in_range != 0);
+    unsigned int nvalid = 0;
+    if (vo) {
+        store_bits<E>(vo, e0, m, in_range != 0);
+        nvalid = __popc(m);
+        const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
+        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+    }
+}
+
+// (op, scalar) -> [lo, hi] within T's range (lo > hi: empty) + negate.  Returns false when the column type has no integer fast path.
+static bool compare_int_plan(int op, int ta, double s, long long* lo, long long* hi, int* negate) {
+    double tmin, tmax;
+    switch (ta) {
+        case T_I8: tmin = -128.0; tmax = 127.0; break;
+        case T_I16: tmin = -32768.0; tmax = 32767.0; break;
+        case T_I32: tmin = -2147483648.0; tmax = 2147483647.0; break;
+        case T_U8: tmin = 0.0; tmax = 255.0; break;
+        case T_U16: tmin = 0.0; tmax = 65535.0; break;
+        case T_U32: tmin = 0.0; tmax = 4294967295.0; break;
+        default: return false;
+    }
+    *negate = 0;
+    double lod = tmin, hid = tmax;
+    bool empty = false;
+    if (s != s) { empty = true; *negate = op == CMP_NE; }
+    else switch (op) {
+        case CMP_GT: lod = floor(s) + 1.0; break;
+        case CMP_GE: lod = ceil(s); break;
+        case CMP_LT: hid = ceil(s) - 1.0; break;
+        case CMP_LE: hid = floor(s); break;
+        default:   // EQ / NE
+            if (floor(s) == s && s >= tmin && s <= tmax) { lod = s; hid = s; } else empty = true;
+            *negate = op == CMP_NE;
+            break;
+    }
+    if (lod > tmax || hid < tmin || lod > hid) empty = true;
+    if (empty) { *lo = 1; *hi = 0; return true; }
+    *lo = (long long)(lod < tmin ? tmin : lod);
+    *hi = (long long)(hid > tmax ? tmax : hid);
+    return true;
+}
+
 int compare_tile_elems() { return kThreads * kUnroll * 2; }
+static_assert(kThreads * kUnroll * 2 == kThreads * 8, "k_compare_int walks the host's compare tiles");
 
 cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, int ta, int tb, bool scalar_rhs, double scalar, uint32_t* wc,
                            cudaStream_t s) {
     if (tiles <= 0) return cudaSuccess;
     if (tiles > 0x7fffffffLL) return cudaErrorInvalidConfiguration;
+    long long lo = 0, hi = 0;
+    int negate = 0;
+    if (scalar_rhs && op >= CMP_GT && op <= CMP_LE && compare_int_plan(op, ta, scalar, &lo, &hi, &negate)) {
+        const unsigned g = (unsigned)tiles;
+        switch (ta) {
+            case T_I8: k_compare_int<int8_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            case T_I16: k_compare_int<int16_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            case T_I32: k_compare_int<int32_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            case T_U8: k_compare_int<uint8_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            case T_U16: k_compare_int<uint16_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            default: k_compare_int<uint32_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+        }
+        return cudaGetLastError();
+    }
     switch (op) {
         case CMP_GT: return cmp_one<CMP_GT>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);
         case CMP_GE: return cmp_one<CMP_GE>(d, n, tiles, ta, tb, scalar_rhs, scalar, wc, s);

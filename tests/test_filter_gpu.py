@@ -154,3 +154,28 @@ def test_lazy_filter_pipeline_1e8(rdf, ctx, oracle):
     assert kcount == count and all(g.null_count == 0 for g in got)   # nulls never pass `f > 0`: the mask is null there
     assert abs(np.longdouble(ksum) - exact) <= 16 * np.log2(1e8) * 2.0 ** -53 * sum_abs
     assert 0.4 < sum(g.length for g in got) / 1e8 < 0.5
+
+
+@pytest.mark.parametrize("ltype", ["I8", "I16", "I32", "U8", "U16", "U32"])
+def test_integer_column_against_scalar_fast_path(rdf, ctx, oracle, ltype):
+    """k_compare_int: `cast(x, Float64) OP s` decided in the integer domain.  Every scalar that can trip the floor / ceil / clamp
+    logic: fractions either side of zero, values at and beyond the type's range, infinities, NaN, signed zero."""
+    lt = getattr(rdf, ltype)
+    npdt = rdf.NP_DTYPES[lt]
+    info = np.iinfo(npdt)
+    rng = np.random.default_rng(lt + 77)
+    scalars = [0.0, -0.0, 3.0, 2.5, -2.5, -3.0, 0.49, float(info.max), float(info.min), info.max + 0.5, info.min - 0.5, float(info.max) + 1, float(info.min) - 1,
+               1e10, -1e10, np.inf, -np.inf, np.nan, 126.999999, 65534.5]
+    for null_frac, sliced in ((0, False), (0.25, True)):
+        a = make_col(rdf, rng, lt, RAGGED, null_frac, sliced)
+        edge = np.array([info.min, info.max, 0, 1, 2, 3, info.max - 1, min(info.min + 1, info.max)], dtype=npdt)
+        a[-1].values[a[-1].offset:a[-1].offset + len(edge)] = edge   # the values the scalars sit next to
+        ca = rdf.Column.upload(a)
+        for s in scalars:
+            for op in range(6):
+                got = ca.compare(op, s).download()
+                for i, g in enumerate(got):
+                    st, want = oracle.compare(op, a[i], None, scalar=s)
+                    assert st == oracle.OK
+                    check_bool(g, want, f"{ltype} op{op} scalar {s!r} chunk {i} nulls={null_frac}")
+        ca.free()
