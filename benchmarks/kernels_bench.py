@@ -172,6 +172,28 @@ def main():
     sidx = rdf.sort_indices([(a, False)])
     report("take f64 by the sort indices (random gather)", "sort", timed(ctx, lambda: b.take(sidx), reps=4), "take")
     report("take i32 10% nulls by the sort indices", "sort", timed(ctx, lambda: i32n.take(sidx), reps=4), "take")
+    # ---- group-by aggregate: sort the key, gather key and value, head bitmap, two compactions, one warp per group ----
+    def group_total(key, val, what):
+        res = timed(ctx, lambda: _free_group(rdf.group_aggregate(key, [val])), reps=3)
+        total = sum(v[0] for v in res.values())
+        print(f"{what:44s} {total:8.4f} ms  (" + ", ".join(f"{k} {v[0]:.3f}" for k, v in sorted(res.items())) + ")", flush=True)
+        rows_out.append({"case": what, "config": "group", "kernel": "sort + take + filter + group", "ms": total, "rows": args.rows, "parts": {k: v[0] for k, v in res.items()}})
+
+    def _free_group(r):
+        keys, res = r
+        keys.free()
+        for d in res:
+            for c in d.values():
+                if c is not None:
+                    c.free()
+        return None
+
+    kf = G(rdf.F64, lens, 0, -100.0, 100.0, col_id=22)
+    small = kf.cast(rdf.I8)                                        # 200 distinct keys: every group is a hot key (k_group_big)
+    kf.free()
+    group_total(small, a, "group-by i8 key (200 groups), sum f64")
+    group_total(i32n, i64n, "group-by i32 key (~1e8 groups), i64 4-in-1")
+    small.free()
     if args.json:
         with open(args.json, "w") as f:
             json.dump({"rows": args.rows, "peak_GBs_measured": pk, "results": rows_out}, f, indent=1)

@@ -404,14 +404,19 @@ static cudaError_t cmp_one(const BinDesc* d, int n, int64_t tiles, int ta, int t
 // The host turns (op, s) into a closed range [lo, hi] of T (possibly empty) and a negate flag; the kernel is then a range test on
 // 8 elements per lane (one or two 16-byte loads), against 2 elements per lane, an I2F.F64 and a DSETP per element in k_compare --
 // the generic kernel ran an Int32 column at 0.33 of the roofline (conversion-issue bound).  Null slots compare as 0, the cast's payload.
+constexpr int kCmpIntTiles = 4;
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-k_compare_int(const BinDesc* __restrict__ descs, int n_chunks, long long lo64, long long hi64, int negate, uint32_t* __restrict__ warp_counts) {
+k_compare_int(const BinDesc* __restrict__ descs, int n_chunks, long long total_tiles, long long lo64, long long hi64, int negate,
+              uint32_t* __restrict__ warp_counts) {
     constexpr int E = 8;
     constexpr int TILE = kThreads * E;   // == compare_tile_elems(): the host's tile numbering and count layout stay as they are
     using C = typename std::conditional<((T)-1 < (T)0), int, unsigned int>::type;
     const C lo = (C)lo64, hi = (C)hi64;
-    const int64_t tile = blockIdx.x;
+#pragma unroll 1
+    for (int kk = 0; kk < kCmpIntTiles; kk++) {   // a tile is only 2-8 KiB of input here: several per CTA
+    const int64_t tile = (int64_t)blockIdx.x * kCmpIntTiles + kk;
+    if (tile >= total_tiles) break;
     const int c = (n_chunks == 1) ? 0 : find_chunk(descs, n_chunks, tile);
     const T* __restrict__ pa = (const T*)descs[c].a;
     uint32_t* __restrict__ po = (uint32_t*)descs[c].out;
@@ -455,7 +460,8 @@ k_compare_int(const BinDesc* __restrict__ descs, int n_chunks, long long lo64, l
         store_bits<E>(vo, e0, m, in_range != 0);
         nvalid = __popc(m);
         const unsigned int wvalid = __reduce_add_sync(0xffffffffu, nvalid);
-        if ((threadIdx.x & 31) == 0) warp_counts[(int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+        if ((threadIdx.x & 31) == 0) warp_counts[tile * kWarpsPerCta + (threadIdx.x >> 5)] = wvalid;
+    }
     }
 }
 
@@ -502,14 +508,14 @@ cudaError_t launch_compare(int op, const BinDesc* d, int n, int64_t tiles, int t
     long long lo = 0, hi = 0;
     int negate = 0;
     if (scalar_rhs && op >= CMP_GT && op <= CMP_LE && compare_int_plan(op, ta, scalar, &lo, &hi, &negate)) {
-        const unsigned g = (unsigned)tiles;
+        const unsigned g = (unsigned)((tiles + kCmpIntTiles - 1) / kCmpIntTiles);
         switch (ta) {
-            case T_I8: k_compare_int<int8_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
-            case T_I16: k_compare_int<int16_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
-            case T_I32: k_compare_int<int32_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
-            case T_U8: k_compare_int<uint8_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
-            case T_U16: k_compare_int<uint16_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
-            default: k_compare_int<uint32_t><<<g, kThreads, 0, s>>>(d, n, lo, hi, negate, wc); break;
+            case T_I8: k_compare_int<int8_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
+            case T_I16: k_compare_int<int16_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
+            case T_I32: k_compare_int<int32_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
+            case T_U8: k_compare_int<uint8_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
+            case T_U16: k_compare_int<uint16_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
+            default: k_compare_int<uint32_t><<<g, kThreads, 0, s>>>(d, n, tiles, lo, hi, negate, wc); break;
         }
         return cudaGetLastError();
     }
