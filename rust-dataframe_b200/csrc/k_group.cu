@@ -60,7 +60,7 @@ __device__ __forceinline__ void group_write(const FusedAgg<T>& a, unsigned long 
         if (out_min) {
             out_min[g] = cnt ? (T)(U)(a.kmin ^ flip) : (T)0;
             out_max[g] = cnt ? (T)(U)(a.kmax ^ flip) : (T)0;
-            if (cnt) atomicOr(&mm_valid[g >> 5], 1u << (g & 31));
+            if (cnt && mm_valid) atomicOr(&mm_valid[g >> 5], 1u << (g & 31));
         }
     }
 }
@@ -123,36 +123,58 @@ __global__ void k_group_big_finish(const BigWork* __restrict__ big, const FusedA
     group_write<T>(a, cnt, (long long)bg.g, out_sum, out_count, out_min, out_max, mm_valid, GroupFlip<T>::value);
 }
 
-template <typename T>
+// LANES lanes per group (32, 8 or 1 -- the launcher picks by the average group length, so ~1e8 one-row groups do not spend a
+// warp each).  No lane leaves before the shuffles: a sub-group that is past the end, or defers its group, folds an empty range.
+template <typename T, int LANES>
 __global__ void __launch_bounds__(kThreads)
 k_group_reduce(const T* __restrict__ val, const uint32_t* __restrict__ vvalid, const uint32_t* __restrict__ starts, long long n_groups,
                long long n_rows, T* __restrict__ out_sum, long long* __restrict__ out_count, T* __restrict__ out_min, T* __restrict__ out_max,
                uint32_t* __restrict__ mm_valid, BigWork* __restrict__ big) {
-    const long long g = (long long)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5);
-    if (g >= n_groups) return;
-    const int lane = threadIdx.x & 31;
-    const long long b = starts[g], e = g + 1 < n_groups ? (long long)starts[g + 1] : n_rows;
-    if (big && e - b > kBigGroup) {   // a hot key: leave it to k_group_big (one CTA per segment)
-        if (lane == 0) {
+    constexpr int kGroupsPerWarp = 32 / LANES;
+    const long long t = (long long)blockIdx.x * kThreads + threadIdx.x;
+    const long long g = t / LANES;
+    const int sub = threadIdx.x & (LANES - 1);
+    bool mine = g < n_groups;
+    long long b = 0, e = 0;
+    if (mine) { b = starts[g]; e = g + 1 < n_groups ? (long long)starts[g + 1] : n_rows; }
+    if (mine && big && e - b > kBigGroup) {   // a hot key: leave it to k_group_big (one CTA per segment)
+        if (sub == 0) {
             const unsigned int nseg = (unsigned int)((e - b + kBigGroup - 1) / kBigGroup);
             const unsigned int slot = atomicAdd(&big->n_groups, 1u);
             const unsigned int base = atomicAdd(&big->n_segments, nseg);
             big->list[slot] = BigGroup{(unsigned long long)g, (unsigned long long)b, (unsigned long long)e, base, nseg};
         }
-        return;
+        mine = false;
+        e = b;
     }
     FusedAgg<T> a;
     a.init();
     unsigned long long cnt = 0;
-    constexpr unsigned long long flip = IsFloat<T>::value ? 0ull : (((T)-1 < (T)0) ? (1ull << (8 * sizeof(T) - 1)) : 0ull);
-    for (long long i = b + lane; i < e; i += 32) {
+    constexpr unsigned long long flip = GroupFlip<T>::value;
+    for (long long i = b + sub; i < e; i += LANES) {
         const bool ok = vvalid ? ((vvalid[i >> 5] >> (i & 31)) & 1u) : true;
         a.add(val[i], ok, flip);
         cnt += ok ? 1ull : 0ull;
     }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) { a.merge_shfl(o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
-    if (lane == 0) group_write<T>(a, cnt, g, out_sum, out_count, out_min, out_max, mm_valid, flip);
+    for (int o = LANES / 2; o > 0; o >>= 1) { a.merge_shfl(o); cnt += __shfl_xor_sync(0xffffffffu, cnt, o); }
+    const bool writer = mine && sub == 0;
+    if (writer) group_write<T>(a, cnt, g, out_sum, out_count, out_min, out_max, nullptr, flip);
+    if constexpr (!IsFloat<T>::value) {
+        if (out_min) {   // min/max validity: the warp's groups share one bitmap word -> one store (LANES == 1) or one atomic per warp
+            const unsigned bal = __ballot_sync(0xffffffffu, writer && cnt != 0);
+            if ((threadIdx.x & 31) == 0) {
+                const long long g0 = (t >> 5) * kGroupsPerWarp;
+                if (g0 < n_groups) {
+                    unsigned word = 0;
+#pragma unroll
+                    for (int j = 0; j < kGroupsPerWarp; j++) word |= ((bal >> (j * LANES)) & 1u) << (((unsigned)g0 + j) & 31u);
+                    if (LANES == 1) mm_valid[g0 >> 5] = word;   // hot groups of this word are OR-ed in later by k_group_big_finish
+                    else if (word) atomicOr(&mm_valid[g0 >> 5], word);
+                }
+            }
+        }
+    }
 }
 
 template <typename T>
@@ -186,8 +208,12 @@ static cudaError_t reduce_one(const void* val, const uint32_t* vvalid, const uin
     BigWork* big = (BigWork*)scratch;
     cudaError_t e = cudaMemsetAsync(big, 0, 8, s);   // the two counters
     if (e != cudaSuccess) return e;
-    k_group_reduce<T><<<(unsigned)((n_groups + kWarpsPerCta - 1) / kWarpsPerCta), kThreads, 0, s>>>((const T*)val, vvalid, starts, n_groups, n_rows, (T*)sum,
-                                                                                                    count, (T*)mn, (T*)mx, mm_valid, big);
+    const long long avg = n_rows / n_groups;   // lanes per group by the average group length
+    const int lanes = avg > 64 ? 32 : avg > 4 ? 8 : 1;
+    const unsigned grid = (unsigned)((n_groups * lanes + kThreads - 1) / kThreads);
+    if (lanes == 32) k_group_reduce<T, 32><<<grid, kThreads, 0, s>>>((const T*)val, vvalid, starts, n_groups, n_rows, (T*)sum, count, (T*)mn, (T*)mx, mm_valid, big);
+    else if (lanes == 8) k_group_reduce<T, 8><<<grid, kThreads, 0, s>>>((const T*)val, vvalid, starts, n_groups, n_rows, (T*)sum, count, (T*)mn, (T*)mx, mm_valid, big);
+    else k_group_reduce<T, 1><<<grid, kThreads, 0, s>>>((const T*)val, vvalid, starts, n_groups, n_rows, (T*)sum, count, (T*)mn, (T*)mx, mm_valid, big);
     if (n_rows > kBigGroup) {   // hot keys are possible: the two follow-up kernels find nothing to do when there are none
         const size_t max_groups = (size_t)(n_rows / kBigGroup) + 2, max_segs = 2 * max_groups + 2;
         char* p = (char*)scratch + 64 + max_groups * sizeof(BigGroup);

@@ -59,7 +59,10 @@ def test_oracle_group_aggregate_matches_pyarrow(oracle):
 
 
 CASES = [("int32", "int64", 200, 0.05, 0.1), ("float64", "float64", 50, 0.0, 0.2), ("int8", "int16", 300, 0.1, 0.0),
-         ("uint64", "uint32", 7, 0.0, 0.5), ("float32", "int8", 1000, 0.02, 0.05), ("int64", "float32", 3, 0.3, 0.0)]
+         ("uint64", "uint32", 7, 0.0, 0.5), ("float32", "int8", 1000, 0.02, 0.05), ("int64", "float32", 3, 0.3, 0.0),
+         # short groups: 8 lanes per group (average 4..64 rows), one lane per group (average <= 4 rows)
+         ("int32", "int32", 20_000, 0.05, 0.3), ("int64", "int64", 400_000, 0.0, 0.4), ("uint64", "float64", 100_000, 0.1, 0.1),
+         ("int16", "uint8", 30_000, 0.0, 0.6)]
 
 
 @pytest.mark.gpu
@@ -201,3 +204,29 @@ def test_group_aggregate_hot_keys(rdf, ctx, oracle):
     assert np.all(np.abs(fs.astype(np.longdouble) - exact) <= 16 * np.log2(np.maximum(wf["count"], 2)) * 2.0 ** -53 * mag + 1e-300)
     keys2, res2 = rdf.group_aggregate(ck, [cf])
     assert np.array_equal(_col_values(res2[0]["sum"])[0].view(np.uint64), fs.view(np.uint64))   # same bits every run
+
+
+@pytest.mark.gpu
+def test_group_aggregate_one_hot_key_among_singletons(rdf, ctx, oracle):
+    """Almost every key is its own group (one lane per group) and ONE key owns 100k rows (deferred to k_group_big): the min/max
+    validity word the hot group shares with 31 singleton groups is written by both kernels."""
+    rng = np.random.default_rng(5)
+    n = 600_000
+    k = rng.permutation(n).astype(np.int64)
+    k[rng.choice(n, 100_000, replace=False)] = 300_001
+    v = rng.integers(-2 ** 40, 2 ** 40, n).astype(np.int64)
+    vm = rng.random(n) >= 0.5
+    lens = [n]
+    kch, vch = _chunks(rdf, k, None, lens), _chunks(rdf, v, vm, lens)
+    ck, cv = rdf.Column.upload(kch, ctx=ctx), rdf.Column.upload(vch, ctx=ctx)
+    keys, res = rdf.group_aggregate(ck, [cv])
+    okeys, okvalid, want = oracle.group_aggregate(kch, vch)
+    gk, gkv, _ = _col_values(keys)
+    assert np.array_equal(gk, okeys) and gkv.all()
+    assert want["count"].max() > 40_000
+    assert np.array_equal(_col_values(res[0]["count"])[0], want["count"])
+    assert np.array_equal(_col_values(res[0]["sum"])[0], want["sum"])
+    for key in ("min", "max"):
+        g, gv, arr = _col_values(res[0][key])
+        assert np.array_equal(gv, want[key][1]) and np.array_equal(g[gv], want[key][0][want[key][1]])
+        assert arr.null_count == int((~want[key][1]).sum())
