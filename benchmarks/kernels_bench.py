@@ -147,6 +147,14 @@ def main():
     report("sum/min/max/count i8 full range, 10% nulls", "extra", timed(ctx, lambda: i8v.aggregate_all()), "reduce")
     report("sum/min/max/count i16 full range, 10% nulls", "extra", timed(ctx, lambda: i16v.aggregate_all()), "reduce")
     report("sum/min/max/count u16, no nulls", "extra", timed(ctx, lambda: u16.aggregate_all()), "reduce")
+    # the same kernels over as many BYTES as the f64 rows move (1e8 i8 rows are 0.11 GB: 17 us at the copy peak, launch-sized)
+    big_lens = [32_000_000] * max(1, args.rows * 8 // 32_000_000)
+    i8big = G(rdf.I8, big_lens, 2, col_id=27, null_mod=10)
+    report("sum/min/max/count i8 10% nulls, 8x the rows", "extra", timed(ctx, lambda: i8big.aggregate_all()), "reduce")
+    i8big.free()
+    i16big = G(rdf.I16, big_lens[: len(big_lens) // 2], 2, col_id=28, null_mod=10)
+    report("sum/min/max/count i16 10% nulls, 4x the rows", "extra", timed(ctx, lambda: i16big.aggregate_all()), "reduce")
+    i16big.free()
     report("sum/min/max/count i32 full range, 10% nulls", "extra", timed(ctx, lambda: i32n.aggregate_all()), "reduce")
     for col in (i8b, i8v, i16v, u16):
         col.free()

@@ -11,7 +11,7 @@
 // null flag moves the nulls behind the valid rows without disturbing either group.
 //
 // Pass structure (per 8-bit digit): k_radix_hist (per-CTA digit counts over the CTA's contiguous range of tiles) ->
-// k_radix_scan (one CTA, exclusive scan in digit-major order) -> k_radix_scatter (per tile: warp-level match_any ranks,
+// k_radix_scan (one CTA, exclusive scan in digit-major order) -> k_radix_scatter (per tile: warp-level peer masks from per-bit ballots -> ranks,
 // reorder through shared memory, write each digit's run contiguously).  A digit on which every key agrees is skipped:
 // k_sort_keys also folds the OR and the AND of the keys it builds.
 // HBM traffic per executed pass: 8 (hist) + 12 + 12 B/row with 64-bit keys, 4 + 8 + 8 with 32-bit keys (criteria of at most
@@ -175,6 +175,22 @@ __global__ void __launch_bounds__(1024) k_radix_scan(unsigned int* __restrict__ 
     for (int64_t i = begin; i < end; i++) { const unsigned int v = data[i]; data[i] = run; run += v; }
 }
 
+// Lanes of the warp holding the same 9-bit value (digit, or 256 for "not a key"): one ballot per bit instead of MATCH.ANY.  ncu
+// showed the scatter kernel bound by the pipe that executes MATCH (sm__inst_executed_pipe_adu 73 % with eight MATCH.ANY per thread
+// and tile; profiles/r2_ncu_n2_n3_sort_take.csv) while the ALU sat at 13 %.  Nine VOTEs turned out to cost what one MATCH costs:
+// 1e8 rows, 32-bit keys 7.44 -> 7.02 ms, 64-bit keys 10.64 -> 10.99 ms (profiles/r2_sort_notes.log) -- so the ballots serve the
+// 32-bit instantiation and MATCH.ANY stays in the 64-bit one.
+__device__ __forceinline__ unsigned int digit_peers(unsigned int d) {
+    unsigned int peers = 0xffffffffu;
+#pragma unroll
+    for (int b = 0; b < 9; b++) {
+        const bool bit = (d >> b) & 1u;
+        const unsigned int m = __ballot_sync(0xffffffffu, bit);
+        peers &= bit ? m : ~m;
+    }
+    return peers;
+}
+
 // Stable scatter of the CTA's tiles.  Within a tile, warp w owns elements [w*256, (w+1)*256) as 8 rows of 32 lanes, so
 // (warp, row, lane) order is the input order; ranks come from match_any + per-warp digit counters.  Threads 0..255 own
 // one digit each in the counting phases.
@@ -215,7 +231,7 @@ k_radix_scatter(const K* __restrict__ keys_in, const uint32_t* __restrict__ idx_
             const int e = warp * (kSortItems * 32) + it * 32 + lane;
             const bool ok = e < in_tile;
             const unsigned int d = ok ? (unsigned int)((key[it] >> shift) & 0xff) : 256u;   // 256: not a key
-            const unsigned int peers = __match_any_sync(0xffffffffu, d);
+            const unsigned int peers = sizeof(K) == 4 ? digit_peers(d) : __match_any_sync(0xffffffffu, d);
             const int leader = __ffs(peers) - 1;
             unsigned int old = 0;
             if (lane == leader && ok) { old = s_cnt[warp][d]; s_cnt[warp][d] = old + __popc(peers); }
