@@ -95,11 +95,13 @@ class IpcFile:
         ``batches`` restricts the read to those RecordBatches (one rank's share: ``parallel.shard_indices``)."""
         from .functions import Column
 
-        ctx = ctx or N.default_context()
         if columns is None:
             idx = [i for i, (_, dt, _) in enumerate(self.schema) if dt >= 0]
         else:
             idx = [self.column_index(c) for c in columns]
+        if not idx:   # no column of a type on the path: an empty frame, not BDF_INVALID from the C side
+            return {}
+        ctx = ctx or N.default_context()
         arr = (C.c_int32 * len(idx))(*idx)
         outs = (C.c_void_p * len(idx))()
         flags = N.ASYNC if asynchronous else 0

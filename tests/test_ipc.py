@@ -451,3 +451,16 @@ def test_reader_bounds_schema_work(rdf, tmp_path):
             if patched >= 300:
                 return
     assert patched > 0
+
+
+def test_a_file_without_columns_on_the_path_is_an_empty_frame(rdf, tmp_path):
+    """Only Utf8 columns: nothing to read, so no device call is made at all (the C entry rejects n_cols == 0) -- works without a GPU."""
+    path = str(tmp_path / "strings.arrow")
+    table = pa.table({"city": pa.array(["Elgin", "Stoke-on-Trent", None]), "county": pa.array(["Moray", None, "x"])})
+    with pa.OSFile(path, "wb") as sink, pa.ipc.new_file(sink, table.schema) as w:
+        w.write_table(table)
+    with rdf.IpcFile(path) as f:
+        assert [dt for _, dt, _ in f.schema] == [-1, -1]
+        assert f.read() == {}
+    frame = rdf.DeviceFrame.from_arrow(path)
+    assert list(frame.columns) == []
