@@ -55,21 +55,37 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-class ClockSampler(threading.Thread):
-    """Polls NVML for SM clock and throttle reasons while the timed region runs."""
+def _nvml_index(cuda_index: int) -> int:
+    """CUDA ordinal -> NVML index when CUDA_VISIBLE_DEVICES is a plain list of integers (otherwise the ordinal itself)."""
+    cvd = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+    try:
+        ids = [int(x) for x in cvd.split(",") if x.strip() != ""]
+        return ids[cuda_index] if cuda_index < len(ids) else cuda_index
+    except ValueError:
+        return cuda_index
 
-    def __init__(self, device_index: int):
+
+class ClockSampler(threading.Thread):
+    """Polls NVML for SM clock and throttle reasons while the timed region runs.  ONE poller per job: rank 0 watches every GPU of
+    the job (eight processes polling NVML at once starved each other: one sample in 140 ms at N = 8); the other ranks pass []."""
+
+    def __init__(self, device_indices):
         super().__init__(daemon=True)
-        self.samples = []
+        self.samples = []          # (time, [mhz per GPU], OR of the reasons)
         self.stop_flag = False
         self.ok = False
+        self.err = "not polled on this rank (rank 0 watches every GPU of the job)"
+        self.handles = []
+        if not device_indices:
+            return
         try:
             import pynvml
 
             pynvml.nvmlInit()
             self.nv = pynvml
-            self.h = pynvml.nvmlDeviceGetHandleByIndex(device_index)
-            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            for d in device_indices:
+                self.handles.append(pynvml.nvmlDeviceGetHandleByIndex(_nvml_index(int(d))))
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.handles[0], pynvml.NVML_CLOCK_SM)
             self.ok = True
         except Exception as e:  # pragma: no cover
             self.err = str(e)
@@ -80,8 +96,10 @@ class ClockSampler(threading.Thread):
         nv = self.nv
         while not self.stop_flag:
             try:
-                mhz = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
-                reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                mhz, reasons = [], 0
+                for h in self.handles:
+                    mhz.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                    reasons |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(h))
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
@@ -89,7 +107,7 @@ class ClockSampler(threading.Thread):
 
     def summary(self, t0: float, t1: float):
         if not self.ok:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: " + str(self.err)]}
         nv = self.nv
         win = [s for s in self.samples if t0 <= s[0] <= t1] or self.samples[-3:]
         names = {
@@ -104,8 +122,12 @@ class ClockSampler(threading.Thread):
             for bit, name in names.items():
                 if r & bit:
                     seen.add(name)
-        return {"sm_mhz": float(np.median([s[1] for s in win])) if win else None, "sm_max_mhz": float(self.max_mhz),
-                "reasons": sorted(seen), "samples": len(win)}
+        every = [m for s in win for m in s[1]]
+        out = {"sm_mhz": float(np.median(every)) if every else None, "sm_max_mhz": float(self.max_mhz),
+               "reasons": sorted(seen), "samples": len(win), "gpus_watched": len(self.handles)}
+        if len(self.handles) > 1 and win:
+            out["sm_mhz_per_gpu"] = [float(np.median([s[1][g] for s in win])) for g in range(len(self.handles))]
+        return out
 
 
 def bind_to_gpu_numa_node(device_index: int):
@@ -342,7 +364,7 @@ def run_gpu_arm(args, rank: int, world: int, local: int):
         ctx.comm_collective(True)
         tiny.free()
 
-    sampler = ClockSampler(local)
+    sampler = ClockSampler(list(range(world)) if rank == 0 else [])   # one node: the job's GPUs are local ranks 0..world-1
     sampler.start()
     ctx.profile_read()  # drop warm-up records
     ctx.profile_enable(True)
