@@ -31,6 +31,16 @@ pub enum BdfIpc {}   // a mapped Arrow IPC file
 #[repr(C)]
 pub struct BdfExprNode { pub op: i32, pub a: i32, pub b: i32 }   // op: bdf_binop, or BDF_EXPR_UNARY + bdf_unop
 pub const BDF_EXPR_UNARY: i32 = 100;
+/// bdf_group_out: per value column; `min` / `max` are NULL for Float columns (T::Native: Ord).
+#[repr(C)]
+#[derive(Clone, Copy)]
+pub struct BdfGroupOut {
+    pub sum: *mut BdfCol,
+    pub count: *mut BdfCol,
+    pub min: *mut BdfCol,
+    pub max: *mut BdfCol,
+}
+
 #[repr(C)]
 pub struct BdfSortKey { pub column: *const BdfCol, pub descending: i32 }
 pub const BDF_ASYNC: c_int = 1;
@@ -83,6 +93,9 @@ extern "C" {
     // DataFrame::sort
     pub fn bdf_sort_indices_dev(ctx: *mut BdfCtx, n_keys: i32, keys: *const BdfSortKey, indices: *mut *mut BdfCol) -> c_int;
     pub fn bdf_take_dev(ctx: *mut BdfCtx, values: *const BdfCol, indices: *const BdfCol, out: *mut *mut BdfCol) -> c_int;
+    // group-by aggregate (Transformation::GroupAggregate, src/evaluation.rs:73; planned shape src/expression.rs:114-221)
+    pub fn bdf_group_aggregate_dev(ctx: *mut BdfCtx, key: *const BdfCol, n_values: i32, values: *const *const BdfCol, out_keys: *mut *mut BdfCol,
+                                   out: *mut BdfGroupOut, n_groups: *mut i64) -> c_int;
     // Arrow IPC files (DataFrame::from_arrow / to_arrow)
     pub fn bdf_ipc_open(path: *const c_char, out: *mut *mut BdfIpc) -> c_int;
     pub fn bdf_ipc_close(file: *mut BdfIpc);

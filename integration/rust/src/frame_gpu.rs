@@ -1,4 +1,4 @@
-//! Device-resident frames: how `DataFrame::{from_arrow, to_arrow, sort}` and a fused run of Calculations map onto
+//! Device-resident frames: how `DataFrame::{from_arrow, to_arrow, sort}`, the group-by aggregate and a fused run of Calculations map onto
 //! libb200df.so.  UNCOMPILED here (see ../README.md); the same flow is exercised from Python in
 //! rust-dataframe_b200/frame.py (tests/test_frame.py, tests/test_ipc.py, tests/test_sort_gpu.py).
 use std::ffi::{CStr, CString};
@@ -77,6 +77,51 @@ pub fn sort_device(frame: &DeviceColumns, criteria: &[(usize, bool)]) -> Result<
         let mut taken: *mut BdfCol = std::ptr::null_mut();
         check(unsafe { bdf_take_dev(dev(), *c, idx.cols[0], &mut taken) })?;                            // sort_by_indices -> Column::take
         out.cols.push(taken);
+    }
+    Ok(out)
+}
+
+/// One aggregate of the plan `Dataset::try_aggregate` makes (src/expression.rs:114-221): the ones on this path.
+#[derive(Clone, Copy, PartialEq)]
+pub enum GroupFn { Sum, Count, Min, Max }
+
+/// `Transformation::GroupAggregate` (a `panic!("aggregations not supported")` in src/evaluation.rs:73): group by ONE key column,
+/// output = the key column, then `sum(x)` / `min(x)` / `max(x)` (type of x) or `count(x)` (UInt32) per requested aggregate -- the
+/// names and types of the planned schema.  Groups in ascending key order, the null key last.
+pub fn group_aggregate_device(frame: &DeviceColumns, key: usize, aggr: &[(usize, GroupFn)]) -> Result<DeviceColumns, String> {
+    const BDF_U32: i32 = 6;   // include/b200df.h bdf_dtype
+    let mut value_cols: Vec<usize> = vec![];
+    for (c, _) in aggr { if !value_cols.contains(c) { value_cols.push(*c); } }
+    let vals: Vec<*const BdfCol> = value_cols.iter().map(|c| frame.cols[*c] as *const BdfCol).collect();
+    let mut keys: *mut BdfCol = std::ptr::null_mut();
+    let mut n_groups = 0i64;
+    let null = std::ptr::null_mut();
+    let mut outs = vec![BdfGroupOut { sum: null, count: null, min: null, max: null }; vals.len()];
+    check(unsafe { bdf_group_aggregate_dev(dev(), frame.cols[key], vals.len() as i32, vals.as_ptr(), &mut keys, outs.as_mut_ptr(), &mut n_groups) })?;
+    // every column the library returned is owned by a guard from here on: the ones the plan did not ask for are dropped with it
+    let mut spare = DeviceColumns { names: vec![], cols: outs.iter().flat_map(|o| vec![o.sum, o.count, o.min, o.max]).collect() };
+    let mut out = DeviceColumns { names: vec![frame.names[key].clone()], cols: vec![keys] };
+    for (c, f) in aggr {
+        let j = value_cols.iter().position(|v| v == c).unwrap();
+        let slot = 4 * j + match f { GroupFn::Sum => 0, GroupFn::Count => 1, GroupFn::Min => 2, GroupFn::Max => 3 };
+        let col = spare.cols[slot];
+        if col.is_null() {
+            return Err("min/max need T::Native: Ord (integer columns), or the aggregate was requested twice".to_string());
+        }
+        let x = &frame.names[*c];
+        match f {
+            GroupFn::Count => {   // count(x) is planned as UInt32; group sizes are below 2^32 (row numbers are UInt32), the cast cannot fail
+                let mut c32: *mut BdfCol = std::ptr::null_mut();
+                check(unsafe { bdf_cast_dev(dev(), BDF_U32, col, &mut c32) })?;
+                out.names.push(format!("count({})", x));
+                out.cols.push(c32);
+            }
+            _ => {
+                spare.cols[slot] = null;   // moves to the result
+                out.names.push(format!("{}({})", match f { GroupFn::Sum => "sum", GroupFn::Min => "min", _ => "max" }, x));
+                out.cols.push(col);
+            }
+        }
     }
     Ok(out)
 }

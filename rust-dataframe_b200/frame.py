@@ -30,7 +30,7 @@ from typing import Dict, List, Optional, Sequence, Tuple, Union
 import numpy as np
 
 from . import _native as N
-from .arrays import F32, F64, I8, U8, PrimitiveArray, is_float
+from .arrays import F32, F64, I8, U8, U32, PrimitiveArray, is_float
 from .functions import Column, _expr_nodes, eval_expr, sort_indices
 from .ipc import BOOL, IpcFile, write_ipc
 
@@ -302,29 +302,48 @@ class DeviceFrame:
         idx = sort_indices([(self.column(c), d) for c, d in criteria])
         return DeviceFrame(OrderedDict((n, c.take(idx)) for n, c in self.columns.items()))
 
-    def group_aggregate(self, key: str, aggregates: Sequence[Tuple[str, str]]) -> "DeviceFrame":
+    def group_aggregate(self, groups, aggregates: Sequence[Tuple[str, str]]) -> "DeviceFrame":
         """What `Transformation::GroupAggregate` is meant to do (the reference's evaluator panics on it, src/evaluation.rs:73, and
-        `evaluate` below mirrors that): group by ONE key column, fold `(column, "sum" | "count" | "min" | "max")` per group.
-        Result frame: the key column, then one column per aggregate named `<fn>_<column>`; groups in ascending key order,
-        the null key last (bdf_group_aggregate_dev)."""
+        `evaluate` below mirrors that): group by ONE key column (`groups`: its name, or a one-element list like the reference's
+        `&[&str]`), fold `(column, "sum" | "count" | "min" | "max")` per group.  The result frame has the schema
+        `Dataset::try_aggregate` plans (src/expression.rs:114-221): the group column, then one column per aggregate named
+        `sum(x)` / `min(x)` / `max(x)` (type of x) or `count(x)` (UInt32); groups in ascending key order, the null key last
+        (bdf_group_aggregate_dev).  A missing column is the ComputeError of :121-126,140-145; the aggregates the plan lists but this
+        path does not compute (avg, first, last, count_distinct, ...) are UnsupportedType."""
         from .functions import group_aggregate
 
-        names = list(OrderedDict.fromkeys(c for c, _ in aggregates))
-        keys, res = group_aggregate(self.column(key), [self.column(c) for c in names])
-        out: "OrderedDict[str, Column]" = OrderedDict([(key, keys)])
-        used = set()
+        if not isinstance(groups, str):
+            groups = list(groups)
+            if len(groups) != 1:
+                raise N.UnsupportedType("group-by over one key column is on the path; got %d grouping columns" % len(groups))
+            groups = groups[0]
+        if groups not in self.columns:
+            raise N.ComputeError(f"Grouping column {groups!r} does not exist")
         for cname, fn in aggregates:
-            r = res[names.index(cname)]
+            if cname not in self.columns:
+                raise N.ComputeError(f"Aggregating column {cname!r} does not exist")
             if fn not in ("sum", "count", "min", "max"):
                 raise N.UnsupportedType(f"aggregate {fn!r} is not on the path")
-            if r[fn] is None:
-                raise N.UnsupportedType("min/max need T::Native: Ord (integers only)")
-            out[f"{fn}_{cname}"] = r[fn]
-            used.add(id(r[fn]))
-        for r in res:   # aggregates nobody asked for
-            for c in r.values():
-                if c is not None and id(c) not in used:
-                    c.free()
+        names = list(OrderedDict.fromkeys(c for c, _ in aggregates))
+        keys, res = group_aggregate(self.column(groups), [self.column(c) for c in names])
+        out: "OrderedDict[str, Column]" = OrderedDict([(groups, keys)])
+        used = set()
+        try:
+            for cname, fn in aggregates:
+                r = res[names.index(cname)]
+                if f"{fn}({cname})" in out:
+                    continue
+                if r[fn] is None:
+                    raise N.UnsupportedType("min/max need T::Native: Ord (integers only)")
+                # count(x) is planned as UInt32 (:169-173); a group never has 2^32 rows (row numbers are UInt32), so the cast cannot fail
+                out[f"{fn}({cname})"] = r[fn].cast(U32) if fn == "count" else r[fn]
+                if fn != "count":
+                    used.add(id(r[fn]))
+        finally:
+            for r in res:   # aggregates nobody asked for, and the Int64 counts behind count(x)
+                for c in r.values():
+                    if c is not None and id(c) not in used:
+                        c.free()
         return DeviceFrame(out)
 
     def limit(self, count: int) -> "DeviceFrame":

@@ -160,13 +160,24 @@ def test_device_frame_group_aggregate(rdf, ctx):
     y = rng.uniform(-1, 1, n)
     frame = rdf.DeviceFrame.from_host({"k": [rdf.PrimitiveArray.from_numpy(k)], "x": [rdf.PrimitiveArray.from_numpy(x)],
                                        "y": [rdf.PrimitiveArray.from_numpy(y)]}, ctx=ctx)
-    g = frame.group_aggregate("k", [("x", "sum"), ("x", "max"), ("y", "sum"), ("y", "count")]).to_host()
+    g = frame.group_aggregate(["k"], [("x", "sum"), ("x", "max"), ("y", "sum"), ("y", "count")])
+    assert list(g.columns) == ["k", "sum(x)", "max(x)", "sum(y)", "count(y)"]          # the schema Dataset::try_aggregate plans
+    assert g.schema["count(y)"] == rdf.U32 and g.schema["sum(x)"] == rdf.I32
+    g = g.to_host()
     want = pd.DataFrame({"k": k, "x": x, "y": y}).groupby("k").agg(sum_x=("x", "sum"), max_x=("x", "max"), sum_y=("y", "sum"), count_y=("y", "count"))
     assert np.array_equal(g["k"][0].value_slice(), want.index.to_numpy())
-    assert np.array_equal(g["sum_x"][0].value_slice(), want["sum_x"].to_numpy().astype(np.int32))
-    assert np.array_equal(g["max_x"][0].value_slice(), want["max_x"].to_numpy())
-    assert np.allclose(g["sum_y"][0].value_slice(), want["sum_y"].to_numpy(), rtol=0, atol=1e-9)
-    assert np.array_equal(g["count_y"][0].value_slice(), want["count_y"].to_numpy())
+    assert np.array_equal(g["sum(x)"][0].value_slice(), want["sum_x"].to_numpy().astype(np.int32))
+    assert np.array_equal(g["max(x)"][0].value_slice(), want["max_x"].to_numpy())
+    assert np.allclose(g["sum(y)"][0].value_slice(), want["sum_y"].to_numpy(), rtol=0, atol=1e-9)
+    assert np.array_equal(g["count(y)"][0].value_slice(), want["count_y"].to_numpy().astype(np.uint32))
+    with pytest.raises(rdf.ComputeError):
+        frame.group_aggregate("nope", [("x", "sum")])
+    with pytest.raises(rdf.ComputeError):
+        frame.group_aggregate("k", [("nope", "sum")])
+    with pytest.raises(rdf.UnsupportedType):
+        frame.group_aggregate("k", [("x", "avg")])
+    with pytest.raises(rdf.UnsupportedType):
+        frame.group_aggregate("k", [("y", "max")])                                      # T::Native: Ord
     with pytest.raises(rdf.ReferencePanic):
         frame.evaluate([("group_aggregate", None)])
 
