@@ -49,13 +49,18 @@ class Result {
     std::variant<T, ArrowError> v_;
 };
 
-// Process-wide context, created on first use (what the Rust shim keeps in a OnceCell).
+// Process-wide context, created on first use (what the Rust shim keeps in a Once, integration/rust/src/ffi.rs `ctx()`): ONE
+// context over every GPU of the box (bdf_init_multi: the library shards each call by row range, the job rayon's par_iter does in
+// src/functions/scalar.rs:28-31,99-102) -- unless a process-per-GPU launcher started this process (WORLD_SIZE > 1: GPU LOCAL_RANK,
+// the job is joined with bdf_comm_attach) or BDF_ONE_GPU is set.
 inline bdf_ctx* context() {
     static bdf_ctx* ctx = [] {
         bdf_ctx* c = nullptr;
+        const char* ws = std::getenv("WORLD_SIZE");
         const char* lr = std::getenv("LOCAL_RANK");
-        if (bdf_init(lr ? std::atoi(lr) : 0, &c) != BDF_OK)
-            throw std::runtime_error(std::string("bdf_init failed: ") + bdf_last_error());
+        const bool one = (ws && std::atoi(ws) > 1) || std::getenv("BDF_ONE_GPU");
+        const int st = one ? bdf_init(lr ? std::atoi(lr) : 0, &c) : bdf_init_multi(0, nullptr, &c);
+        if (st != BDF_OK) throw std::runtime_error(std::string("libb200df initialisation failed: ") + bdf_last_error());
         return c;
     }();
     return ctx;
