@@ -19,6 +19,10 @@
  *   bdf_*_dev       the same operators on device-resident columns, so a chain of Calculations
  *                   (src/evaluation.rs:66-96 evaluates one after another) uploads once and downloads once.
  *
+ * Threads: a context may be called from several threads; calls on one context are serialised (a one-GPU context by a lock around each
+ * entry, a multi-GPU context around each fan-out to its GPUs), so the reference's callers need no locking of their own -- but
+ * bdf_destroy must not race with another call, and a column or future handle belongs to the thread that is using it.
+ *
  * Error convention: every entry returns a bdf_status; BDF_OK == 0.  bdf_last_error() gives a
  * thread-local message.  No exception or abort crosses the ABI.  Mapping to the reference's errors:
  *   BDF_LENGTH_MISMATCH -> ArrowError::ComputeError("Cannot perform math operation on arrays of different length")

@@ -1928,6 +1928,7 @@ struct Fleet {
         std::string err;
     };
     std::vector<std::unique_ptr<Worker>> workers;
+    std::mutex run_mu;   // one fan-out at a time: two caller threads must not interleave their jobs (or the order of the kids' collectives)
 };
 
 static void fleet_worker_main(Fleet::Worker* w, int device) {
@@ -1980,6 +1981,7 @@ static void fleet_worker_main(Fleet::Worker* w, int device) {
 
 // Run fn(k) for every kid, each on its own thread, and wait.  The first failing status (lowest kid) is returned with its message.
 static int fleet_run(Fleet* f, const std::function<int(int)>& fn) {
+    std::lock_guard<std::mutex> one_at_a_time(f->run_mu);   // the jobs run on the workers and never fan out themselves: no recursion
     const int n = (int)f->kids.size();
     for (int k = 0; k < n; k++) {
         Fleet::Worker* w = f->workers[k].get();
