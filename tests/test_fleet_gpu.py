@@ -177,3 +177,37 @@ def test_generated_columns_are_the_same_rows_for_every_fleet_size(rdf, oracle, f
     for key, op in (("sum", oracle.SUM), ("min", oracle.MIN), ("max", oracle.MAX), ("count", oracle.COUNT)):
         assert int(agg[key]) == int(oracle.aggregate(op, oracle.I64, o)[1]), key
     col.free()
+
+
+def test_one_context_called_from_several_threads(rdf, oracle, fleet):
+    """The reference's callers may sit on different threads (rayon above the function library): calls on one context are
+    serialised by the library, results stay those of the oracle."""
+    import threading
+
+    lens = [30_000, 0, 64, 12_345]
+    work = []
+    for t in range(4):
+        a, b = _chunks(rdf, "int64", 100 + t, lens, 0.1), _chunks(rdf, "int64", 200 + t, lens, 0.0)
+        _, want = oracle.col_binary(oracle.ADD, oracle.I64, a, b)
+        nonempty = [c for c in a if c.length]
+        work.append((a, b, want, int(oracle.aggregate(oracle.SUM, oracle.I64, nonempty)[1]), nonempty))
+    errors = []
+
+    def run(t):
+        a, b, want, want_sum, nonempty = work[t]
+        try:
+            for _ in range(6):
+                got = rdf.ScalarFunctions.add(a, b, ctx=fleet)
+                for i, (g, w) in enumerate(zip(got, want)):
+                    assert_same_array(g, w, what=f"thread {t} chunk {i}")
+                assert int(rdf.AggregateFunctions.sum(nonempty, dtype=a[0].dtype, ctx=fleet)) == want_sum
+        except BaseException as e:   # noqa: BLE001 -- reported on the main thread
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=run, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join(timeout=120)
+    assert not errors, errors
+    assert not any(th.is_alive() for th in threads)
