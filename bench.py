@@ -103,7 +103,7 @@ class ClockSampler(threading.Thread):
                 self.samples.append((time.perf_counter(), mhz, reasons))
             except Exception:
                 pass
-            time.sleep(0.002)
+            time.sleep(0.01)   # ~15 samples over the 150 ms window; a tighter loop would compete with rank 0's hot loop for the GIL
 
     def summary(self, t0: float, t1: float):
         if not self.ok:
