@@ -241,3 +241,50 @@ def test_group_aggregate_one_hot_key_among_singletons(rdf, ctx, oracle):
         g, gv, arr = _col_values(res[0][key])
         assert np.array_equal(gv, want[key][1]) and np.array_equal(g[gv], want[key][0][want[key][1]])
         assert arr.null_count == int((~want[key][1]).sum())
+
+
+def test_oracle_group_aggregate_small_cases_against_pandas(oracle):
+    """Many tiny random shapes (empty, one row, all-null keys, all-null values, several chunks) of the numpy restatement against
+    pandas' groupby -- the checker of the GPU tests is itself checked on the shapes where off-by-one errors live."""
+    import pandas as pd
+    from hypothesis import given, settings, strategies as st
+
+    class Ch:
+        def __init__(self, values, mask):
+            self.values, self.offset, self.length, self._m = values, 0, len(values), mask
+
+        def valid_mask(self):
+            return self._m
+
+    @settings(max_examples=80, deadline=None)
+    @given(st.integers(0, 40), st.integers(1, 6), st.floats(0, 1), st.floats(0, 1), st.integers(0, 2 ** 31), st.integers(1, 3))
+    def check(n, card, knull, vnull, seed, n_chunks):
+        rng = np.random.default_rng(seed)
+        k = rng.integers(-card, card, n).astype(np.int64)
+        v = rng.integers(-100, 100, n).astype(np.int32)
+        km, vm = rng.random(n) >= knull, rng.random(n) >= vnull
+        cuts = sorted(rng.integers(0, n + 1, n_chunks - 1).tolist()) if n_chunks > 1 else []
+        bounds = [0] + cuts + [n]
+        kch = [Ch(k[a:b], km[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+        vch = [Ch(v[a:b], vm[a:b]) for a, b in zip(bounds[:-1], bounds[1:])]
+        keys, kvalid, out = oracle.group_aggregate(kch, vch)
+        df = pd.DataFrame({"k": pd.array(np.where(km, k, 0), dtype="Int64").astype(object), "v": v.astype(np.int64), "ok": vm})
+        df.loc[~km, "k"] = None
+        df["v_valid"] = df["v"].where(df["ok"])
+        want = df.groupby("k", dropna=False, sort=True).agg(s=("v_valid", "sum"), c=("ok", "sum"), mn=("v_valid", "min"), mx=("v_valid", "max"))
+        assert len(keys) == len(want)
+        got_keys = [int(x) if ok else None for x, ok in zip(keys, kvalid)]
+        valid_keys = [x for x in got_keys if x is not None]
+        assert valid_keys == sorted(valid_keys) and got_keys.count(None) <= 1 and (None not in got_keys or got_keys[-1] is None)
+        rows = {(None if pd.isna(x) else int(x)): r for x, r in zip(want.index, want.itertuples(index=False))}   # pandas' own order is not ours
+        assert set(rows) == set(got_keys)
+        for i, key in enumerate(got_keys):
+            r = rows[key]
+            assert int(out["count"][i]) == int(r.c) and int(out["sum"][i]) == (0 if pd.isna(r.s) else int(r.s))
+            for name, w in (("min", r.mn), ("max", r.mx)):
+                vals, valid = out[name]
+                assert bool(valid[i]) == (not pd.isna(w))
+                if valid[i]:
+                    assert int(vals[i]) == int(w)
+
+    check()
